@@ -1,0 +1,174 @@
+"""Host-side plumbing shared by :class:`tPLS` and :class:`ctPLS`: input
+validation with the reference's error behaviour, engine/communicator caching,
+fetching the fitted state, and the model-side inputs of ``transform``.
+
+All arithmetic on X happens in the CUDA library; what is done here in numpy is
+bookkeeping on replicated, loading-sized arrays (kron of loading vectors, the
+final ``scores @ coef_ @ Q.T`` of predict).
+"""
+
+from __future__ import annotations
+
+from functools import reduce
+
+import numpy as np
+
+from . import _engine
+
+_engines: dict = {}
+_comm_ready: set = set()
+
+
+def _is_torch(a) -> bool:
+    return type(a).__module__.split(".")[0] == "torch"
+
+
+def _device_of(arrays, default=None) -> int:
+    for a in arrays:
+        if _is_torch(a) and a.is_cuda:
+            return a.device.index if a.device.index is not None else 0
+    if default is not None:
+        return int(default)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+def get_engine(device: int) -> _engine.Engine:
+    eng = _engines.get(device)
+    if eng is None or eng.h is None:
+        eng = _engine.Engine(device)
+        _engines[device] = eng
+    return eng
+
+
+def _ensure_comm(eng, group):
+    """Create the NCCL communicator of ``group`` (a torch.distributed process
+    group, or True for the default one) once per engine."""
+    import torch.distributed as dist
+    pg = None if group is True else group
+    world = dist.get_world_size(pg)
+    rank = dist.get_rank(pg)
+    key = (eng.device, id(pg) if pg is not None else 0, world)
+    if key in _comm_ready:
+        return rank, world
+    box = [eng.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(pg, 0) if pg is not None else 0, group=pg)
+    eng.init_comm(box[0], rank, world)
+    _comm_ready.add(key)
+    return rank, world
+
+
+def as_input(a, what):
+    """numpy array or torch tensor, C-contiguous; anything else goes through np.asarray."""
+    if _is_torch(a):
+        return a if a.is_contiguous() else a.contiguous()
+    a = np.asarray(a)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    return np.ascontiguousarray(a)
+
+
+def y_as_f64_2d(Y):
+    """Y as float64 (n, m); a 1-D Y becomes (n, 1) (tpls.py:48-49)."""
+    if _is_torch(Y):
+        import torch
+        Y = Y.to(torch.float64)
+        if Y.ndim == 1:
+            Y = Y.reshape(-1, 1)
+        return Y.contiguous()
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y.reshape(-1, 1)
+    return np.ascontiguousarray(Y)
+
+
+def np_dtype_of(a):
+    return np.dtype(str(a.dtype).replace("torch.", ""))
+
+
+def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwrite=False, flags=0):
+    """Upload (or adopt) the shards, run the device fit, fetch the state.
+
+    Returns a dict with T, W (list per tensor of loading matrices), U, Q, coef,
+    R2X (list), R2Y, X_mean (list), Y_mean, has_miss (list), trips, stats.
+    """
+    Xs = [as_input(X, "X") for X in Xs]
+    Y2 = y_as_f64_2d(Y)
+    dev = _device_of(Xs + [Y2], device)
+    eng = get_engine(dev)
+    if group is not None and group is not False:
+        _ensure_comm(eng, group)
+    n, m = int(Y2.shape[0]), int(Y2.shape[1])
+    R = int(n_components)
+    for i, X in enumerate(Xs):
+        fl = _engine.X_MAY_OVERWRITE if (overwrite and _is_torch(X) and X.is_cuda) else 0
+        eng.set_x(i, X, fl)
+    eng.set_y(Y2)
+    try:
+        eng.fit(len(Xs), R, tol, max_iter, flags)
+        out = dict(
+            T=eng.x_factor(0, 0, n, R),
+            W=[[eng.x_factor(i, k, int(X.shape[k]), R) for k in range(1, X.ndim)] for i, X in enumerate(Xs)],
+            U=eng.y_factor(0, n, R),
+            Q=eng.y_factor(1, m, R),
+            coef=eng.coef(R),
+            R2X=[eng.r2x(i, R) for i in range(len(Xs))],
+            R2Y=eng.r2y(R),
+            X_mean=[eng.x_mean(i, tuple(int(s) for s in X.shape[1:]), np_dtype_of(X)) for i, X in enumerate(Xs)],
+            Y_mean=eng.y_mean(m),
+            has_miss=[eng.has_missing(i) for i in range(len(Xs))],
+            trips=eng.trips(R),
+            stats=eng.stats(),
+            device=dev,
+        )
+    finally:
+        eng.release_data()
+    return out
+
+
+def kron_rows(loadings, R):
+    """(R, P) matrix whose row a is kron(w_2[:, a], w_3[:, a], ...)."""
+    return np.ascontiguousarray(np.stack([reduce(np.kron, [w[:, a] for w in loadings]) for a in range(R)]))
+
+
+def run_transform(Xs, means, loadings_per_tensor, R, device=None):
+    """Scores (n_new, R) of new data through the stored loadings."""
+    Xs = [as_input(X, "X") for X in Xs]
+    dev = _device_of(Xs, device)
+    eng = get_engine(dev)
+    wk = [kron_rows(ws, R) for ws in loadings_per_tensor]
+    mm = [np.ascontiguousarray(np.asarray(mu, dtype=np_dtype_of(X)).reshape(-1)) for mu, X in zip(means, Xs)]
+    return eng.transform(Xs, mm, wk)
+
+
+def y_scores(Y, Y_mean, Y_shape, X_scores, coef, Q):
+    """The Y branch of transform (tpls.py:167-184): small, replicated, host-side."""
+    if _is_torch(Y):
+        Y = Y.detach().cpu().numpy()
+    Y = np.array(Y, dtype=np.float64, copy=True)
+    if (Y.ndim != 1) and (Y.ndim != 2):
+        raise ValueError("Only a matrix (2-mode tensor) Y is allowed.")
+    if Y.ndim == 1:
+        Y = Y.reshape((-1, 1))
+    if tuple(Y_shape[1:]) != tuple(Y.shape[1:]):
+        raise ValueError(f"Training Y has shape {tuple(Y_shape)}, while the new Y has shape {Y.shape}")
+    Y -= Y_mean
+    R = X_scores.shape[1]
+    out = np.zeros((Y.shape[0], R))
+    for a in range(R):
+        out[:, a] = Y @ Q[:, a]
+        Y -= X_scores @ coef[:, [a]] @ Q[:, [a]].T
+    return out
+
+
+def rank_r_dense(factors):
+    """sum_r a_r o b_r o ... (util.py:18-20) -- used only by X_reconstructed."""
+    rest = np.ones((1, factors[0].shape[1]))
+    for f in factors[1:]:
+        rest = (rest[:, None, :] * f[None, :, :]).reshape(-1, f.shape[1])
+    return (factors[0] @ rest.T).reshape([f.shape[0] for f in factors])

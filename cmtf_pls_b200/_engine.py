@@ -1,0 +1,232 @@
+"""ctypes binding of the C ABI in include/tpls_b200.h.
+
+The shared library ``libtpls_b200.so`` is built in-tree by
+``cmtf_pls_b200/csrc/Makefile`` (``__graft_entry__.build()``).  There is no CPU
+fallback: if the library is missing, or no sm_100 device is visible, using the
+estimators raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtpls_b200.so")
+
+F32, F64 = 0, 1
+X_MAY_OVERWRITE = 1
+FIT_NORMALIZE_ON_BREAK = 1
+MAX_TENSORS = 8
+MAX_MODES = 8
+
+_lib = None
+
+
+class TplsError(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("fit_ms", C.c_double),
+        ("alg_bytes", C.c_double),
+        ("streamed_bytes", C.c_double),
+        ("kernel_launches", C.c_int64),
+        ("total_trips", C.c_int64),
+        ("collectives", C.c_int64),
+        ("h2d_bytes", C.c_double),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/tpls_b200.h
+_H = C.c_void_p
+_P = C.c_void_p
+SIGNATURES = {
+    "tpls_version": (C.c_int, []),
+    "tpls_last_error": (C.c_char_p, [_H]),
+    "tpls_create": (C.c_int, [C.POINTER(_H), C.c_int, _P]),
+    "tpls_destroy": (C.c_int, [_H]),
+    "tpls_comm_unique_id": (C.c_int, [_P]),
+    "tpls_comm_init": (C.c_int, [_H, _P, C.c_int, C.c_int]),
+    "tpls_set_x": (C.c_int, [_H, C.c_int, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "tpls_set_y": (C.c_int, [_H, _P, C.c_int64, C.c_int64]),
+    "tpls_fit": (C.c_int, [_H, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]),
+    "tpls_get_x_factor": (C.c_int, [_H, C.c_int, C.c_int, _P]),
+    "tpls_get_y_factor": (C.c_int, [_H, C.c_int, _P]),
+    "tpls_get_coef": (C.c_int, [_H, _P]),
+    "tpls_get_r2x": (C.c_int, [_H, C.c_int, _P]),
+    "tpls_get_r2y": (C.c_int, [_H, _P]),
+    "tpls_get_x_mean": (C.c_int, [_H, C.c_int, _P]),
+    "tpls_get_y_mean": (C.c_int, [_H, _P]),
+    "tpls_get_has_missing": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int)]),
+    "tpls_get_trips": (C.c_int, [_H, _P]),
+    "tpls_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
+    "tpls_release_data": (C.c_int, [_H]),
+    "tpls_transform": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(C.c_int), C.c_int64,
+                                 C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P]),
+    "tpls_op_contract": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P, C.POINTER(C.c_float), C.c_int]),
+    "tpls_op_project": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P, C.POINTER(C.c_float), C.c_int]),
+    "tpls_op_deflate_contract": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, C.c_int, _P, _P,
+                                           C.POINTER(C.c_float), C.c_int]),
+    "tpls_op_rank1": (C.c_int, [_H, _P, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_int, _P, _P, C.POINTER(C.c_int),
+                                C.POINTER(C.c_float), C.c_int]),
+}
+
+
+def load_library(path: str | None = None):
+    """dlopen the C-ABI library and bind every declared symbol (no GPU needed)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise TplsError(
+            f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C cmtf_pls_b200/csrc).  cmtf_pls_b200 has no CPU fallback.")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a) -> int:
+    """Raw address of a numpy array (host) or torch tensor (host or CUDA)."""
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a.data_ptr())
+
+
+def dtype_code(a) -> int:
+    name = str(a.dtype).replace("torch.", "")
+    if name == "float32":
+        return F32
+    if name == "float64":
+        return F64
+    raise TypeError(f"X must be float32 or float64, got {a.dtype}")
+
+
+class Engine:
+    """One fit context (``tpls_handle``) on one CUDA device."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        self.h = _H()
+        rc = self.lib.tpls_create(C.byref(self.h), int(device), C.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise TplsError(self.lib.tpls_last_error(None).decode())
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.tpls_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TplsError(self.lib.tpls_last_error(self.h).decode())
+
+    # ---- multi-GPU ----
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.lib.tpls_comm_unique_id(buf) != 0:
+            raise TplsError(self.lib.tpls_last_error(None).decode())
+        return buf.raw
+
+    def init_comm(self, uid: bytes, rank: int, world: int):
+        self._ck(self.lib.tpls_comm_init(self.h, C.c_char_p(uid), rank, world))
+
+    # ---- data ----
+    def set_x(self, index, x, flags=0):
+        shape = (C.c_int64 * len(x.shape))(*[int(s) for s in x.shape])
+        self._keep.append(x)
+        self._ck(self.lib.tpls_set_x(self.h, index, _ptr(x), dtype_code(x), len(x.shape), shape, flags))
+
+    def set_y(self, y):
+        self._keep.append(y)
+        self._ck(self.lib.tpls_set_y(self.h, _ptr(y), int(y.shape[0]), int(y.shape[1])))
+
+    def fit(self, n_tensors, n_components, tol, max_iter, flags=0):
+        self._ck(self.lib.tpls_fit(self.h, n_tensors, n_components, float(tol), int(max_iter), flags))
+        self._keep.clear()
+
+    # ---- results ----
+    def x_factor(self, index, mode, rows, R):
+        out = np.empty((rows, R), dtype=np.float64)
+        self._ck(self.lib.tpls_get_x_factor(self.h, index, mode, out.ctypes.data))
+        return out
+
+    def y_factor(self, which, rows, R):
+        out = np.empty((rows, R), dtype=np.float64)
+        self._ck(self.lib.tpls_get_y_factor(self.h, which, out.ctypes.data))
+        return out
+
+    def coef(self, R):
+        out = np.empty((R, R), dtype=np.float64)
+        self._ck(self.lib.tpls_get_coef(self.h, out.ctypes.data))
+        return out
+
+    def r2x(self, index, R):
+        out = np.empty(R, dtype=np.float64)
+        self._ck(self.lib.tpls_get_r2x(self.h, index, out.ctypes.data))
+        return out
+
+    def r2y(self, R):
+        out = np.empty(R, dtype=np.float64)
+        self._ck(self.lib.tpls_get_r2y(self.h, out.ctypes.data))
+        return out
+
+    def x_mean(self, index, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        self._ck(self.lib.tpls_get_x_mean(self.h, index, out.ctypes.data))
+        return out
+
+    def y_mean(self, m):
+        out = np.empty(m, dtype=np.float64)
+        self._ck(self.lib.tpls_get_y_mean(self.h, out.ctypes.data))
+        return out
+
+    def has_missing(self, index) -> bool:
+        v = C.c_int(0)
+        self._ck(self.lib.tpls_get_has_missing(self.h, index, C.byref(v)))
+        return bool(v.value)
+
+    def trips(self, R):
+        out = np.empty(R, dtype=np.int32)
+        self._ck(self.lib.tpls_get_trips(self.h, out.ctypes.data))
+        return out
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self.lib.tpls_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def release_data(self):
+        self._ck(self.lib.tpls_release_data(self.h))
+
+    def transform(self, xs, means, wkrons):
+        """xs[l]: (n_new, ...) array/tensor; means[l]: numpy, X's dtype; wkrons[l]: (R, P) float64 numpy."""
+        L = len(xs)
+        n_new = int(xs[0].shape[0])
+        R = int(wkrons[0].shape[0])
+        xp = (_P * L)(*[_ptr(x) for x in xs])
+        dt = (C.c_int * L)(*[dtype_code(x) for x in xs])
+        ps = (C.c_int64 * L)(*[int(w.shape[1]) for w in wkrons])
+        mp = (_P * L)(*[_ptr(m) for m in means])
+        wp = (_P * L)(*[_ptr(w) for w in wkrons])
+        out = np.empty((n_new, R), dtype=np.float64)
+        self._ck(self.lib.tpls_transform(self.h, L, R, xp, dt, n_new, ps, mp, wp, out.ctypes.data))
+        return out

@@ -1,0 +1,1184 @@
+// Host side of the C ABI (include/tpls_b200.h): device state of one fit, the
+// NIPALS driver that enqueues the passes, and NCCL all-reduces of the small
+// replicated quantities.  No CPU arithmetic on the data path.
+#include "../../include/tpls_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "nccl_dl.h"
+#include "passes.cuh"
+#include "rank1.cuh"
+#include "small.cuh"
+
+using namespace tpls;
+
+namespace {
+
+std::string g_error;
+NcclApi g_nccl;
+
+struct Tensor {
+    bool set = false;
+    int dtype = 0, elem = 4, ndim = 0;
+    long long shape[TPLS_MAX_MODES] = {0};
+    long long n = 0;
+    int p = 0, pitch = 0;
+    const void* src = nullptr;  // centred from here ...
+    void* work = nullptr;       // ... into here (may alias src)
+    void* owned = nullptr;      // library-owned staging / work allocation(s)
+    void* owned2 = nullptr;
+    bool masked = false;
+    PassGeom g{};
+    // per-fit device buffers
+    double *zpart = nullptr, *cntpart = nullptr, *sspart = nullptr;
+    double *mean_d = nullptr, *wkron = nullptr, *tpart = nullptr, *cpart = nullptr, *r1_scratch = nullptr;
+    void* mean_native = nullptr;
+    double* W[TPLS_MAX_MODES] = {nullptr};
+    int* miss_flag = nullptr;
+    int* sweeps = nullptr;
+    size_t r1_ws = 0;
+    int r1_nmax = 1;
+    // arena offsets (doubles)
+    size_t off_colsum = 0, off_colcnt = 0, off_z = 0, off_ss = 0;
+};
+
+}  // namespace
+
+struct tpls_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string error;
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    // data
+    Tensor x[TPLS_MAX_TENSORS];
+    long long n = 0;
+    int m = 0, pitch_y = 0;
+    double *y_src = nullptr, *y_work = nullptr;
+    PassGeom gy{};
+    double h2d_bytes = 0;
+    // fit state
+    int L = 0, R = 0;
+    bool fitted = false;
+    std::vector<void*> fit_allocs;
+    double *T = nullptr, *U = nullptr, *Q = nullptr, *coef = nullptr, *gram = nullptr;
+    double *arena = nullptr, *qvec = nullptr, *svec = nullptr, *ymean_d = nullptr;
+    double *zpart_y = nullptr, *cntpart_y = nullptr, *sspart_y = nullptr, *d2part = nullptr, *dotpart = nullptr;
+    double* scratch_ss = nullptr;
+    int* trips_dev = nullptr;
+    int* ymiss_flag = nullptr;
+    Ctrl* ctrl = nullptr;
+    int* h_done = nullptr;  // pinned
+    size_t arena_doubles = 0, off_ysum = 0, off_ycnt = 0, off_n = 0, off_stats_end = 0, off_zcat = 0, zcat_len = 0,
+           off_q = 0, off_d2 = 0, off_dots = 0, off_ss = 0, ss_len = 0;
+    std::vector<double> r2x[TPLS_MAX_TENSORS];
+    std::vector<double> r2y;
+    std::vector<int> trips;
+    double n_total = 0;
+    tpls_stats stats{};
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_trip[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int fail(tpls_handle h, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h)
+        h->error = buf;
+    else
+        g_error = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(h, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));        \
+    } while (0)
+
+#define CKN(call)                                                                                        \
+    do {                                                                                                 \
+        int r__ = (call);                                                                                \
+        if (r__ != 0) return fail(h, "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+#define TRY(call)                  \
+    do {                           \
+        int r__ = (call);          \
+        if (r__ != 0) return r__;  \
+    } while (0)
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int dev_alloc(tpls_handle h, void** out, size_t bytes, std::vector<void*>* track) {
+    *out = nullptr;
+    CK(cudaMalloc(out, std::max<size_t>(bytes, 16)));
+    if (track) track->push_back(*out);
+    return 0;
+}
+
+void free_fit(tpls_handle h) {
+    for (void* p : h->fit_allocs) cudaFree(p);
+    h->fit_allocs.clear();
+    h->fitted = false;
+}
+
+void free_tensor(Tensor& t) {
+    if (t.owned) cudaFree(t.owned);
+    if (t.owned2) cudaFree(t.owned2);
+    t = Tensor();
+}
+
+int allreduce(tpls_handle h, double* buf, size_t count) {
+    if (h->world <= 1 || count == 0) return 0;
+    CKN(g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream));
+    h->stats.collectives++;
+    return 0;
+}
+
+// ---- pass wrappers that keep the launch / byte counters ----
+int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a) {
+    CK(launch_colpass(dtype, masked, flags, a, h->stream));
+    h->stats.kernel_launches++;
+    const double bytes = (double)a.g.n_rows * a.g.pitch * a.g.elem_size;
+    h->stats.streamed_bytes += bytes * ((flags & PF_WRITE) ? 2.0 : 1.0);
+    return 0;
+}
+
+int row_pass(tpls_handle h, int dtype, bool masked, RowPassArgs& a) {
+    CK(launch_rowpass(dtype, masked, a, h->stream));
+    h->stats.kernel_launches++;
+    h->stats.streamed_bytes += (double)a.g.n_rows * a.g.pitch * a.g.elem_size;
+    if (a.g.n_slabs > 1) {
+        RowFinishArgs f{};
+        f.n_rows = a.g.n_rows;
+        f.n_slabs = a.g.n_slabs;
+        f.tpart = a.tpart;
+        f.cpart = masked ? a.cpart : nullptr;
+        f.p_total = (double)a.g.p;
+        f.t_out = a.t_out;
+        f.epi = a.epi;
+        f.div = a.div;
+        f.d2part = a.d2part;
+        f.ctrl = a.ctrl;
+        f.trip = a.trip;
+        CK(launch_row_finish(f, nullptr, h->stream));
+        h->stats.kernel_launches++;
+    }
+    return 0;
+}
+
+int reduce_cols(tpls_handle h, const double* part, double* out, int n_cols, int stride, int n_parts,
+                const double* sspart, double* ss_out, int n_ss, const Ctrl* ctrl, int trip) {
+    ReduceArgs r{};
+    r.part = part;
+    r.out = out;
+    r.n_cols = n_cols;
+    r.stride = stride;
+    r.n_parts = n_parts;
+    r.sspart = sspart;
+    r.ss_out = ss_out;
+    r.n_ss = n_ss;
+    r.ctrl = ctrl;
+    r.trip = trip;
+    CK(launch_reduce_cols(r, h->stream));
+    h->stats.kernel_launches++;
+    return 0;
+}
+
+int d2_grid(const PassGeom& g) { return g.n_slabs > 1 ? row_finish_grid(g.n_rows) : g.grid_x; }
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int tpls_version(void) { return 100; }
+
+const char* tpls_last_error(tpls_handle h) { return h ? h->error.c_str() : g_error.c_str(); }
+
+int tpls_create(tpls_handle* out, int device, void* cuda_stream) {
+    tpls_handle h = nullptr;
+    if (!out) return fail(nullptr, "tpls_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, "tpls_create: no CUDA device is visible (this library has no CPU path)");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, "tpls_create: device %d out of range (%d visible)", device, count);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, "tpls_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major,
+                    prop.minor);
+    h = new tpls_ctx();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    cudaSetDevice(device);
+    if (cuda_stream) {
+        h->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete h;
+            return fail(nullptr, "cudaStreamCreate failed");
+        }
+        h->own_stream = true;
+    }
+    cudaEventCreate(&h->ev_start);
+    cudaEventCreate(&h->ev_stop);
+    for (auto& e : h->ev_trip) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaMallocHost((void**)&h->h_done, sizeof(int) * 4096);
+    *out = h;
+    return 0;
+}
+
+int tpls_destroy(tpls_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_fit(h);
+    for (auto& t : h->x) free_tensor(t);
+    if (h->y_src) cudaFree(h->y_src);
+    if (h->y_work) cudaFree(h->y_work);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
+    if (h->h_done) cudaFreeHost(h->h_done);
+    cudaEventDestroy(h->ev_start);
+    cudaEventDestroy(h->ev_stop);
+    for (auto& e : h->ev_trip) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int tpls_comm_unique_id(void* id128) {
+    const char* why = "";
+    if (!g_nccl.load(&why)) return fail(nullptr, "tpls_comm_unique_id: %s", why);
+    NcclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, "ncclGetUniqueId -> %s", g_nccl.GetErrorString(r));
+    memcpy(id128, &id, sizeof id);
+    return 0;
+}
+
+int tpls_comm_init(tpls_handle h, const void* id128, int rank, int world) {
+    if (!h) return fail(nullptr, "NULL handle");
+    if (world <= 1) {
+        h->rank = 0;
+        h->world = 1;
+        return 0;
+    }
+    const char* why = "";
+    if (!g_nccl.load(&why)) return fail(h, "tpls_comm_init: %s", why);
+    CK(cudaSetDevice(h->device));
+    NcclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    CKN(g_nccl.CommInitRank(&h->comm, world, id, rank));
+    h->rank = rank;
+    h->world = world;
+    return 0;
+}
+
+int tpls_set_x(tpls_handle h, int index, const void* x, int dtype, int ndim, const int64_t* shape, int flags) {
+    if (!h) return fail(nullptr, "NULL handle");
+    if (index < 0 || index >= TPLS_MAX_TENSORS) return fail(h, "tpls_set_x: index %d out of range", index);
+    if (ndim < 2 || ndim > TPLS_MAX_MODES) return fail(h, "tpls_set_x: X must have 2..%d modes, got %d", TPLS_MAX_MODES, ndim);
+    if (dtype != TPLS_F32 && dtype != TPLS_F64) return fail(h, "tpls_set_x: dtype must be TPLS_F32 or TPLS_F64");
+    CK(cudaSetDevice(h->device));
+    Tensor& t = h->x[index];
+    free_tensor(t);
+    t.dtype = dtype;
+    t.elem = dtype == TPLS_F32 ? 4 : 8;
+    t.ndim = ndim;
+    long long p = 1;
+    for (int k = 0; k < ndim; ++k) {
+        if (shape[k] <= 0) return fail(h, "tpls_set_x: empty mode %d", k);
+        t.shape[k] = shape[k];
+        if (k) p *= shape[k];
+    }
+    if (p > (1ll << 30)) return fail(h, "tpls_set_x: trailing size %lld too large", p);
+    t.n = shape[0];
+    t.p = (int)p;
+    const int vec = 16 / t.elem;
+    t.pitch = (int)((p + vec - 1) / vec * vec);
+    const size_t bytes = (size_t)t.n * t.pitch * t.elem;
+    const bool dev = is_device_ptr(x);
+    if (dev && t.pitch == t.p && ((uintptr_t)x % 16 == 0)) {
+        t.src = x;
+        if (flags & TPLS_X_MAY_OVERWRITE) {
+            t.work = const_cast<void*>(x);
+        } else {
+            TRY(dev_alloc(h, &t.owned, bytes, nullptr));
+            t.work = t.owned;
+        }
+    } else {
+        TRY(dev_alloc(h, &t.owned, bytes, nullptr));
+        if (t.pitch != t.p) CK(cudaMemsetAsync(t.owned, 0, bytes, h->stream));
+        CK(cudaMemcpy2DAsync(t.owned, (size_t)t.pitch * t.elem, x, (size_t)t.p * t.elem, (size_t)t.p * t.elem, t.n,
+                             cudaMemcpyDefault, h->stream));
+        if (!dev) h->h2d_bytes += (double)t.n * t.p * t.elem;
+        t.src = t.owned;
+        t.work = t.owned;
+    }
+    t.set = true;
+    h->fitted = false;
+    return 0;
+}
+
+int tpls_set_y(tpls_handle h, const double* y, int64_t n, int64_t m) {
+    if (!h) return fail(nullptr, "NULL handle");
+    if (n <= 0 || m <= 0) return fail(h, "tpls_set_y: empty Y");
+    CK(cudaSetDevice(h->device));
+    if (h->y_src) cudaFree(h->y_src);
+    if (h->y_work) cudaFree(h->y_work);
+    h->y_src = h->y_work = nullptr;
+    h->n = n;
+    h->m = (int)m;
+    h->pitch_y = (int)((m + 1) / 2 * 2);
+    const size_t bytes = (size_t)n * h->pitch_y * sizeof(double);
+    CK(cudaMalloc((void**)&h->y_src, bytes));
+    CK(cudaMalloc((void**)&h->y_work, bytes));
+    if (h->pitch_y != m) CK(cudaMemsetAsync(h->y_src, 0, bytes, h->stream));
+    CK(cudaMemcpy2DAsync(h->y_src, (size_t)h->pitch_y * 8, y, (size_t)m * 8, (size_t)m * 8, n, cudaMemcpyDefault,
+                         h->stream));
+    if (!is_device_ptr(y)) h->h2d_bytes += (double)n * m * 8;
+    h->fitted = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// fit
+// ---------------------------------------------------------------------------
+static int alloc_fit(tpls_handle h, int L, int R) {
+    free_fit(h);
+    auto* tr = &h->fit_allocs;
+    const long long n = h->n;
+    h->L = L;
+    h->R = R;
+    h->gy = make_geom(n, h->m, h->pitch_y, 8, h->sm_count);
+    // arena layout
+    size_t off = 0;
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        t.g = make_geom(n, t.p, t.pitch, t.elem, h->sm_count);
+        t.off_colsum = off;
+        off += t.pitch;
+        t.off_colcnt = off;
+        off += t.pitch;
+    }
+    h->off_ysum = off;
+    off += h->pitch_y;
+    h->off_ycnt = off;
+    off += h->pitch_y;
+    h->off_n = off;
+    off += 1;
+    h->off_stats_end = off;
+    off = (off + 1) / 2 * 2;
+    h->off_zcat = off;
+    for (int l = 0; l < L; ++l) {
+        h->x[l].off_z = off;
+        off += h->x[l].pitch;
+    }
+    h->zcat_len = off - h->off_zcat;
+    h->off_q = off;
+    off += h->pitch_y;
+    h->off_d2 = off;
+    off += 2;
+    h->off_dots = off;
+    off += 64;
+    h->off_ss = off;
+    for (int l = 0; l < L; ++l) {
+        h->x[l].off_ss = off;
+        off += R + 1;
+    }
+    off += R + 1;  // Y
+    h->ss_len = off - h->off_ss;
+    h->arena_doubles = off;
+    TRY(dev_alloc(h, (void**)&h->arena, off * sizeof(double), tr));
+    CK(cudaMemsetAsync(h->arena, 0, off * sizeof(double), h->stream));
+
+    TRY(dev_alloc(h, (void**)&h->T, sizeof(double) * n * R, tr));
+    TRY(dev_alloc(h, (void**)&h->U, sizeof(double) * n * R, tr));
+    TRY(dev_alloc(h, (void**)&h->Q, sizeof(double) * h->m * R, tr));
+    TRY(dev_alloc(h, (void**)&h->coef, sizeof(double) * R * R, tr));
+    TRY(dev_alloc(h, (void**)&h->gram, sizeof(double) * R * R, tr));
+    TRY(dev_alloc(h, (void**)&h->qvec, sizeof(double) * h->pitch_y, tr));
+    TRY(dev_alloc(h, (void**)&h->svec, sizeof(double) * n, tr));
+    TRY(dev_alloc(h, (void**)&h->ymean_d, sizeof(double) * h->pitch_y, tr));
+    TRY(dev_alloc(h, (void**)&h->zpart_y, sizeof(double) * h->gy.grid_x * h->pitch_y, tr));
+    TRY(dev_alloc(h, (void**)&h->cntpart_y, sizeof(double) * h->gy.grid_x * h->pitch_y, tr));
+    TRY(dev_alloc(h, (void**)&h->sspart_y, sizeof(double) * h->gy.grid_x * h->gy.n_slabs, tr));
+    TRY(dev_alloc(h, (void**)&h->d2part, sizeof(double) * 2048, tr));
+    TRY(dev_alloc(h, (void**)&h->dotpart, sizeof(double) * 148 * 64, tr));
+    TRY(dev_alloc(h, (void**)&h->scratch_ss, sizeof(double) * 8, tr));
+    TRY(dev_alloc(h, (void**)&h->trips_dev, sizeof(int) * R, tr));
+    TRY(dev_alloc(h, (void**)&h->ymiss_flag, sizeof(int) * 4, tr));
+    TRY(dev_alloc(h, (void**)&h->ctrl, sizeof(Ctrl), tr));
+    CK(cudaMemsetAsync(h->T, 0, sizeof(double) * n * R, h->stream));
+    CK(cudaMemsetAsync(h->U, 0, sizeof(double) * n * R, h->stream));
+    CK(cudaMemsetAsync(h->Q, 0, sizeof(double) * h->m * R, h->stream));
+    CK(cudaMemsetAsync(h->coef, 0, sizeof(double) * R * R, h->stream));
+    CK(cudaMemsetAsync(h->gram, 0, sizeof(double) * R * R, h->stream));
+    CK(cudaMemsetAsync(h->trips_dev, 0, sizeof(int) * R, h->stream));
+    CK(cudaMemsetAsync(h->ymiss_flag, 0, sizeof(int) * 4, h->stream));
+
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        const size_t gp = (size_t)t.g.grid_x * t.pitch;
+        TRY(dev_alloc(h, (void**)&t.zpart, sizeof(double) * gp, tr));
+        TRY(dev_alloc(h, (void**)&t.cntpart, sizeof(double) * gp, tr));
+        TRY(dev_alloc(h, (void**)&t.sspart, sizeof(double) * t.g.grid_x * t.g.n_slabs, tr));
+        TRY(dev_alloc(h, (void**)&t.mean_d, sizeof(double) * t.pitch, tr));
+        TRY(dev_alloc(h, &t.mean_native, (size_t)t.elem * t.pitch, tr));
+        TRY(dev_alloc(h, (void**)&t.wkron, sizeof(double) * t.pitch * R, tr));
+        CK(cudaMemsetAsync(t.wkron, 0, sizeof(double) * t.pitch * R, h->stream));
+        if (t.g.n_slabs > 1) {
+            TRY(dev_alloc(h, (void**)&t.tpart, sizeof(double) * n * t.g.n_slabs, tr));
+            TRY(dev_alloc(h, (void**)&t.cpart, sizeof(double) * n * t.g.n_slabs, tr));
+        }
+        for (int k = 1; k < t.ndim; ++k) {
+            TRY(dev_alloc(h, (void**)&t.W[k], sizeof(double) * t.shape[k] * R, tr));
+            CK(cudaMemsetAsync(t.W[k], 0, sizeof(double) * t.shape[k] * R, h->stream));
+        }
+        TRY(dev_alloc(h, (void**)&t.miss_flag, sizeof(int) * 4, tr));
+        CK(cudaMemsetAsync(t.miss_flag, 0, sizeof(int) * 4, h->stream));
+        TRY(dev_alloc(h, (void**)&t.sweeps, sizeof(int) * 4, tr));
+        int dims[kMaxZModes];
+        for (int k = 1; k < t.ndim; ++k) dims[k - 1] = (int)t.shape[k];
+        t.r1_ws = rank1_workspace_doubles(t.ndim - 1, dims, &t.r1_nmax);
+        TRY(dev_alloc(h, (void**)&t.r1_scratch, sizeof(double) * t.r1_ws, tr));
+    }
+    return 0;
+}
+
+static void fill_rank1_task(tpls_handle h, Tensor& t, int a, Rank1Task& k, bool use_smem) {
+    k.z = h->arena + t.off_z;
+    k.colcnt = t.masked ? h->arena + t.off_colcnt : nullptr;
+    k.n_total = h->n_total;
+    k.p = t.p;
+    k.pitch = t.pitch;
+    k.nmodes = t.ndim - 1;
+    for (int m = 1; m < t.ndim; ++m) {
+        k.dims[m - 1] = (int)t.shape[m];
+        k.w[m - 1] = t.W[m] + (size_t)a * t.shape[m];
+    }
+    k.wkron = t.wkron + (size_t)a * t.pitch;
+    k.scratch = t.r1_scratch;
+    k.use_smem = use_smem ? 1 : 0;
+    k.nmax = t.r1_nmax;
+    k.sweeps = t.sweeps;
+}
+
+int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max_iter, int flags) {
+    if (!h) return fail(nullptr, "NULL handle");
+    const int L = n_tensors, R = n_components;
+    if (L < 1 || L > TPLS_MAX_TENSORS) return fail(h, "tpls_fit: n_tensors must be 1..%d", TPLS_MAX_TENSORS);
+    if (R < 1 || R > 32) return fail(h, "tpls_fit: n_components must be 1..32");
+    if (max_iter < 1 || max_iter > 4096) return fail(h, "tpls_fit: max_iter must be 1..4096");
+    if (!h->y_src) return fail(h, "tpls_fit: Y not set");
+    for (int l = 0; l < L; ++l) {
+        if (!h->x[l].set) return fail(h, "tpls_fit: X[%d] not set", l);
+        if (h->x[l].n != h->n)
+            return fail(h, "tpls_fit: X[%d] has %lld samples, Y has %lld", l, h->x[l].n, h->n);
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const double h2d = h->h2d_bytes;
+    h->stats = tpls_stats{};
+    h->stats.h2d_bytes = h2d;
+    h->h2d_bytes = 0;
+    TRY(alloc_fit(h, L, R));
+    CK(cudaEventRecord(h->ev_start, st));
+    const long long n = h->n;
+    double* A = h->arena;
+
+    // ---- column statistics (np.nanmean, tpls.py:66-67) ----
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        ColPassArgs c{};
+        c.g = t.g;
+        c.x_in = t.src;
+        c.zpart = t.zpart;
+        c.cntpart = t.cntpart;
+        TRY(col_pass(h, t.dtype, true, PF_COLSTAT, c));
+        TRY(reduce_cols(h, t.zpart, A + t.off_colsum, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, nullptr, 0));
+        TRY(reduce_cols(h, t.cntpart, A + t.off_colcnt, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, nullptr, 0));
+    }
+    {
+        ColPassArgs c{};
+        c.g = h->gy;
+        c.x_in = h->y_src;
+        c.zpart = h->zpart_y;
+        c.cntpart = h->cntpart_y;
+        TRY(col_pass(h, TPLS_F64, true, PF_COLSTAT, c));
+        TRY(reduce_cols(h, h->zpart_y, A + h->off_ysum, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, nullptr, 0));
+        TRY(reduce_cols(h, h->cntpart_y, A + h->off_ycnt, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, nullptr, 0));
+        CK(launch_fill(A + h->off_n, 1, (double)n, st));
+        h->stats.kernel_launches++;
+    }
+    TRY(allreduce(h, A, h->off_stats_end));
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        CK(launch_finalize_mean(t.dtype, A + t.off_colsum, A + t.off_colcnt, A + h->off_n, t.p, t.pitch, t.mean_d,
+                                t.mean_native, t.miss_flag, st));
+        h->stats.kernel_launches++;
+    }
+    CK(launch_finalize_mean(TPLS_F64, A + h->off_ysum, A + h->off_ycnt, A + h->off_n, h->m, h->pitch_y, h->ymean_d,
+                            nullptr, h->ymiss_flag, st));
+    h->stats.kernel_launches++;
+    {
+        int flagsh[TPLS_MAX_TENSORS] = {0};
+        for (int l = 0; l < L; ++l)
+            CK(cudaMemcpyAsync(&flagsh[l], h->x[l].miss_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h->n_total, A + h->off_n, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int l = 0; l < L; ++l) h->x[l].masked = flagsh[l] != 0;
+    }
+
+    // ---- centre Y (tpls.py:71), u0 = first column (tpls.py:78) ----
+    double* ss_y = A + h->off_ss + (size_t)L * (R + 1);
+    {
+        ColPassArgs c{};
+        c.g = h->gy;
+        c.x_in = h->y_src;
+        c.x_out = h->y_work;
+        c.col_w = h->ymean_d;
+        c.sspart = h->sspart_y;
+        TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c));
+        TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
+        CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U, st));
+        h->stats.kernel_launches++;
+    }
+    // ---- centre X fused with the first contraction ----
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        ColPassArgs c{};
+        c.g = t.g;
+        c.x_in = t.src;
+        c.x_out = t.work;
+        c.col_w = t.mean_d;
+        c.row_u = h->U;
+        c.zpart = t.zpart;
+        c.sspart = t.sspart;
+        TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ, c));
+        TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, t.sspart, A + t.off_ss,
+                        t.g.grid_x * t.g.n_slabs, nullptr, 0));
+    }
+
+    // rank-1 launch configuration
+    size_t r1_smem = 0;
+    bool r1_use_smem = true;
+    for (int l = 0; l < L; ++l) r1_smem = std::max(r1_smem, h->x[l].r1_ws * sizeof(double));
+    if (r1_smem > 200 * 1024) {
+        r1_use_smem = false;
+        r1_smem = 0;
+    }
+
+    const int LOOK = 1;
+    for (int a = 0; a < R; ++a) {
+        double* Ta = h->T + (size_t)a * n;
+        double* Ua = h->U + (size_t)a * n;
+        CK(launch_reset_ctrl(h->ctrl, st));
+        h->stats.kernel_launches++;
+        for (int trip = 0; trip < max_iter; ++trip) {
+            if (trip >= 1 + LOOK) {
+                const int back = trip - 1 - LOOK;
+                CK(cudaEventSynchronize(h->ev_trip[back & 3]));
+                if (h->h_done[back] >= 0) break;
+            }
+            // K1: Z = X x_1 u (trip 0 got it from the fused centring / deflation pass)
+            if (trip > 0) {
+                for (int l = 0; l < L; ++l) {
+                    Tensor& t = h->x[l];
+                    ColPassArgs c{};
+                    c.g = t.g;
+                    c.x_in = t.work;
+                    c.row_u = Ua;
+                    c.zpart = t.zpart;
+                    c.ctrl = h->ctrl;
+                    c.trip = trip;
+                    TRY(col_pass(h, t.dtype, t.masked, PF_CONTRACT, c));
+                    TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
+                }
+            }
+            TRY(allreduce(h, A + h->off_zcat, h->zcat_len));
+            // K3: rank-1 weight vectors, one CTA per tensor
+            {
+                Rank1Args ra{};
+                ra.n_tasks = L;
+                ra.tol = tol;
+                ra.normalize_on_break = (flags & TPLS_FIT_NORMALIZE_ON_BREAK) ? 1 : 0;
+                ra.ctrl = h->ctrl;
+                ra.trip = trip;
+                for (int l = 0; l < L; ++l) fill_rank1_task(h, h->x[l], a, ra.t[l], r1_use_smem);
+                CK(launch_rank1(ra, r1_smem, st));
+                h->stats.kernel_launches++;
+            }
+            // K2: t = X x_2 w2 x_3 w3 ..., averaged over the coupled tensors (cmtf.py:120)
+            for (int l = 0; l < L; ++l) {
+                Tensor& t = h->x[l];
+                RowPassArgs r{};
+                r.g = t.g;
+                r.x_in = t.work;
+                r.col_w = t.wkron + (size_t)a * t.pitch;
+                r.t_out = Ta;
+                r.tpart = t.tpart;
+                r.cpart = t.cpart;
+                r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
+                r.div = (double)L;
+                r.ctrl = h->ctrl;
+                r.trip = trip;
+                TRY(row_pass(h, t.dtype, t.masked, r));
+            }
+            // K4: q = Y't / ||.||, u = Y q, stop test (tpls.py:100-107)
+            {
+                ColPassArgs c{};
+                c.g = h->gy;
+                c.x_in = h->y_work;
+                c.row_u = Ta;
+                c.zpart = h->zpart_y;
+                c.ctrl = h->ctrl;
+                c.trip = trip;
+                TRY(col_pass(h, TPLS_F64, false, PF_CONTRACT, c));
+                TRY(reduce_cols(h, h->zpart_y, A + h->off_q, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
+                TRY(allreduce(h, A + h->off_q, h->pitch_y));
+                CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, trip, st));
+                h->stats.kernel_launches++;
+                RowPassArgs r{};
+                r.g = h->gy;
+                r.x_in = h->y_work;
+                r.col_w = h->qvec;
+                r.t_out = Ua;
+                r.epi = 0;
+                r.div = 1.0;
+                r.d2part = h->d2part;
+                r.ctrl = h->ctrl;
+                r.trip = trip;
+                TRY(row_pass(h, TPLS_F64, false, r));
+                const int nd2 = d2_grid(h->gy);
+                if (h->world > 1) {
+                    CK(launch_sum_small(h->d2part, nd2, A + h->off_d2, h->ctrl, trip, st));
+                    h->stats.kernel_launches++;
+                    TRY(allreduce(h, A + h->off_d2, 1));
+                    CK(launch_stop(h->ctrl, trip, A + h->off_d2, 1, tol, st));
+                } else {
+                    CK(launch_stop(h->ctrl, trip, h->d2part, nd2, tol, st));
+                }
+                h->stats.kernel_launches++;
+            }
+            CK(cudaMemcpyAsync(&h->h_done[trip], &h->ctrl->done_trip, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(h->ev_trip[trip & 3], st));
+        }
+
+        // ---- regression on the scores so far (tpls.py:110-112) ----
+        {
+            DotPairs d{};
+            d.n = n;
+            d.npairs = 2 * (a + 1);
+            for (int b = 0; b <= a; ++b) {
+                d.a[b] = h->T + (size_t)b * n;
+                d.b[b] = Ta;
+                d.a[a + 1 + b] = h->T + (size_t)b * n;
+                d.b[a + 1 + b] = Ua;
+            }
+            int gx = 1;
+            CK(launch_multi_dot(d, h->dotpart, &gx, st));
+            h->stats.kernel_launches++;
+            TRY(reduce_cols(h, h->dotpart, A + h->off_dots, d.npairs, d.npairs, gx, nullptr, nullptr, 0, nullptr, 0));
+            TRY(allreduce(h, A + h->off_dots, d.npairs));
+            CK(launch_solve_coef(A + h->off_dots, h->gram, h->coef, R, a, h->ctrl, h->trips_dev, st));
+            h->stats.kernel_launches++;
+        }
+        // ---- Y deflation (tpls.py:113) + ||Y||^2 for R2Y ----
+        {
+            CK(launch_lincomb(h->T, n, n, h->coef, R, a, h->svec, st));
+            h->stats.kernel_launches++;
+            ColPassArgs c{};
+            c.g = h->gy;
+            c.x_in = h->y_work;
+            c.x_out = h->y_work;
+            c.row_a = h->svec;
+            c.col_w = h->qvec;
+            c.sspart = h->sspart_y;
+            TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c));
+            TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y + a + 1, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
+        }
+        // ---- X deflation (tpls.py:109) fused with the next component's first contraction ----
+        if (a + 1 < R) {
+            CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U + (size_t)(a + 1) * n, st));
+            h->stats.kernel_launches++;
+        }
+        for (int l = 0; l < L; ++l) {
+            Tensor& t = h->x[l];
+            ColPassArgs c{};
+            c.g = t.g;
+            c.x_in = t.work;
+            c.x_out = t.work;
+            c.row_a = Ta;
+            c.col_w = t.wkron + (size_t)a * t.pitch;
+            c.sspart = t.sspart;
+            if (a + 1 < R) {
+                c.row_u = h->U + (size_t)(a + 1) * n;
+                c.zpart = t.zpart;
+                TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ, c));
+                TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, t.sspart, A + t.off_ss + a + 1,
+                                t.g.grid_x * t.g.n_slabs, nullptr, 0));
+            } else {
+                TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_SUMSQ, c));
+                TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, t.sspart, A + t.off_ss + a + 1, t.g.grid_x * t.g.n_slabs, nullptr, 0));
+            }
+        }
+    }
+
+    // ---- R2X / R2Y from the residual norms ----
+    TRY(allreduce(h, A + h->off_ss, h->ss_len));
+    std::vector<double> ss(h->ss_len);
+    h->trips.assign(R, 0);
+    CK(cudaMemcpyAsync(ss.data(), A + h->off_ss, sizeof(double) * h->ss_len, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->trips.data(), h->trips_dev, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev_stop, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
+    h->stats.fit_ms = ms;
+    for (int l = 0; l < L; ++l) {
+        h->r2x[l].assign(R, 0.0);
+        const double* s = ss.data() + (h->x[l].off_ss - h->off_ss);
+        for (int a = 0; a < R; ++a) h->r2x[l][a] = 1.0 - s[a + 1] / s[0];
+    }
+    h->r2y.assign(R, 0.0);
+    {
+        const double* s = ss.data() + (size_t)L * (R + 1);
+        for (int a = 0; a < R; ++a) h->r2y[a] = 1.0 - s[a + 1] / s[0];
+    }
+    long long total = 0;
+    for (int a = 0; a < R; ++a) total += h->trips[a];
+    h->stats.total_trips = total;
+    double alg = 0.0;
+    for (int l = 0; l < L; ++l) alg += (double)h->x[l].elem * n * h->x[l].p * (2.0 * total + R + 2);
+    h->stats.alg_bytes = alg;
+    h->fitted = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// getters
+// ---------------------------------------------------------------------------
+static int copy_out_transposed(tpls_handle h, const double* colmajor, long long rows, int cols, double* out) {
+    CK(cudaSetDevice(h->device));
+    if (is_device_ptr(out)) {
+        CK(launch_transpose_out(colmajor, rows, rows, cols, out, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    double* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, sizeof(double) * std::max<long long>(1, rows * cols)));
+    cudaError_t e = launch_transpose_out(colmajor, rows, rows, cols, tmp, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, sizeof(double) * rows * cols, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    CK(e);
+    return 0;
+}
+
+#define NEED_FIT()                                     \
+    if (!h) return fail(nullptr, "NULL handle");       \
+    if (!h->fitted) return fail(h, "not fitted")
+
+int tpls_get_x_factor(tpls_handle h, int index, int mode, double* out) {
+    NEED_FIT();
+    if (index < 0 || index >= h->L) return fail(h, "tensor index %d out of range", index);
+    Tensor& t = h->x[index];
+    if (mode < 0 || mode >= t.ndim) return fail(h, "mode %d out of range", mode);
+    if (mode == 0) return copy_out_transposed(h, h->T, h->n, h->R, out);
+    return copy_out_transposed(h, t.W[mode], t.shape[mode], h->R, out);
+}
+
+int tpls_get_y_factor(tpls_handle h, int which, double* out) {
+    NEED_FIT();
+    if (which == 0) return copy_out_transposed(h, h->U, h->n, h->R, out);
+    if (which == 1) return copy_out_transposed(h, h->Q, h->m, h->R, out);
+    return fail(h, "which must be 0 (U) or 1 (Q)");
+}
+
+int tpls_get_coef(tpls_handle h, double* out) {
+    NEED_FIT();
+    CK(cudaMemcpyAsync(out, h->coef, sizeof(double) * h->R * h->R, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tpls_get_r2x(tpls_handle h, int index, double* out) {
+    NEED_FIT();
+    if (index < 0 || index >= h->L) return fail(h, "tensor index %d out of range", index);
+    memcpy(out, h->r2x[index].data(), sizeof(double) * h->R);
+    return 0;
+}
+
+int tpls_get_r2y(tpls_handle h, double* out) {
+    NEED_FIT();
+    memcpy(out, h->r2y.data(), sizeof(double) * h->R);
+    return 0;
+}
+
+int tpls_get_x_mean(tpls_handle h, int index, void* out) {
+    NEED_FIT();
+    if (index < 0 || index >= h->L) return fail(h, "tensor index %d out of range", index);
+    Tensor& t = h->x[index];
+    CK(cudaMemcpyAsync(out, t.mean_native, (size_t)t.elem * t.p, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tpls_get_y_mean(tpls_handle h, double* out) {
+    NEED_FIT();
+    CK(cudaMemcpyAsync(out, h->ymean_d, sizeof(double) * h->m, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tpls_get_has_missing(tpls_handle h, int index, int* out) {
+    NEED_FIT();
+    if (index < 0 || index >= h->L) return fail(h, "tensor index %d out of range", index);
+    *out = h->x[index].masked ? 1 : 0;
+    return 0;
+}
+
+int tpls_get_trips(tpls_handle h, int* out) {
+    NEED_FIT();
+    memcpy(out, h->trips.data(), sizeof(int) * h->R);
+    return 0;
+}
+
+int tpls_get_stats(tpls_handle h, tpls_stats* out) {
+    if (!h) return fail(nullptr, "NULL handle");
+    *out = h->stats;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// transform
+// ---------------------------------------------------------------------------
+int tpls_release_data(tpls_handle h) {
+    if (!h) return fail(nullptr, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto& t : h->x) {
+        if (t.owned) cudaFree(t.owned);
+        if (t.owned2) cudaFree(t.owned2);
+        t.owned = t.owned2 = nullptr;
+        t.src = nullptr;
+        t.work = nullptr;
+        t.set = false;
+    }
+    if (h->y_src) cudaFree(h->y_src);
+    if (h->y_work) cudaFree(h->y_work);
+    h->y_src = h->y_work = nullptr;
+    return 0;
+}
+
+int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* const* xs, const int* dtypes,
+                   int64_t n_new, const int64_t* ps, const void* const* means, const double* const* wkrons,
+                   double* scores_out) {
+    if (!h) return fail(nullptr, "NULL handle");
+    const int L = n_tensors, R = n_components;
+    if (L < 1 || L > TPLS_MAX_TENSORS || R < 1 || n_new <= 0) return fail(h, "tpls_transform: bad sizes");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    std::vector<void*> tmp;
+    double *S = nullptr, *sspart = nullptr;
+    int rc = 0;
+    std::vector<void*> xw(L, nullptr);
+    std::vector<PassGeom> gs(L);
+    std::vector<double*> tpart(L, nullptr), cpart(L, nullptr), mean_d(L, nullptr), wk(L, nullptr);
+    std::vector<int> pitch(L), elem(L);
+    do {
+        if ((rc = dev_alloc(h, (void**)&S, sizeof(double) * n_new * R, &tmp))) break;
+        if ((rc = dev_alloc(h, (void**)&sspart, sizeof(double) * 4096, &tmp))) break;
+        for (int l = 0; l < L && !rc; ++l) {
+            if (dtypes[l] != TPLS_F32 && dtypes[l] != TPLS_F64) {
+                rc = fail(h, "tpls_transform: bad dtype for X[%d]", l);
+                break;
+            }
+            elem[l] = dtypes[l] == TPLS_F32 ? 4 : 8;
+            const int vec = 16 / elem[l];
+            const int p = (int)ps[l];
+            pitch[l] = (p + vec - 1) / vec * vec;
+            const size_t bytes = (size_t)n_new * pitch[l] * elem[l];
+            if ((rc = dev_alloc(h, &xw[l], bytes, &tmp))) break;
+            if ((rc = dev_alloc(h, (void**)&mean_d[l], sizeof(double) * pitch[l], &tmp))) break;
+            if ((rc = dev_alloc(h, (void**)&wk[l], sizeof(double) * pitch[l] * R, &tmp))) break;
+            void* mean_nat = nullptr;
+            if ((rc = dev_alloc(h, &mean_nat, (size_t)elem[l] * pitch[l], &tmp))) break;
+            cudaError_t e = cudaMemsetAsync(xw[l], 0, bytes, st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(wk[l], 0, sizeof(double) * pitch[l] * R, st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(mean_nat, 0, (size_t)elem[l] * pitch[l], st);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(xw[l], (size_t)pitch[l] * elem[l], xs[l], (size_t)p * elem[l], (size_t)p * elem[l],
+                                      n_new, cudaMemcpyDefault, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(mean_nat, means[l], (size_t)elem[l] * p, cudaMemcpyDefault, st);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(wk[l], sizeof(double) * pitch[l], wkrons[l], sizeof(double) * p, sizeof(double) * p, R,
+                                      cudaMemcpyDefault, st);
+            if (e == cudaSuccess) e = launch_widen(dtypes[l], mean_nat, mean_d[l], pitch[l], st);
+            if (e != cudaSuccess) {
+                rc = fail(h, "tpls_transform: staging X[%d] -> %s", l, cudaGetErrorString(e));
+                break;
+            }
+            gs[l] = make_geom(n_new, p, pitch[l], elem[l], h->sm_count);
+            if (gs[l].n_slabs > 1) {
+                if ((rc = dev_alloc(h, (void**)&tpart[l], sizeof(double) * n_new * gs[l].n_slabs, &tmp))) break;
+                if ((rc = dev_alloc(h, (void**)&cpart[l], sizeof(double) * n_new * gs[l].n_slabs, &tmp))) break;
+            }
+            // centre with the training mean (tpls.py:151)
+            ColPassArgs c{};
+            c.g = gs[l];
+            c.x_in = xw[l];
+            c.x_out = xw[l];
+            c.col_w = mean_d[l];
+            c.sspart = sspart;
+            if ((rc = col_pass(h, dtypes[l], true, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c))) break;
+        }
+        if (rc) break;
+        // per component: project (averaged over the coupled tensors), then deflate with the stored loadings
+        for (int a = 0; a < R && !rc; ++a) {
+            double* Sa = S + (size_t)a * n_new;
+            for (int l = 0; l < L && !rc; ++l) {
+                RowPassArgs r{};
+                r.g = gs[l];
+                r.x_in = xw[l];
+                r.col_w = wk[l] + (size_t)a * pitch[l];
+                r.t_out = Sa;
+                r.tpart = tpart[l];
+                r.cpart = cpart[l];
+                r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
+                r.div = (double)L;
+                rc = row_pass(h, dtypes[l], true, r);
+            }
+            for (int l = 0; l < L && !rc && a + 1 < R; ++l) {
+                ColPassArgs c{};
+                c.g = gs[l];
+                c.x_in = xw[l];
+                c.x_out = xw[l];
+                c.row_a = Sa;
+                c.col_w = wk[l] + (size_t)a * pitch[l];
+                c.sspart = sspart;
+                rc = col_pass(h, dtypes[l], true, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c);
+            }
+        }
+        if (rc) break;
+        rc = copy_out_transposed(h, S, n_new, R, scores_out);
+    } while (0);
+    cudaStreamSynchronize(st);
+    for (void* p : tmp) cudaFree(p);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// single operators
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+static int time_loop(tpls_handle h, int repeats, float* ms_out, const std::function<int()>& body) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    repeats = std::max(1, repeats);
+    int rc = 0;
+    if (repeats > 1) rc = body();  // warm-up
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < repeats && !rc; ++i) rc = body();
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_out) *ms_out = ms / repeats;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+extern "C" {
+
+static int op_check(tpls_handle h, int dtype, int64_t n, int64_t p) {
+    if (!h) return fail(nullptr, "NULL handle");
+    if (dtype != TPLS_F32 && dtype != TPLS_F64) return fail(h, "bad dtype");
+    const int elem = dtype == TPLS_F32 ? 4 : 8;
+    if (n <= 0 || p <= 0 || (p * elem) % 16 != 0) return fail(h, "operator needs p*elem %% 16 == 0 (p=%lld)", (long long)p);
+    return 0;
+}
+
+int tpls_op_contract(tpls_handle h, const void* x, int dtype, int64_t n, int64_t p, const double* u, int masked,
+                     double* z_out, float* ms_out, int repeats) {
+    TRY(op_check(h, dtype, n, p));
+    CK(cudaSetDevice(h->device));
+    const int elem = dtype == TPLS_F32 ? 4 : 8;
+    PassGeom g = make_geom(n, (int)p, (int)p, elem, h->sm_count);
+    double *zpart = nullptr, *cntpart = nullptr, *cnt = nullptr;
+    CK(cudaMalloc((void**)&zpart, sizeof(double) * g.grid_x * p));
+    CK(cudaMalloc((void**)&cntpart, sizeof(double) * g.grid_x * p));
+    CK(cudaMalloc((void**)&cnt, sizeof(double) * p));
+    int rc = 0;
+    if (masked) {
+        ColPassArgs c{};
+        c.g = g;
+        c.x_in = x;
+        c.zpart = zpart;
+        c.cntpart = cntpart;
+        rc = col_pass(h, dtype, true, PF_COLSTAT, c);
+        if (!rc) rc = reduce_cols(h, cntpart, cnt, (int)p, (int)p, g.grid_x, nullptr, nullptr, 0, nullptr, 0);
+    }
+    if (!rc)
+        rc = time_loop(h, repeats, ms_out, [&]() -> int {
+            ColPassArgs c{};
+            c.g = g;
+            c.x_in = x;
+            c.row_u = u;
+            c.zpart = zpart;
+            TRY(col_pass(h, dtype, masked != 0, PF_CONTRACT, c));
+            return reduce_cols(h, zpart, z_out, (int)p, (int)p, g.grid_x, nullptr, nullptr, 0, nullptr, 0);
+        });
+    // during a fit the observed-count rescaling (missingvals.py:18) is applied by the rank-1 kernel
+    if (!rc && masked) {
+        cudaError_t e = launch_count_rescale(z_out, cnt, (double)n, (int)p, h->stream);
+        if (e != cudaSuccess) rc = fail(h, "count_rescale -> %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(zpart);
+    cudaFree(cntpart);
+    cudaFree(cnt);
+    return rc;
+}
+
+int tpls_op_project(tpls_handle h, const void* x, int dtype, int64_t n, int64_t p, const double* w, int masked,
+                    double* t_out, float* ms_out, int repeats) {
+    TRY(op_check(h, dtype, n, p));
+    CK(cudaSetDevice(h->device));
+    const int elem = dtype == TPLS_F32 ? 4 : 8;
+    PassGeom g = make_geom(n, (int)p, (int)p, elem, h->sm_count);
+    double *tpart = nullptr, *cpart = nullptr;
+    if (g.n_slabs > 1) {
+        CK(cudaMalloc((void**)&tpart, sizeof(double) * n * g.n_slabs));
+        CK(cudaMalloc((void**)&cpart, sizeof(double) * n * g.n_slabs));
+    }
+    int rc = time_loop(h, repeats, ms_out, [&]() -> int {
+        RowPassArgs r{};
+        r.g = g;
+        r.x_in = x;
+        r.col_w = w;
+        r.t_out = t_out;
+        r.tpart = tpart;
+        r.cpart = cpart;
+        r.epi = 0;
+        r.div = 1.0;
+        return row_pass(h, dtype, masked != 0, r);
+    });
+    cudaStreamSynchronize(h->stream);
+    if (tpart) cudaFree(tpart);
+    if (cpart) cudaFree(cpart);
+    return rc;
+}
+
+int tpls_op_deflate_contract(tpls_handle h, void* x, int dtype, int64_t n, int64_t p, const double* t,
+                             const double* w, const double* u, int masked, double* z_out, double* ss_out,
+                             float* ms_out, int repeats) {
+    TRY(op_check(h, dtype, n, p));
+    CK(cudaSetDevice(h->device));
+    const int elem = dtype == TPLS_F32 ? 4 : 8;
+    PassGeom g = make_geom(n, (int)p, (int)p, elem, h->sm_count);
+    double *zpart = nullptr, *sspart = nullptr;
+    CK(cudaMalloc((void**)&zpart, sizeof(double) * g.grid_x * p));
+    CK(cudaMalloc((void**)&sspart, sizeof(double) * g.grid_x * g.n_slabs));
+    int rc = time_loop(h, repeats, ms_out, [&]() -> int {
+        ColPassArgs c{};
+        c.g = g;
+        c.x_in = x;
+        c.x_out = x;
+        c.row_a = t;
+        c.col_w = w;
+        c.row_u = u;
+        c.zpart = zpart;
+        c.sspart = sspart;
+        TRY(col_pass(h, dtype, masked != 0, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ, c));
+        return reduce_cols(h, zpart, z_out, (int)p, (int)p, g.grid_x, sspart, ss_out, g.grid_x * g.n_slabs, nullptr, 0);
+    });
+    cudaStreamSynchronize(h->stream);
+    cudaFree(zpart);
+    cudaFree(sspart);
+    return rc;
+}
+
+int tpls_op_rank1(tpls_handle h, const double* z, int nmodes, const int* dims, double tol, int flags, double* w_out,
+                  double* wkron_out, int* sweeps_out, float* ms_out, int repeats) {
+    if (!h) return fail(nullptr, "NULL handle");
+    if (nmodes < 1 || nmodes > kMaxZModes) return fail(h, "tpls_op_rank1: nmodes must be 1..%d", kMaxZModes);
+    CK(cudaSetDevice(h->device));
+    Rank1Args ra{};
+    ra.n_tasks = 1;
+    ra.tol = tol;
+    ra.normalize_on_break = (flags & TPLS_FIT_NORMALIZE_ON_BREAK) ? 1 : 0;
+    Rank1Task& k = ra.t[0];
+    long long p = 1;
+    size_t off = 0;
+    for (int m = 0; m < nmodes; ++m) {
+        k.dims[m] = dims[m];
+        k.w[m] = w_out + off;
+        off += dims[m];
+        p *= dims[m];
+    }
+    k.z = z;
+    k.p = (int)p;
+    k.pitch = (int)p;
+    k.nmodes = nmodes;
+    k.wkron = wkron_out;
+    int nmax = 1;
+    const size_t ws = rank1_workspace_doubles(nmodes, dims, &nmax);
+    k.nmax = nmax;
+    double* scratch = nullptr;
+    int* sweeps = nullptr;
+    CK(cudaMalloc((void**)&scratch, sizeof(double) * ws));
+    CK(cudaMalloc((void**)&sweeps, sizeof(int) * 4));
+    k.scratch = scratch;
+    k.sweeps = sweeps;
+    size_t smem = ws * sizeof(double);
+    k.use_smem = smem <= 200 * 1024;
+    if (!k.use_smem) smem = 0;
+    int rc = time_loop(h, repeats, ms_out, [&]() -> int {
+        CK(launch_rank1(ra, smem, h->stream));
+        h->stats.kernel_launches++;
+        return 0;
+    });
+    cudaStreamSynchronize(h->stream);
+    if (!rc && sweeps_out) cudaMemcpy(sweeps_out, sweeps, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(scratch);
+    cudaFree(sweeps);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,582 @@
+// Streaming column/row passes over an X (or Y) shard -- see passes.cuh.
+#include "passes.cuh"
+
+#include <algorithm>
+
+namespace tpls {
+
+// ---------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------
+static int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count) {
+    PassGeom g{};
+    const int vec = 16 / elem_size;
+    g.n_rows = n_rows;
+    g.p = p;
+    g.pitch = pitch;
+    g.elem_size = elem_size;
+    const int cg_total = pitch / vec;
+    const int max_cg = kConsumers * kMaxCpt;
+    g.n_slabs = (cg_total + max_cg - 1) / max_cg;
+    const int slab_cg = (cg_total + g.n_slabs - 1) / g.n_slabs;
+    g.slab_w = slab_cg * vec;
+    if (slab_cg >= kConsumers) {
+        g.lpr = kConsumers;
+        const int need = (slab_cg + kConsumers - 1) / kConsumers;
+        g.cpt = need <= 1 ? 1 : (need <= 2 ? 2 : 4);
+    } else {
+        g.lpr = pow2_ceil(slab_cg);
+        g.cpt = 1;
+    }
+    g.rpt = kConsumers / g.lpr;
+    const long long row_bytes = (long long)(g.n_slabs == 1 ? pitch : g.slab_w) * elem_size;
+    long long tr = std::max<long long>(1, (32 * 1024) / row_bytes);
+    tr = std::min<long long>(tr, std::max<long long>(1, n_rows));
+    tr = std::min<long long>(tr, 4096);
+    g.tile_rows = (int)tr;
+    const long long stage_bytes = tr * row_bytes;
+    g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, (100 * 1024) / stage_bytes));
+    const long long n_tiles = (n_rows + tr - 1) / tr;
+    const long long want = std::max(1, (sm_count * 2) / g.n_slabs);
+    g.grid_x = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
+    return g;
+}
+
+static size_t stage_bytes_of(const PassGeom& g) {
+    return (size_t)g.tile_rows * (g.n_slabs == 1 ? g.pitch : g.slab_w) * g.elem_size;
+}
+
+size_t colpass_smem(const PassGeom& g) {
+    const size_t tiles = g.stages * stage_bytes_of(g);
+    const size_t red = (size_t)kConsumers * 16 / g.elem_size * sizeof(double);  // rpt > 1 => cpt == 1
+    return std::max(tiles, red) + 128;
+}
+
+size_t rowpass_smem(const PassGeom& g) {
+    size_t red = 0;
+    if (g.lpr > 32) red = (size_t)2 * g.tile_rows * (g.lpr / 32) * 2 * sizeof(double);
+    return g.stages * stage_bytes_of(g) + 128 + red;
+}
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+template <typename XT>
+struct VecOf;
+template <>
+struct VecOf<float> {
+    using type = float4;
+    static constexpr int N = 4;
+};
+template <>
+struct VecOf<double> {
+    using type = double2;
+    static constexpr int N = 2;
+};
+
+template <typename XT>
+union Pack {
+    typename VecOf<XT>::type v;
+    XT e[VecOf<XT>::N];
+};
+
+// Producer: one elected lane streams this CTA's row tiles into the smem ring.
+template <typename XT>
+__device__ __forceinline__ void produce_tiles(const PassGeom& g, const XT* __restrict__ x, XT* tiles, uint64_t* full,
+                                              uint64_t* empty, int c0, int slab_cols, int srow) {
+    const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
+    const size_t stage_elems = (size_t)g.tile_rows * srow;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = (int)(it % g.stages);
+        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+        if (it >= g.stages) mbar_wait(&empty[s], ph ^ 1u);
+        const long long r0 = tile * g.tile_rows;
+        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+        XT* dst = tiles + s * stage_elems;
+        const XT* src = x + r0 * g.pitch + c0;
+        if (g.n_slabs == 1) {
+            const uint32_t bytes = (uint32_t)((size_t)rows * g.pitch * sizeof(XT));
+            mbar_arrive_expect_tx(&full[s], bytes);
+            bulk_g2s(dst, src, bytes, &full[s]);
+        } else {
+            const uint32_t rb = (uint32_t)(slab_cols * sizeof(XT));
+            mbar_arrive_expect_tx(&full[s], rb * rows);
+            for (int r = 0; r < rows; ++r) bulk_g2s(dst + (size_t)r * srow, src + (size_t)r * g.pitch, rb, &full[s]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// column pass
+// ---------------------------------------------------------------------------
+template <typename XT, int CPT, bool MASKED, int FLAGS>
+__global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_constant__ ColPassArgs a) {
+    constexpr int VEC = VecOf<XT>::N;
+    constexpr bool DEFLATE = (FLAGS & PF_DEFLATE) != 0;
+    constexpr bool WRITE = (FLAGS & PF_WRITE) != 0;
+    constexpr bool CONTRACT = (FLAGS & PF_CONTRACT) != 0;
+    constexpr bool SUMSQ = (FLAGS & PF_SUMSQ) != 0;
+    constexpr bool COLSTAT = (FLAGS & PF_COLSTAT) != 0;
+    constexpr bool ZACC = CONTRACT || COLSTAT;
+
+    if (trip_is_dead(a.ctrl, a.trip)) return;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PassGeom& g = a.g;
+    const int c0 = blockIdx.y * g.slab_w;
+    const int slab_cols = min(g.slab_w, g.pitch - c0);
+    const int srow = (g.n_slabs == 1) ? g.pitch : g.slab_w;
+    const size_t stage_elems = (size_t)g.tile_rows * srow;
+    XT* tiles = reinterpret_cast<XT*>(smem);
+    const size_t tile_area = max((size_t)g.stages * stage_elems * sizeof(XT), (size_t)kConsumers * VEC * sizeof(double));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + tile_area);
+    uint64_t* empty = full + kMaxStages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumers / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= kConsumers) {
+        if (threadIdx.x == kConsumers)
+            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow);
+        return;
+    }
+
+    const int tid = threadIdx.x;
+    const int cl = tid & (g.lpr - 1);
+    const int rl = tid / g.lpr;
+    const int lane = tid & 31;
+
+    double wreg[CPT][VEC];
+    double zacc[CPT][VEC];
+    double cacc[CPT][VEC];
+    bool cvalid[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int cg = cl + k * g.lpr;
+        cvalid[k] = cg * VEC < slab_cols;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            zacc[k][j] = 0.0;
+            cacc[k][j] = 0.0;
+            wreg[k][j] = (DEFLATE && cvalid[k]) ? a.col_w[c0 + cg * VEC + j] : 0.0;
+        }
+    }
+    double ss = 0.0;
+
+    XT* xo = reinterpret_cast<XT*>(a.x_out);
+    const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = (int)(it % g.stages);
+        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+        const long long r0 = tile * g.tile_rows;
+        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+        mbar_wait(&full[s], ph);
+        const XT* tp = tiles + s * stage_elems;
+        for (int r = rl; r < rows; r += g.rpt) {
+            const long long grow = r0 + r;
+            double ar = 1.0, ur = 0.0;
+            if (DEFLATE && a.row_a != nullptr) ar = __ldg(a.row_a + grow);
+            if (CONTRACT) ur = __ldg(a.row_u + grow);
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                if (!cvalid[k]) continue;
+                const int cg = cl + k * g.lpr;
+                Pack<XT> in, out;
+                in.v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const XT xs = in.e[j];
+                    const bool ob = MASKED ? (xs == xs) : true;
+                    double xd = (double)xs;
+                    if (DEFLATE) {
+                        xd = fma(-ar, wreg[k][j], xd);
+                        out.e[j] = (XT)xd;       // NaN stays NaN
+                        xd = (double)out.e[j];   // later passes see the stored (rounded) value
+                    }
+                    if (MASKED && !ob) xd = 0.0;
+                    if (CONTRACT) zacc[k][j] = fma(xd, ur, zacc[k][j]);
+                    if (COLSTAT) {
+                        zacc[k][j] += xd;
+                        cacc[k][j] += ob ? 1.0 : 0.0;
+                    }
+                    if (SUMSQ) ss = fma(xd, xd, ss);
+                }
+                if (WRITE) {
+                    __stcs(reinterpret_cast<typename VecOf<XT>::type*>(xo + grow * g.pitch + c0 + cg * VEC), out.v);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ---- epilogue: fold row lanes, publish this CTA's column partials ----
+    if (ZACC) {
+        double* red = reinterpret_cast<double*>(smem);
+        const int wcols = g.lpr * VEC;  // rpt > 1 => CPT == 1
+        for (int pass = 0; pass < (COLSTAT ? 2 : 1); ++pass) {
+            double(*acc)[VEC] = pass == 0 ? zacc : cacc;
+            double* outp = (pass == 0 ? a.zpart : a.cntpart) + (size_t)blockIdx.x * g.pitch + c0;
+            if (g.rpt > 1) {
+                named_bar_sync(1, kConsumers);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) red[(size_t)rl * wcols + cl * VEC + j] = acc[0][j];
+                named_bar_sync(1, kConsumers);
+                if (rl == 0 && cvalid[0]) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        double t = 0.0;
+                        for (int q = 0; q < g.rpt; ++q) t += red[(size_t)q * wcols + cl * VEC + j];
+                        outp[cl * VEC + j] = t;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    if (!cvalid[k]) continue;
+                    const int cg = cl + k * g.lpr;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) outp[cg * VEC + j] = acc[k][j];
+                }
+            }
+        }
+    }
+    if (SUMSQ) {
+        double* red = reinterpret_cast<double*>(smem);
+        named_bar_sync(1, kConsumers);
+        ss = warp_sum(ss);
+        if (lane == 0) red[tid >> 5] = ss;
+        named_bar_sync(1, kConsumers);
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kConsumers / 32; ++w) t += red[w];
+            a.sspart[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// row pass
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long grow, double v, double& d2) {
+    double* tp = a.t_out + grow;
+    const double old = *tp;
+    double nv = v;
+    if (a.epi == 1) nv = old + v;
+    if (a.epi == 2) nv = (old + v) / a.div;
+    *tp = nv;
+    if (a.d2part != nullptr) {
+        const double d = old - nv;
+        d2 = fma(d, d, d2);
+    }
+}
+
+template <typename XT, int CPT, bool MASKED>
+__global__ void __launch_bounds__(kThreads, 2) rowpass_kernel(const __grid_constant__ RowPassArgs a) {
+    constexpr int VEC = VecOf<XT>::N;
+    if (trip_is_dead(a.ctrl, a.trip)) return;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PassGeom& g = a.g;
+    const int c0 = blockIdx.y * g.slab_w;
+    const int slab_cols = min(g.slab_w, g.pitch - c0);
+    const int srow = (g.n_slabs == 1) ? g.pitch : g.slab_w;
+    const size_t stage_elems = (size_t)g.tile_rows * srow;
+    XT* tiles = reinterpret_cast<XT*>(smem);
+    const size_t tile_area = (size_t)g.stages * stage_elems * sizeof(XT);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + tile_area);
+    uint64_t* empty = full + kMaxStages;
+    double* red = reinterpret_cast<double*>(smem + tile_area + 128);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumers / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= kConsumers) {
+        if (threadIdx.x == kConsumers)
+            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow);
+        return;
+    }
+
+    const int tid = threadIdx.x;
+    const int cl = tid & (g.lpr - 1);
+    const int rl = tid / g.lpr;
+    const int lane = tid & 31;
+    const int wpr = g.lpr >> 5;  // warps per row when lpr > 32
+    const bool slabbed = g.n_slabs > 1;
+    const double p_total = (double)g.p;
+
+    double wreg[CPT][VEC];
+    bool cvalid[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int cg = cl + k * g.lpr;
+        cvalid[k] = cg * VEC < slab_cols;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) wreg[k][j] = cvalid[k] ? a.col_w[c0 + cg * VEC + j] : 0.0;
+    }
+    double d2 = 0.0;
+
+    const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = (int)(it % g.stages);
+        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+        const long long r0 = tile * g.tile_rows;
+        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+        mbar_wait(&full[s], ph);
+        const XT* tp = tiles + s * stage_elems;
+        double* redt = red + (size_t)(it & 1) * g.tile_rows * max(wpr, 1) * 2;
+        // every lane of a row group walks the same number of rounds so that the shuffles stay converged
+        for (int rb = 0; rb < rows; rb += g.rpt) {
+            const int r = rb + rl;
+            const bool live = r < rows;
+            double v = 0.0, cnt = 0.0;
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    if (!cvalid[k]) continue;
+                    const int cg = cl + k * g.lpr;
+                    Pack<XT> in;
+                    in.v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const XT xs = in.e[j];
+                        if (MASKED) {
+                            const bool ob = (xs == xs) && (c0 + cg * VEC + j < g.p);
+                            v = fma(ob ? (double)xs : 0.0, wreg[k][j], v);
+                            cnt += ob ? 1.0 : 0.0;
+                        } else {
+                            v = fma((double)xs, wreg[k][j], v);
+                        }
+                    }
+                }
+            }
+            // reduce over the lanes of this row
+            const int span = g.lpr < 32 ? g.lpr : 32;
+            for (int m = span >> 1; m >= 1; m >>= 1) {
+                v += shfl_xor_d(v, m);
+                if (MASKED) cnt += shfl_xor_d(cnt, m);
+            }
+            if (g.lpr <= 32) {
+                if (live && cl == 0) {
+                    const long long grow = r0 + r;
+                    if (slabbed) {
+                        a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
+                        if (MASKED) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
+                    } else {
+                        if (MASKED) v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
+                        row_epilogue(a, grow, v, d2);
+                    }
+                }
+            } else if (live && lane == 0) {
+                redt[((size_t)r * wpr + (cl >> 5)) * 2 + 0] = v;
+                redt[((size_t)r * wpr + (cl >> 5)) * 2 + 1] = cnt;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (g.lpr > 32) {
+            named_bar_sync(1, kConsumers);
+            for (int r = tid; r < rows; r += kConsumers) {
+                double v = 0.0, cnt = 0.0;
+                for (int w = 0; w < wpr; ++w) {
+                    v += redt[((size_t)r * wpr + w) * 2 + 0];
+                    cnt += redt[((size_t)r * wpr + w) * 2 + 1];
+                }
+                const long long grow = r0 + r;
+                if (slabbed) {
+                    a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
+                    if (MASKED) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
+                } else {
+                    if (MASKED) v = v / cnt * p_total;
+                    row_epilogue(a, grow, v, d2);
+                }
+            }
+        }
+    }
+
+    if (a.d2part != nullptr && !slabbed) {
+        double* r2 = reinterpret_cast<double*>(smem);  // tiles are drained
+        named_bar_sync(1, kConsumers);
+        d2 = warp_sum(d2);
+        if (lane == 0) r2[tid >> 5] = d2;
+        named_bar_sync(1, kConsumers);
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kConsumers / 32; ++w) t += r2[w];
+            a.d2part[blockIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// small finishing kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
+    if (trip_is_dead(a.ctrl, a.trip)) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < a.n_cols) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        int b = 0;
+        for (; b + 4 <= a.n_parts; b += 4) {
+            t0 += a.part[(size_t)(b + 0) * a.stride + c];
+            t1 += a.part[(size_t)(b + 1) * a.stride + c];
+            t2 += a.part[(size_t)(b + 2) * a.stride + c];
+            t3 += a.part[(size_t)(b + 3) * a.stride + c];
+        }
+        for (; b < a.n_parts; ++b) t0 += a.part[(size_t)b * a.stride + c];
+        a.out[c] = (t0 + t1) + (t2 + t3);
+    }
+    if (a.ss_out != nullptr && blockIdx.x == 0) {
+        __shared__ double red[40];
+        double t = 0.0;
+        for (int i = threadIdx.x; i < a.n_ss; i += blockDim.x) t += a.sspart[i];
+        t = block_sum(t, red);
+        if (threadIdx.x == 0) a.ss_out[0] = t;
+    }
+}
+
+cudaError_t launch_reduce_cols(const ReduceArgs& a, cudaStream_t s) {
+    const int blocks = std::max(1, (a.n_cols + 255) / 256);
+    reduce_cols_kernel<<<blocks, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) row_finish_kernel(const RowFinishArgs a) {
+    if (trip_is_dead(a.ctrl, a.trip)) return;
+    __shared__ double red[40];
+    double d2 = 0.0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        double v = 0.0, cnt = 0.0;
+        for (int s = 0; s < a.n_slabs; ++s) {
+            v += a.tpart[(size_t)s * a.n_rows + r];
+            if (a.cpart != nullptr) cnt += a.cpart[(size_t)s * a.n_rows + r];
+        }
+        if (a.cpart != nullptr) v = v / cnt * a.p_total;
+        const double old = a.t_out[r];
+        double nv = v;
+        if (a.epi == 1) nv = old + v;
+        if (a.epi == 2) nv = (old + v) / a.div;
+        a.t_out[r] = nv;
+        const double d = old - nv;
+        d2 = fma(d, d, d2);
+    }
+    if (a.d2part != nullptr) {
+        d2 = block_sum(d2, red);
+        if (threadIdx.x == 0) a.d2part[blockIdx.x] = d2;
+    }
+}
+
+int row_finish_grid(long long n_rows) {
+    return (int)std::max<long long>(1, std::min<long long>(296, (n_rows + 255) / 256));
+}
+
+cudaError_t launch_row_finish(const RowFinishArgs& a, int* grid_out, cudaStream_t s) {
+    const int blocks = row_finish_grid(a.n_rows);
+    if (grid_out) *grid_out = blocks;
+    row_finish_kernel<<<blocks, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------
+template <typename XT, int CPT, bool MASKED, int FLAGS>
+static cudaError_t run_colpass(const ColPassArgs& a, cudaStream_t s) {
+    auto kern = colpass_kernel<XT, CPT, MASKED, FLAGS>;
+    const size_t smem = colpass_smem(a.g);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(a.g.grid_x, a.g.n_slabs);
+    kern<<<grid, kThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename XT, int CPT, bool MASKED>
+static cudaError_t colpass_flags(int flags, const ColPassArgs& a, cudaStream_t s) {
+    switch (flags) {
+        case PF_COLSTAT:
+            return run_colpass<XT, CPT, true, PF_COLSTAT>(a, s);
+        case PF_CONTRACT:
+            return run_colpass<XT, CPT, MASKED, PF_CONTRACT>(a, s);
+        case PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ:
+            return run_colpass<XT, CPT, MASKED, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ>(a, s);
+        case PF_DEFLATE | PF_WRITE | PF_SUMSQ:
+            return run_colpass<XT, CPT, MASKED, PF_DEFLATE | PF_WRITE | PF_SUMSQ>(a, s);
+        case PF_DEFLATE | PF_SUMSQ:
+            return run_colpass<XT, CPT, MASKED, PF_DEFLATE | PF_SUMSQ>(a, s);
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
+
+template <typename XT>
+static cudaError_t colpass_cpt(bool masked, int flags, const ColPassArgs& a, cudaStream_t s) {
+#define TPLS_CP(C)                                                  \
+    return masked ? colpass_flags<XT, C, true>(flags, a, s) : colpass_flags<XT, C, false>(flags, a, s)
+    switch (a.g.cpt) {
+        case 1:
+            TPLS_CP(1);
+        case 2:
+            TPLS_CP(2);
+        default:
+            TPLS_CP(4);
+    }
+#undef TPLS_CP
+}
+
+cudaError_t launch_colpass(int dtype, bool masked, int flags, const ColPassArgs& a, cudaStream_t s) {
+    return dtype == 0 ? colpass_cpt<float>(masked, flags, a, s) : colpass_cpt<double>(masked, flags, a, s);
+}
+
+template <typename XT, int CPT, bool MASKED>
+static cudaError_t run_rowpass(const RowPassArgs& a, cudaStream_t s) {
+    auto kern = rowpass_kernel<XT, CPT, MASKED>;
+    const size_t smem = rowpass_smem(a.g);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(a.g.grid_x, a.g.n_slabs);
+    kern<<<grid, kThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename XT>
+static cudaError_t rowpass_cpt(bool masked, const RowPassArgs& a, cudaStream_t s) {
+#define TPLS_RP(C) return masked ? run_rowpass<XT, C, true>(a, s) : run_rowpass<XT, C, false>(a, s)
+    switch (a.g.cpt) {
+        case 1:
+            TPLS_RP(1);
+        case 2:
+            TPLS_RP(2);
+        default:
+            TPLS_RP(4);
+    }
+#undef TPLS_RP
+}
+
+cudaError_t launch_rowpass(int dtype, bool masked, const RowPassArgs& a, cudaStream_t s) {
+    return dtype == 0 ? rowpass_cpt<float>(masked, a, s) : rowpass_cpt<double>(masked, a, s);
+}
+
+}  // namespace tpls

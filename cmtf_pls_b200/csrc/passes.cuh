@@ -1,0 +1,123 @@
+// Streaming passes over one X (or Y) shard: argument blocks and launchers.
+//
+// X is viewed as n_rows x p, row-major, row pitch `pitch` elements with
+// pitch*sizeof(XT) a multiple of 16 (numpy C order, last mode
+// fastest).  Two kernel families cover every pass of the fit:
+//
+//   colpass  : per-COLUMN accumulation over the sample mode
+//              (contraction Z = X x_1 u  -- reference cmtf_pls/tpls.py:83,
+//               missingvals.py:7-20; column sums for nanmean tpls.py:66;
+//               rank-1 deflation tpls.py:109 fused with the NEXT contraction
+//               and with the residual norm that gives R2X, util.py:7-15)
+//   rowpass  : per-ROW reduction over the feature modes
+//              (projection t = X x_2 w2 x_3 w3 ... -- tpls.py:97-99,
+//               missingvals.py:23-38; also u = Y q, tpls.py:102)
+//
+// Both stage row tiles in shared memory with 1-D bulk async copies (TMA engine,
+// mbarrier complete_tx) issued by a dedicated producer warp, and accumulate in
+// fp64 whatever the storage type.
+#pragma once
+
+#include "common.cuh"
+
+namespace tpls {
+
+constexpr int kConsumers = 256;             // consumer threads per CTA
+constexpr int kThreads = kConsumers + 32;   // + one producer warp
+constexpr int kMaxStages = 6;
+constexpr int kMaxCpt = 4;                  // 16-byte column groups per thread
+
+enum PassFlags : int {
+    PF_DEFLATE = 1,    // xn = x - a[row] * w[col]
+    PF_WRITE = 2,      // store xn (rounded to the storage type)
+    PF_CONTRACT = 4,   // zacc[col] += xn * u[row]
+    PF_SUMSQ = 8,      // ss += xn^2
+    PF_COLSTAT = 16,   // zacc[col] += x over observed rows, cnt[col] += observed
+};
+
+struct PassGeom {
+    long long n_rows;
+    int p;          // valid columns
+    int pitch;      // elements per row (multiple of 16/sizeof(XT))
+    int slab_w;     // columns per CTA column slab (multiple of 16/sizeof(XT))
+    int n_slabs;
+    int lpr;        // lanes per row (power of two <= kConsumers)
+    int rpt;        // row lanes = kConsumers / lpr
+    int cpt;        // 16-byte groups per lane actually needed (1..kMaxCpt)
+    int tile_rows;  // rows per staged tile
+    int stages;
+    int grid_x;     // CTAs along the row-tile axis
+    int elem_size;  // 4 or 8
+};
+
+// Chooses slab width, thread layout, tile size and grid for a shard.
+PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count);
+size_t colpass_smem(const PassGeom& g);
+size_t rowpass_smem(const PassGeom& g);
+
+struct ColPassArgs {
+    PassGeom g;
+    const void* x_in;
+    void* x_out;            // PF_WRITE (may alias x_in)
+    const double* row_a;    // PF_DEFLATE per-row scalar, nullptr => 1
+    const double* col_w;    // PF_DEFLATE per-column vector [pitch]
+    const double* row_u;    // PF_CONTRACT per-row weights
+    double* zpart;          // [grid_x][pitch] per-CTA column partials
+    double* cntpart;        // PF_COLSTAT [grid_x][pitch]
+    double* sspart;         // PF_SUMSQ [n_slabs * grid_x]
+    const Ctrl* ctrl;
+    int trip;
+};
+
+struct RowPassArgs {
+    PassGeom g;
+    const void* x_in;
+    const double* col_w;    // [pitch]
+    double* t_out;          // [n_rows]
+    double* tpart;          // n_slabs > 1: [n_slabs][n_rows] partial dots
+    double* cpart;          // n_slabs > 1 and masked: [n_slabs][n_rows] observed counts
+    int epi;                // 0: t = v   1: t += v   2: t = (t + v) / div
+    double div;
+    double* d2part;         // optional [grid_x]: sum over rows of (t_old - t_new)^2
+    const Ctrl* ctrl;
+    int trip;
+};
+
+// dtype: 0 = float32, 1 = float64
+cudaError_t launch_colpass(int dtype, bool masked, int flags, const ColPassArgs& a, cudaStream_t s);
+cudaError_t launch_rowpass(int dtype, bool masked, const RowPassArgs& a, cudaStream_t s);
+
+// out[c] = sum_b part[b*stride + c]  (fixed order => bit-reproducible); optionally
+// ss_out[0] = sum of sspart[0..n_ss).
+struct ReduceArgs {
+    const double* part;
+    double* out;
+    int n_cols;
+    int stride;
+    int n_parts;
+    const double* sspart;
+    double* ss_out;
+    int n_ss;
+    const Ctrl* ctrl;
+    int trip;
+};
+cudaError_t launch_reduce_cols(const ReduceArgs& a, cudaStream_t s);
+
+// n_slabs > 1 only: t = epilogue(sum over slabs of tpart), masked scaling included.
+struct RowFinishArgs {
+    long long n_rows;
+    int n_slabs;
+    const double* tpart;
+    const double* cpart;    // nullptr when dense
+    double p_total;
+    double* t_out;
+    int epi;
+    double div;
+    double* d2part;         // [gridDim.x]
+    const Ctrl* ctrl;
+    int trip;
+};
+int row_finish_grid(long long n_rows);
+cudaError_t launch_row_finish(const RowFinishArgs& a, int* grid_out, cudaStream_t s);
+
+}  // namespace tpls

@@ -1,0 +1,46 @@
+// Rank-1 factorisation of the (small) covariance tensor Z, one CTA per coupled
+// tensor, convergence test on the device -- the step the reference delegates to
+//   Z / norm(Z)                                            (cmtf_pls/tpls.py:84)
+//   tensorly parafac(Z, 1, tol, init="svd", normalize_factors=True)[1]
+//                                                          (tpls.py:85-88, cmtf.py:98-102)
+// whose algorithm is restated in oracle/tensorly_standin/.../_cp.py.
+#pragma once
+
+#include "common.cuh"
+
+namespace tpls {
+
+constexpr int kMaxZModes = 7;   // Z modes (X has one more)
+constexpr int kMaxTensors = 8;  // coupled tensors per fit
+constexpr int kRank1Threads = 512;
+
+struct Rank1Task {
+    const double* z;        // [p] sum over samples (already all-reduced)
+    const double* colcnt;   // masked fit: observed rows per column (global); nullptr when dense
+    double n_total;         // masked fit: global sample count
+    int p;
+    int pitch;              // length of wkron (pads are zeroed)
+    int nmodes;
+    int dims[kMaxZModes];
+    double* w[kMaxZModes];  // out: unit weight vector of every mode (contiguous)
+    double* wkron;          // out: kron(w_0, w_1, ...) in the row layout of X
+    double* scratch;        // global workspace (used when it does not fit in shared memory)
+    int use_smem;
+    int nmax;               // largest Gram order needed
+    int* sweeps;            // out (optional): ALS sweeps taken
+};
+
+struct Rank1Args {
+    Rank1Task t[kMaxTensors];
+    int n_tasks;
+    double tol;
+    int normalize_on_break;  // see oracle/.../_cp.py NORMALIZE_ON_BREAK
+    const Ctrl* ctrl;
+    int trip;
+};
+
+// doubles of workspace a task needs, and the Gram order it implies
+size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out);
+cudaError_t launch_rank1(const Rank1Args& a, size_t smem_bytes, cudaStream_t s);
+
+}  // namespace tpls

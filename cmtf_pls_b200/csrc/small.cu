@@ -1,0 +1,237 @@
+// Small kernels -- see small.cuh.
+#include "small.cuh"
+
+#include <algorithm>
+
+namespace tpls {
+
+template <typename XT>
+__global__ void finalize_mean_kernel(const double* colsum, const double* colcnt, const double* n_total, int p, int pitch,
+                                     double* mean_d, XT* native_out, int* miss_flag) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= pitch) return;
+    if (c >= p) {
+        mean_d[c] = 0.0;
+        return;
+    }
+    const double cnt = colcnt[c];
+    const XT m = (XT)(colsum[c] / cnt);  // 0/0 -> NaN for an all-missing column, like np.nanmean
+    mean_d[c] = (double)m;
+    if (native_out) native_out[c] = m;
+    if (cnt < *n_total) atomicOr(miss_flag, 1);
+}
+
+cudaError_t launch_finalize_mean(int dtype, const double* colsum, const double* colcnt, const double* n_total, int p,
+                                 int pitch, double* mean_d, void* native_out, int* miss_flag, cudaStream_t s) {
+    const int blocks = (pitch + 255) / 256;
+    if (dtype == 0)
+        finalize_mean_kernel<float><<<blocks, 256, 0, s>>>(colsum, colcnt, n_total, p, pitch, mean_d,
+                                                           (float*)native_out, miss_flag);
+    else
+        finalize_mean_kernel<double><<<blocks, 256, 0, s>>>(colsum, colcnt, n_total, p, pitch, mean_d,
+                                                            (double*)native_out, miss_flag);
+    return cudaGetLastError();
+}
+
+__global__ void gather_col_kernel(const double* src, long long n, int pitch, int col, double* dst) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i * pitch + col];
+}
+
+cudaError_t launch_gather_col(const double* src, long long n, int pitch, int col, double* dst, cudaStream_t s) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
+    gather_col_kernel<<<blocks, 256, 0, s>>>(src, n, pitch, col, dst);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) normalize_q_kernel(const double* qraw, int m, int pitch, double* qcol,
+                                                          double* qvec, const Ctrl* ctrl, int trip) {
+    if (trip_is_dead(ctrl, trip)) return;
+    __shared__ double red[40];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s = fma(qraw[i], qraw[i], s);
+    const double nrm = sqrt(block_sum(s, red));
+    for (int i = threadIdx.x; i < pitch; i += blockDim.x) {
+        const double q = i < m ? qraw[i] / nrm : 0.0;
+        if (i < m) qcol[i] = q;
+        qvec[i] = q;
+    }
+}
+
+cudaError_t launch_normalize_q(const double* qraw, int m, int pitch, double* qcol, double* qvec, const Ctrl* ctrl,
+                               int trip, cudaStream_t s) {
+    normalize_q_kernel<<<1, 256, 0, s>>>(qraw, m, pitch, qcol, qvec, ctrl, trip);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) sum_small_kernel(const double* parts, int n, double* out, const Ctrl* ctrl,
+                                                        int trip) {
+    if (trip_is_dead(ctrl, trip)) return;
+    __shared__ double red[40];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += parts[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+cudaError_t launch_sum_small(const double* parts, int n, double* out, const Ctrl* ctrl, int trip, cudaStream_t s) {
+    sum_small_kernel<<<1, 256, 0, s>>>(parts, n, out, ctrl, trip);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) stop_kernel(Ctrl* ctrl, int trip, const double* parts, int n, double tol) {
+    if (trip_is_dead(ctrl, trip)) return;
+    __shared__ double red[40];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += parts[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        ctrl->trips_taken = trip + 1;
+        ctrl->last_d2 = s;
+        // trip 0 compares against +inf in the reference (tpls.py:77) and can never stop
+        if (trip >= 1 && sqrt(s) < tol) ctrl->done_trip = trip;
+    }
+}
+
+cudaError_t launch_stop(Ctrl* ctrl, int trip, const double* parts, int n, double tol, cudaStream_t s) {
+    stop_kernel<<<1, 256, 0, s>>>(ctrl, trip, parts, n, tol);
+    return cudaGetLastError();
+}
+
+__global__ void reset_ctrl_kernel(Ctrl* ctrl) {
+    ctrl->done_trip = -1;
+    ctrl->trips_taken = 0;
+    ctrl->last_d2 = 0.0;
+}
+
+cudaError_t launch_reset_ctrl(Ctrl* ctrl, cudaStream_t s) {
+    reset_ctrl_kernel<<<1, 1, 0, s>>>(ctrl);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) multi_dot_kernel(const __grid_constant__ DotPairs d, double* part) {
+    __shared__ double red[40];
+    const int j = blockIdx.y;
+    const double* a = d.a[j];
+    const double* b = d.b[j];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += (long long)gridDim.x * blockDim.x)
+        s = fma(a[i], b[i], s);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * d.npairs + j] = s;
+}
+
+cudaError_t launch_multi_dot(const DotPairs& d, double* part, int* grid_out, cudaStream_t s) {
+    const int gx = (int)std::max<long long>(1, std::min<long long>(148, (d.n + 2047) / 2048));
+    if (grid_out) *grid_out = gx;
+    multi_dot_kernel<<<dim3(gx, d.npairs), 256, 0, s>>>(d, part);
+    return cudaGetLastError();
+}
+
+__global__ void solve_coef_kernel(const double* dots, double* gram, double* coef, int R, int a, const Ctrl* ctrl,
+                                  int* trips_out) {
+    if (threadIdx.x != 0) return;
+    const int k = a + 1;
+    for (int b = 0; b < k; ++b) {
+        gram[b * R + a] = dots[b];
+        gram[a * R + b] = dots[b];
+    }
+    // Cholesky of the leading k x k block (k <= 64), solve gram * x = rhs
+    double Lm[64 * 64];
+    double y[64], x[64];
+    for (int i = 0; i < k; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            double s = gram[i * R + j];
+            for (int q = 0; q < j; ++q) s -= Lm[i * 64 + q] * Lm[j * 64 + q];
+            Lm[i * 64 + j] = (i == j) ? sqrt(s) : s / Lm[j * 64 + j];
+        }
+    }
+    for (int i = 0; i < k; ++i) {
+        double s = dots[k + i];
+        for (int q = 0; q < i; ++q) s -= Lm[i * 64 + q] * y[q];
+        y[i] = s / Lm[i * 64 + i];
+    }
+    for (int i = k - 1; i >= 0; --i) {
+        double s = y[i];
+        for (int q = i + 1; q < k; ++q) s -= Lm[q * 64 + i] * x[q];
+        x[i] = s / Lm[i * 64 + i];
+    }
+    for (int b = 0; b < k; ++b) coef[b * R + a] = x[b];
+    if (trips_out != nullptr && ctrl != nullptr) trips_out[a] = ctrl->trips_taken;
+}
+
+cudaError_t launch_solve_coef(const double* dots, double* gram, double* coef, int R, int a, const Ctrl* ctrl,
+                              int* trips_out, cudaStream_t s) {
+    solve_coef_kernel<<<1, 32, 0, s>>>(dots, gram, coef, R, a, ctrl, trips_out);
+    return cudaGetLastError();
+}
+
+__global__ void lincomb_kernel(const double* T, long long n, long long ldt, const double* coef, int R, int a,
+                               double* out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b <= a; ++b) s = fma(T[b * ldt + i], coef[b * R + a], s);
+        out[i] = s;
+    }
+}
+
+cudaError_t launch_lincomb(const double* T, long long n, long long ldt, const double* coef, int R, int a, double* out,
+                           cudaStream_t s) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
+    lincomb_kernel<<<blocks, 256, 0, s>>>(T, n, ldt, coef, R, a, out);
+    return cudaGetLastError();
+}
+
+__global__ void transpose_out_kernel(const double* in, long long n, long long ld, int cols, double* out) {
+    const long long total = n * cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / cols;
+        const int c = (int)(e - i * cols);
+        out[e] = in[c * ld + i];
+    }
+}
+
+cudaError_t launch_transpose_out(const double* in, long long n, long long ld, int cols, double* out, cudaStream_t s) {
+    const long long total = n * cols;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (total + 255) / 256));
+    transpose_out_kernel<<<blocks, 256, 0, s>>>(in, n, ld, cols, out);
+    return cudaGetLastError();
+}
+
+__global__ void fill_kernel(double* p, long long n, double v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t s) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
+    fill_kernel<<<blocks, 256, 0, s>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+__global__ void count_rescale_kernel(double* z, const double* cnt, double n_total, int p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < p) z[c] = cnt[c] > 0.0 ? z[c] / cnt[c] * n_total : 0.0;
+}
+
+cudaError_t launch_count_rescale(double* z, const double* cnt, double n_total, int p, cudaStream_t s) {
+    count_rescale_kernel<<<(p + 255) / 256, 256, 0, s>>>(z, cnt, n_total, p);
+    return cudaGetLastError();
+}
+
+template <typename XT>
+__global__ void widen_kernel(const XT* src, double* dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (double)src[i];
+}
+
+cudaError_t launch_widen(int dtype, const void* src, double* dst, int n, cudaStream_t s) {
+    if (dtype == 0)
+        widen_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)src, dst, n);
+    else
+        widen_kernel<double><<<(n + 255) / 256, 256, 0, s>>>((const double*)src, dst, n);
+    return cudaGetLastError();
+}
+
+}  // namespace tpls

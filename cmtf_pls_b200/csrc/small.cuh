@@ -1,0 +1,59 @@
+// Small (latency-bound) kernels of the fit: means, Y-side normalisation, stop
+// test, score Gram / regression, linear combinations.
+#pragma once
+
+#include "common.cuh"
+
+namespace tpls {
+
+// mean[c] = colsum[c] / colcnt[c], rounded to the storage type of X (the reference's
+// np.nanmean keeps X's dtype, tpls.py:66); pads -> 0.  miss_flag |= any column with
+// colcnt < n_total.  native_out receives the p means in the storage type.
+cudaError_t launch_finalize_mean(int dtype, const double* colsum, const double* colcnt, const double* n_total, int p,
+                                 int pitch, double* mean_d, void* native_out, int* miss_flag, cudaStream_t s);
+
+// dst[i] = src[i*pitch + col]
+cudaError_t launch_gather_col(const double* src, long long n, int pitch, int col, double* dst, cudaStream_t s);
+
+// q = qraw / ||qraw||  (tpls.py:100-101) -> qcol[m] and qvec[pitch] (pads 0)
+cudaError_t launch_normalize_q(const double* qraw, int m, int pitch, double* qcol, double* qvec, const Ctrl* ctrl,
+                               int trip, cudaStream_t s);
+
+// out[0] = sum parts[0..n)
+cudaError_t launch_sum_small(const double* parts, int n, double* out, const Ctrl* ctrl, int trip, cudaStream_t s);
+
+// stop test of tpls.py:103 on d2 = sum parts: trip >= 1 and sqrt(d2) < tol -> done
+cudaError_t launch_stop(Ctrl* ctrl, int trip, const double* parts, int n, double tol, cudaStream_t s);
+cudaError_t launch_reset_ctrl(Ctrl* ctrl, cudaStream_t s);
+
+// part[bx*npairs + j] = partial dot(a[j], b[j]) over this CTA's rows
+struct DotPairs {
+    const double* a[64];
+    const double* b[64];
+    int npairs;
+    long long n;
+};
+cudaError_t launch_multi_dot(const DotPairs& d, double* part, int* grid_out, cudaStream_t s);
+
+// Regression of u_a on the scores so far (np.linalg.lstsq over the non-zero columns,
+// tpls.py:110-112): dots = [T_b.T_a (b<=a), T_b.u_a (b<=a)]; updates the persistent
+// Gram matrix, solves by Cholesky, writes coef[b*R + a]; also trips_out[a] = ctrl->trips_taken.
+cudaError_t launch_solve_coef(const double* dots, double* gram, double* coef, int R, int a, const Ctrl* ctrl,
+                              int* trips_out, cudaStream_t s);
+
+// s[i] = sum_{b<=a} T_b[i] * coef[b*R + a]      (T column-major, column stride ldt)
+cudaError_t launch_lincomb(const double* T, long long n, long long ldt, const double* coef, int R, int a, double* out,
+                           cudaStream_t s);
+
+// out (n x cols, C order) = in^T where `in` is column-major with column stride ld
+cudaError_t launch_transpose_out(const double* in, long long n, long long ld, int cols, double* out, cudaStream_t s);
+
+cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t s);
+
+// z[c] = cnt[c] > 0 ? z[c] / cnt[c] * n_total : 0     (missingvals.py:18)
+cudaError_t launch_count_rescale(double* z, const double* cnt, double n_total, int p, cudaStream_t s);
+
+// dst[i] = (double)src[i], src in the storage type
+cudaError_t launch_widen(int dtype, const void* src, double* dst, int n, cudaStream_t s);
+
+}  // namespace tpls

@@ -1,0 +1,107 @@
+"""``tPLS`` -- single-tensor N-PLS estimator with the reference's API
+(meyer-lab/cmtf-pls, cmtf_pls/tpls.py:15-189), fitted by the sm_100a CUDA
+library.  Same constructor, methods, attribute names, Mapping protocol and
+error behaviour; inputs may be numpy arrays (staged to the GPU) or torch CUDA
+tensors (used where they are).
+
+Extra, not in the reference: ``device`` / ``process_group`` keyword arguments,
+``n_iter_`` (inner trips per component) and ``stats_`` (timings and bytes of
+the last fit).  With a process group every rank passes its own block of rows of
+X and Y; loadings, Q, coef_, R2X/R2Y and the means are replicated, the scores
+``X_factors[0]`` / ``Y_factors[0]`` are this rank's rows.
+"""
+
+from collections.abc import Mapping
+from copy import copy
+
+import numpy as np
+
+from . import _core
+
+
+class tPLS(Mapping):
+    """Tensor PLS (cmtf_pls/tpls.py:15)."""
+
+    def __init__(self, n_components: int, device=None, process_group=None):
+        super().__init__()
+        self.n_components = n_components
+        self.device = device
+        self.process_group = process_group
+
+    # ---- Mapping protocol (tpls.py:23-42) ----
+    def __getitem__(self, index):
+        if index == 0:
+            return self.X_factors
+        elif index == 1:
+            return self.Y_factors
+        elif index == 2:
+            return self.coef_
+        else:
+            raise IndexError
+
+    def __iter__(self):
+        yield self.X_factors
+        yield self.Y_factors
+        yield self.coef_
+
+    def __len__(self):
+        return 3
+
+    def copy(self):
+        return copy(self)
+
+    # ---- fit (tpls.py:44-120) ----
+    def fit(self, X, Y, tol=1e-8, max_iter=100, verbose=0, overwrite_x=False):
+        assert X.shape[0] == Y.shape[0]
+        assert Y.ndim <= 2, "Only a matrix (2-mode tensor) Y is acceptable."
+        st = _core.run_fit([X], Y, self.n_components, tol, max_iter, device=self.device,
+                           group=self.process_group, overwrite=overwrite_x)
+        self.X_dim = X.ndim
+        self.X_shape = tuple(X.shape)
+        self.Y_shape = (int(Y.shape[0]), 1) if Y.ndim == 1 else tuple(Y.shape)
+        self.X_factors = [st["T"]] + st["W"][0]
+        self.Y_factors = [st["U"], st["Q"]]
+        self.R2X = st["R2X"][0]
+        self.R2Y = st["R2Y"]
+        self.X_hasMiss = st["has_miss"][0]
+        if self.X_hasMiss:
+            print("X has missing values")
+        self._X_ref = X
+        self.X_mean = st["X_mean"][0]
+        self.Y_mean = st["Y_mean"]
+        self.coef_ = st["coef"]
+        self.n_iter_ = st["trips"]
+        self.stats_ = st["stats"]
+        self._device = st["device"]
+        if verbose:
+            for a, k in enumerate(self.n_iter_):
+                if k < max_iter:
+                    print("Comp {}: converged after {} iterations".format(a, k - 1))
+
+    @property
+    def X_miss(self):
+        """Positions of missing values of the training X (tpls.py:64), computed on demand."""
+        X = self._X_ref
+        if _core._is_torch(X):
+            return X.isnan().cpu().numpy()
+        return np.isnan(X)
+
+    # ---- new data (tpls.py:122-186) ----
+    def _scores(self, X):
+        if tuple(self.X_shape[1:]) != tuple(X.shape[1:]):
+            raise ValueError(f"Training X has shape {self.X_shape}, while the new X has shape {tuple(X.shape)}")
+        return _core.run_transform([X], [self.X_mean], [self.X_factors[1:]], self.n_components,
+                                   device=getattr(self, "_device", self.device))
+
+    def predict(self, X):
+        return self._scores(X) @ self.coef_ @ self.Y_factors[1].T + self.Y_mean
+
+    def transform(self, X, Y=None):
+        X_scores = self._scores(X)
+        if Y is not None:
+            Y_scores = _core.y_scores(Y, self.Y_mean, self.Y_shape, X_scores, self.coef_, self.Y_factors[1])
+            return X_scores, Y_scores
+        return X_scores
+
+    def X_reconstructed(self):
+        return _core.rank_r_dense(self.X_factors) + self.X_mean

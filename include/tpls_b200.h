@@ -1,0 +1,129 @@
+/* tpls_b200 -- C ABI of the B200-native tensor-PLS (tPLS / coupled ctPLS) fit path.
+ *
+ * The reference (meyer-lab/cmtf-pls) is pure Python and has no FFI of its own;
+ * its boundary for this path is the estimator API
+ *     tPLS.fit / predict / transform     cmtf_pls/tpls.py:73-186
+ *     ctPLS.fit / predict / transform    cmtf_pls/cmtf.py:85-231
+ * and the fitted attributes listed in SURVEY.md §8 row a15.  Each entry point
+ * below names the reference lines it replaces.  The Python classes in
+ * cmtf_pls_b200/{tpls,cmtf}.py bind these with ctypes and keep the reference's
+ * names, argument meaning and error behaviour.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from tpls_last_error().  No exceptions cross the ABI.
+ *   - data pointers may be HOST or DEVICE pointers (resolved with
+ *     cudaPointerGetAttributes); results are copied into caller-owned buffers.
+ *   - a handle is bound to one device and one stream; calls on one handle must
+ *     not overlap.  Different handles are independent.
+ *   - sample-mode sharding: every rank holds the same rows of every coupled
+ *     tensor and of Y; only small replicated quantities cross devices (NCCL).
+ */
+#ifndef TPLS_B200_H
+#define TPLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tpls_ctx* tpls_handle;
+
+enum { TPLS_F32 = 0, TPLS_F64 = 1 };
+
+/* tpls_set_x flags */
+enum {
+    TPLS_X_MAY_OVERWRITE = 1 /* a DEVICE tensor may be centred/deflated in place (saves one copy of X) */
+};
+
+/* tpls_fit flags */
+enum {
+    TPLS_FIT_NORMALIZE_ON_BREAK = 1 /* the other reading of tensorly's last ALS sweep, oracle/_cp.py */
+};
+
+#define TPLS_MAX_TENSORS 8
+#define TPLS_MAX_MODES 8
+
+int tpls_version(void);
+/* last error of `h`, or of the last failed call without a handle when h == NULL */
+const char* tpls_last_error(tpls_handle h);
+
+/* Context bound to CUDA device `device`.  `cuda_stream` is a cudaStream_t to
+ * enqueue on, or NULL for a private non-blocking stream. */
+int tpls_create(tpls_handle* out, int device, void* cuda_stream);
+int tpls_destroy(tpls_handle h);
+
+/* Multi-GPU (one process per GPU).  Rank 0 obtains a 128-byte id, the caller
+ * broadcasts it by any means, every rank calls tpls_comm_init. */
+int tpls_comm_unique_id(void* id128);
+int tpls_comm_init(tpls_handle h, const void* id128, int rank, int world);
+
+/* Training data.  X number `index` of `n_tensors` coupled tensors, C-ordered,
+ * shape[0] = this rank's sample count; Y is (n, m) float64 C-ordered.
+ * Replaces the array arguments of tPLS.fit (tpls.py:73) / ctPLS.fit (cmtf.py:85).
+ * Caller memory is never modified unless TPLS_X_MAY_OVERWRITE is given. */
+int tpls_set_x(tpls_handle h, int index, const void* x, int dtype, int ndim, const int64_t* shape, int flags);
+int tpls_set_y(tpls_handle h, const double* y, int64_t n, int64_t m);
+
+/* The NIPALS fit: preprocess (tpls.py:44-71) + the component loop (tpls.py:76-120,
+ * cmtf.py:88-140).  n_tensors = how many tpls_set_x slots are in use. */
+int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max_iter, int flags);
+
+/* Fitted state (row a15).  All outputs are C-ordered float64 unless noted. */
+int tpls_get_x_factor(tpls_handle h, int index, int mode, double* out); /* mode 0: scores (n, R); k: (shape[k], R) */
+int tpls_get_y_factor(tpls_handle h, int which, double* out);           /* 0: U (n, R)   1: Q (m, R) */
+int tpls_get_coef(tpls_handle h, double* out);                           /* (R, R), upper triangular */
+int tpls_get_r2x(tpls_handle h, int index, double* out);                 /* (R,) */
+int tpls_get_r2y(tpls_handle h, double* out);                            /* (R,) */
+int tpls_get_x_mean(tpls_handle h, int index, void* out);                /* shape[1:], in X's dtype */
+int tpls_get_y_mean(tpls_handle h, double* out);                         /* (m,) */
+int tpls_get_has_missing(tpls_handle h, int index, int* out);
+int tpls_get_trips(tpls_handle h, int* out);                             /* (R,) inner iterations taken */
+
+typedef struct tpls_stats {
+    double fit_ms;              /* device time of the last tpls_fit (CUDA events on the handle's stream) */
+    double alg_bytes;           /* sum_l s*N_local*P_l*(2*sum(trips) + R + 2)   */
+    double streamed_bytes;      /* bytes of X actually read + written by the passes of the last fit */
+    int64_t kernel_launches;    /* kernels of this library launched by the last fit */
+    int64_t total_trips;
+    int64_t collectives;        /* NCCL all-reduces issued by the last fit */
+    double h2d_bytes;           /* bytes staged host->device by tpls_set_x / tpls_set_y since the last fit */
+} tpls_stats;
+int tpls_get_stats(tpls_handle h, tpls_stats* out);
+
+/* Frees the device copies of X and Y held by the handle (the fitted state stays readable). */
+int tpls_release_data(tpls_handle h);
+
+/* New data through a fitted model: scores (n_new, R) of transform (tpls.py:145-165,
+ * cmtf.py:179-210) -- centre with the training mean, then per component project
+ * (averaging over the coupled tensors) and deflate with the stored loadings.
+ * Stateless with respect to tpls_fit: the model is passed in, so it also serves an
+ * estimator that was pickled or fitted elsewhere.  xs[l]: (n_new, ps[l]) in dtypes[l];
+ * means[l]: ps[l] values in dtypes[l]; wkrons[l]: (R, ps[l]) float64, row a = kron of the
+ * component-a loading vectors.  Rows with NaNs use the masked projection
+ * (missingvals.py:23-38). */
+int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* const* xs, const int* dtypes,
+                   int64_t n_new, const int64_t* ps, const void* const* means, const double* const* wkrons,
+                   double* scores_out);
+
+/* ---- single operators (used by the parity tests and by bench.py's per-kernel roofline) ----
+ * All pointers here are DEVICE pointers; x is (n, p) C-ordered with p*elem a multiple of 16. */
+/* z[p] = sum_i x[i,:] * u[i]                      tpls.py:83  (masked: missingvals.py:7-20, n_total = n) */
+int tpls_op_contract(tpls_handle h, const void* x, int dtype, int64_t n, int64_t p, const double* u, int masked,
+                     double* z_out, float* ms_out, int repeats);
+/* t[i] = sum_c x[i,c] * w[c]                      tpls.py:97-99 (masked: missingvals.py:23-38) */
+int tpls_op_project(tpls_handle h, const void* x, int dtype, int64_t n, int64_t p, const double* w, int masked,
+                    double* t_out, float* ms_out, int repeats);
+/* x -= t (x) w in place, z[p] = sum_i x_new[i,:]*u[i], ss = ||x_new||^2   tpls.py:109 fused with :83 and util.py:7-15 */
+int tpls_op_deflate_contract(tpls_handle h, void* x, int dtype, int64_t n, int64_t p, const double* t,
+                             const double* w, const double* u, int masked, double* z_out, double* ss_out,
+                             float* ms_out, int repeats);
+/* unit weight vectors of z (dims[0..nmodes)), concatenated into w_out; kron into wkron_out[p]  tpls.py:84-90 */
+int tpls_op_rank1(tpls_handle h, const double* z, int nmodes, const int* dims, double tol, int flags, double* w_out,
+                  double* wkron_out, int* sweeps_out, float* ms_out, int repeats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPLS_B200_H */

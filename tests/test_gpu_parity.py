@@ -1,0 +1,185 @@
+"""GPU: the CUDA fit path, called through the estimators -> C ABI, against the
+golden vectors of the reference and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-8 relative for fp64 storage, 1e-4
+for fp32 storage, on loadings, scores, Q, coef_, R2X, R2Y after per-component
+sign alignment; measured per factor column as ||a-b|| / ||b||.
+"""
+
+import numpy as np
+import pytest
+
+from _util import golden_cases, load_golden, aligned_errors, col_err
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-8
+FP32_TOL = 1e-4
+
+
+def _state(est, coupled):
+    if coupled:
+        return dict(T=est.factor_T, W=[f[1:] for f in est.Xs_factors], U=est.Y_factors[0], Q=est.Y_factors[1],
+                    coef=est.coef_, R2X=est.R2Xs, R2Y=est.R2Y)
+    return dict(T=est.X_factors[0], W=[est.X_factors[1:]], U=est.Y_factors[0], Q=est.Y_factors[1],
+                coef=est.coef_, R2X=[est.R2X], R2Y=est.R2Y)
+
+
+def _fit(g, **kw):
+    from cmtf_pls_b200 import tPLS, ctPLS
+    R = int(g["n_components"])
+    if bool(g["coupled"]):
+        est = ctPLS(R)
+        est.fit([x.copy() for x in g["Xs"]], g["Y"].copy(), **kw)
+    else:
+        est = tPLS(R)
+        est.fit(g["Xs"][0].copy(), g["Y"].copy(), **kw)
+    return est
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_fit_matches_reference_golden(case):
+    g = load_golden(case)
+    kw = {"max_iter": 4} if "maxiter" in case else {}
+    est = _fit(g, **kw)
+    tol = FP32_TOL if "f32" in case else FP64_TOL
+    assert est.n_iter_.tolist() == g["trips"].tolist()
+    for k, e in aligned_errors(_state(est, bool(g["coupled"])), g).items():
+        assert e < tol, (case, k, e)
+    means = est.Xs_mean if bool(g["coupled"]) else [est.X_mean]
+    for mine, ref in zip(means, g["X_mean"]):
+        assert mine.dtype == ref.dtype and mine.shape == ref.shape
+        np.testing.assert_allclose(mine, ref, rtol=1e-6 if "f32" in case else 1e-12, atol=1e-7 if "f32" in case else 1e-14,
+                                   equal_nan=True)
+    np.testing.assert_allclose(est.Y_mean, g["Y_mean"], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("case", [c for c in golden_cases() if c in (
+    "t3_60x16x12_m4_r5", "t4_60x8x6x4_m3_r4", "t3_miss_70x12x8_m4_r4", "ct_90x32x16_90x24_m4_r5")])
+def test_transform_predict_match_reference_golden(case):
+    g = load_golden(case)
+    est = _fit(g)
+    coupled = bool(g["coupled"])
+    new = [x.copy() for x in g["Xsnew"]]
+    arg = new if coupled else new[0]
+    assert col_err(est.predict(arg), g["predict_new"]) < FP64_TOL
+    s, v = est.transform(arg, g["Ynew"].copy())
+    assert col_err(s, g["transform_new_X"]) < FP64_TOL
+    assert col_err(v, g["transform_new_Y"]) < FP64_TOL
+    # the caller's arrays are never modified (tpls.py:128,151)
+    for a, b in zip(new, g["Xsnew"]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_fit_leaves_inputs_untouched_and_api_surface():
+    g = load_golden("t3_60x16x12_m4_r5")
+    X, Y = g["Xs"][0].copy(), g["Y"].copy()
+    from cmtf_pls_b200 import tPLS
+    est = tPLS(3)
+    assert est.fit(X, Y) is None
+    assert np.array_equal(X, g["Xs"][0]) and np.array_equal(Y, g["Y"])
+    assert est.X_dim == 3 and est.X_shape == X.shape and est.Y_shape == Y.shape
+    assert [f.shape for f in est.X_factors] == [(60, 3), (16, 3), (12, 3)]
+    assert [f.shape for f in est.Y_factors] == [(60, 3), (4, 3)]
+    assert est[0] is est.X_factors and est[1] is est.Y_factors and est[2] is est.coef_
+    assert est.coef_.shape == (3, 3) and np.allclose(np.tril(est.coef_, -1), 0)
+    assert est.X_hasMiss is False and est.X_miss.shape == X.shape and not est.X_miss.any()
+    assert est.X_reconstructed().shape == X.shape
+    with pytest.raises(ValueError, match="Training X has shape"):
+        est.predict(np.zeros((3, 16, 11)))
+    with pytest.raises(ValueError, match="Training Y has shape"):
+        est.transform(X, np.zeros((60, 5)))
+    c = est.copy()
+    assert c.X_factors is est.X_factors
+
+
+@pytest.mark.parametrize("shape,M,R,dtype", [
+    ((500, 64, 64), 4, 3, np.float64),      # c4-shaped rows (P = 4096), fp64 -> two column slabs
+    ((500, 64, 64), 4, 3, np.float32),      # c4-shaped rows, fp32 -> one slab, 4 groups per lane
+    ((400, 32, 16, 8), 4, 3, np.float32),   # c5-shaped rows (4-way)
+    ((300, 24), 4, 3, np.float64),          # matrix X
+    ((257, 7, 3), 2, 2, np.float32),        # row bytes not a multiple of 16 -> pitched staging
+    ((130, 9, 7), 3, 2, np.float64),        # odd P in fp64 -> pitched staging
+    ((64, 130, 40), 3, 2, np.float32),      # P = 5200 > one slab
+])
+def test_fit_matches_oracle_seeded(shape, M, R, dtype):
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import tPLS
+    X, Y, _ = orc.synthetic(shape, M, 5, error=0.5, seed=215)
+    X = X.astype(dtype)
+    ref = orc.fit([X.copy()], Y.copy(), R, r2_mode="residual")
+    est = tPLS(R)
+    est.fit(X, Y)
+    tol = FP32_TOL if dtype == np.float32 else FP64_TOL
+    assert est.n_iter_.tolist() == ref["trips"].tolist()
+    for k, e in aligned_errors(_state(est, False), ref).items():
+        assert e < tol, (shape, k, e)
+
+
+def test_masked_fit_matches_oracle_seeded():
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import tPLS
+    rng = np.random.default_rng(3)
+    for dtype in (np.float64, np.float32):
+        X, Y, _ = orc.synthetic((600, 64, 32), 4, 8, error=0.5, seed=215)
+        X[rng.random(X.shape) < 0.2] = np.nan
+        X = X.astype(dtype)
+        ref = orc.fit([X.copy()], Y.copy(), 3, r2_mode="residual")
+        est = tPLS(3)
+        est.fit(X, Y)
+        assert est.X_hasMiss
+        assert est.n_iter_.tolist() == ref["trips"].tolist()
+        tol = FP32_TOL if dtype == np.float32 else FP64_TOL
+        for k, e in aligned_errors(_state(est, False), ref).items():
+            assert e < tol, (dtype, k, e)
+
+
+def test_torch_cuda_input_is_used_in_place_and_not_modified():
+    import torch
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import tPLS
+    X, Y, _ = orc.synthetic((300, 16, 8), 3, 4, error=0.3, seed=1)
+    ref = orc.fit([X.copy()], Y.copy(), 2, r2_mode="residual")
+    Xd = torch.from_numpy(X).cuda()
+    Yd = torch.from_numpy(Y).cuda()
+    est = tPLS(2)
+    est.fit(Xd, Yd)
+    assert torch.equal(Xd.cpu(), torch.from_numpy(X))
+    assert est.stats_["h2d_bytes"] == 0
+    for k, e in aligned_errors(_state(est, False), ref).items():
+        assert e < FP64_TOL, (k, e)
+    # in-place variant: same numbers, X is consumed
+    est2 = tPLS(2)
+    est2.fit(Xd, Yd, overwrite_x=True)
+    assert not torch.equal(Xd.cpu(), torch.from_numpy(X))
+    assert np.array_equal(est2.X_factors[0], est.X_factors[0])
+
+
+def test_large_shape_properties_fp32():
+    """BASELINE-sized rows (P = 4096) at a sample count the oracle cannot follow:
+    size-independent properties -- unit-norm loadings, monotone R2, the transform of
+    the training data reproduces the scores, nested components."""
+    import torch
+    from cmtf_pls_b200 import ctPLS
+    torch.manual_seed(0)
+    n, L = 40000, 6
+    T = torch.randn(n, L, dtype=torch.float64, device="cuda")
+    A = [torch.randn(64, L, dtype=torch.float64, device="cuda") for _ in range(4)]
+    yf = torch.randn(4, L, dtype=torch.float64, device="cuda")
+    X0 = (torch.einsum("ir,jr,kr->ijk", T, A[0], A[1]) + torch.randn(n, 64, 64, dtype=torch.float64, device="cuda")).float()
+    X1 = (torch.einsum("ir,jr,kr->ijk", T, A[2], A[3]) + torch.randn(n, 64, 64, dtype=torch.float64, device="cuda")).float()
+    Y = T @ yf.T + 0.5 * torch.randn(n, 4, dtype=torch.float64, device="cuda")
+    est = ctPLS(4)
+    est.fit([X0, X1], Y)
+    for fs in est.Xs_factors:
+        for w in fs[1:]:
+            np.testing.assert_allclose(np.linalg.norm(w, axis=0), 1.0, rtol=1e-7)
+    np.testing.assert_allclose(np.linalg.norm(est.Y_factors[1], axis=0), 1.0, rtol=1e-7)
+    assert np.all(np.diff(est.R2Y) >= 0) and np.all(np.diff(est.R2Xs[0]) >= 0) and np.all(np.diff(est.R2Xs[1]) >= 0)
+    assert est.R2Y[-1] > 0.9
+    s = est.transform([X0[:5000], X1[:5000]])
+    assert col_err(s, est.factor_T[:5000]) < 1e-4
+    est2 = ctPLS(2)
+    est2.fit([X0, X1], Y)
+    assert col_err(est2.factor_T, est.factor_T[:, :2]) < 1e-9
+    assert est.stats_["alg_bytes"] > 0 and est.stats_["fit_ms"] > 0
