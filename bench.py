@@ -1,0 +1,376 @@
+"""Benchmark of the tensor-PLS fit path (BASELINE.json metric: tPLS fit time and
+effective X-stream GB/s against the HBM roofline, 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is ONE complete fit (all components) of the workload on synthetic data
+already resident in HBM.  Workload = BASELINE.json configs[3]: a coupled pair of
+1M x 64 x 64 fp32 tensors sharing the sample mode, Y 1M x 4, 10 components; the
+sample mode is sharded over the N ranks (strong scaling: the total stays 1M).
+M, the latent rank and the noise level are not fixed by BASELINE.json; this
+file uses M=4, L=12, error=1.0 and prints them in `config`.
+
+`value`   = effective X-stream bandwidth  B_alg / t_fit  summed over ranks, with
+            B_alg = sum_l s*N*P_l*(2*sum(trips) + R + 2)  (SURVEY.md §8d);
+`e2e`     = the same metric through the estimator API with HOST (pinned) arrays:
+            host->device copy of X and Y and device->host copy of the fitted state
+            are inside the timed region;
+`roofline`= the dominant streaming kernel's algorithmic bytes per launch over its
+            mean launch duration (CUDA events on the launching stream, collected
+            during the timed steps) against MEASURED_PEAKS.json;
+`cpu_baseline` = the oracle port of the reference's numpy fit on a bounded
+            sample of the same workload, on the box's host cores.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tPLS fit effective X-stream bandwidth (B_alg / fit time)"
+UNIT = "GB/s"
+N_TOTAL = 1_000_000
+DIMS = (64, 64)
+M, LATENT, ERROR, R = 4, 12, 1.0, 10
+CPU_SAMPLE_ROWS = 4096
+CPU_SAMPLE_R = 3
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------
+# synthetic inputs
+# --------------------------------------------------------------------------
+def make_shard_device(n_rows, rank, device, rows_offset=0):
+    """CP-structured coupled pair in the spirit of import_synthetic (synthetic.py:59-77):
+    shared scores T, per-tensor mode factors, Gaussian noise; generated on the device
+    (a 32.8 GB numpy draw is impractical).  Mode factors are identical on all ranks."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(215)
+    yf = torch.randn(M, LATENT, generator=g, device=device, dtype=torch.float64)
+    modes = [[torch.randn(d, LATENT, generator=g, device=device, dtype=torch.float64) for d in DIMS] for _ in range(2)]
+    g.manual_seed(1000 + rank)
+    T = torch.randn(n_rows, LATENT, generator=g, device=device, dtype=torch.float64)
+    Xs = []
+    for a, b in modes:
+        kr = (a[:, None, :] * b[None, :, :]).reshape(-1, LATENT).float()      # (P, L)
+        X = torch.empty(n_rows, *DIMS, dtype=torch.float32, device=device)
+        Xf = X.view(n_rows, -1)
+        step = 65536
+        for r0 in range(0, n_rows, step):
+            r1 = min(n_rows, r0 + step)
+            blk = T[r0:r1].float() @ kr.T
+            blk += ERROR * torch.randn(r1 - r0, kr.shape[0], generator=g, device=device, dtype=torch.float32)
+            Xf[r0:r1] = blk
+        Xs.append(X)
+    Y = T @ yf.T + ERROR * torch.randn(n_rows, M, generator=g, device=device, dtype=torch.float64)
+    return Xs, Y
+
+
+def make_sample_host(n_rows, seed=215):
+    rng = np.random.default_rng(seed)
+    T = rng.normal(size=(n_rows, LATENT))
+    yf = rng.normal(size=(M, LATENT))
+    Xs = []
+    for _ in range(2):
+        a, b = rng.normal(size=(DIMS[0], LATENT)), rng.normal(size=(DIMS[1], LATENT))
+        X = np.einsum("ir,jr,kr->ijk", T, a, b) + rng.normal(0, ERROR, size=(n_rows,) + DIMS)
+        Xs.append(X.astype(np.float32))
+    Y = T @ yf.T + rng.normal(0, ERROR, size=(n_rows, M))
+    return Xs, Y
+
+
+def alg_bytes(n_rows, trips_total, n_comp):
+    p = DIMS[0] * DIMS[1]
+    return 2 * 4.0 * n_rows * p * (2.0 * trips_total + n_comp + 2)
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            f = [c.strip() for c in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's numpy fit on a bounded sample
+# --------------------------------------------------------------------------
+def cpu_fit_once(Xs, Y):
+    from oracle import tpls_oracle as orc
+    t0 = time.perf_counter()
+    st = orc.fit([x.copy() for x in Xs], Y.copy(), CPU_SAMPLE_R, r2_mode="reference")
+    dt = time.perf_counter() - t0
+    trips = int(st["trips"].sum())
+    return dt, trips, alg_bytes(Xs[0].shape[0], trips, CPU_SAMPLE_R)
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        n = 1
+    return int(n), len(os.sched_getaffinity(0))
+
+
+def cpu_baseline_block(value, cores, affinity):
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": (f"oracle/tpls_oracle.fit (numpy restatement of cmtf_pls ctPLS.fit incl. its dense R2X/R2Y "
+                       f"re-evaluation) on 2 x [{CPU_SAMPLE_ROWS} x 64 x 64] fp32 + Y {CPU_SAMPLE_ROWS} x {M}, "
+                       f"{CPU_SAMPLE_R} components; BLAS threads {cores}, affinity {affinity}; the contraction is "
+                       f"single-threaded numpy einsum as in the reference")}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Xs, Y = make_sample_host(CPU_SAMPLE_ROWS)
+    cores, aff = cpu_threads()
+    for _ in range(args.warmup):
+        cpu_fit_once(Xs, Y)
+    t_tot, b_tot, trips = 0.0, 0.0, 0
+    for _ in range(args.steps):
+        dt, tr, b = cpu_fit_once(Xs, Y)
+        t_tot += dt
+        b_tot += b
+        trips = tr
+    val = b_tot / t_tot / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[3] shape (coupled pair x64x64 fp32, M=4), bounded CPU sample",
+                   "rows": CPU_SAMPLE_ROWS, "components": CPU_SAMPLE_R, "latent": LATENT, "error": ERROR, "trips": trips},
+        "cpu_baseline": cpu_baseline_block(val, cores, aff),
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cmtf_pls_b200 import ctPLS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = True
+    n_total = args.rows or N_TOTAL
+    base, rem = divmod(n_total, world)
+    n_loc = base + (1 if rank < rem else 0)
+
+    Xs, Y = make_shard_device(n_loc, rank, dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    est = ctPLS(R, device=local, process_group=group)
+    for _ in range(args.warmup):
+        est.fit(Xs, Y)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, prof = 0, None
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        est.fit(Xs, Y, profile=True)
+        launches += est.stats_["kernel_launches"]
+        p = est.profile_
+        if prof is None:
+            prof = p
+        else:
+            for k in prof:
+                for f in ("ms", "launches", "bytes"):
+                    prof[k][f] += p[k][f]
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    trips = int(est.n_iter_.sum())
+    tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    bb = torch.tensor([alg_bytes(n_loc, trips, R)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bb, op=dist.ReduceOp.SUM)
+    ms_step = tt.item() / args.steps
+    value = bb.item() / (ms_step * 1e-3) / 1e9
+    fit_ms_device = est.stats_["fit_ms"]
+
+    # ---- end to end through the estimator API with pinned host arrays ----
+    e2e = None
+    n_iter_resident = est.n_iter_.tolist()
+    try:
+        Xh = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in Xs]
+        for h, d in zip(Xh, Xs):
+            h.copy_(d)
+        Yh = torch.empty(Y.shape, dtype=Y.dtype, pin_memory=True)
+        Yh.copy_(Y)
+        torch.cuda.synchronize()
+        n_iter_resident = est.n_iter_.tolist()
+        del Xs, est                                # the estimator keeps a reference to its training arrays
+        torch.cuda.empty_cache()
+        Xn, Yn = [h.numpy() for h in Xh], Yh.numpy()
+        est2 = ctPLS(R, device=local, process_group=group)
+        est2.fit(Xn, Yn)                         # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            est2.fit(Xn, Yn)
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        trips2 = int(est2.n_iter_.sum())
+        t2 = torch.tensor([dt], dtype=torch.float64, device=dev)
+        b2 = torch.tensor([alg_bytes(n_loc, trips2, R)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(b2, op=dist.ReduceOp.SUM)
+        h2d = sum(x.nbytes for x in Xn) + Yn.nbytes
+        d2h = 8 * (2 * n_loc * R + sum(DIMS) * 2 * R + M * R + R * R + 3 * R + M) + 4 * 2 * DIMS[0] * DIMS[1]
+        e2e = {"value": b2.item() / t2.item() / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "s_per_step": t2.item(), "steps": args.e2e_steps,
+               "timing": "host clock around est.fit(numpy pinned), barrier + synchronize on both sides, max over ranks"}
+    except Exception as exc:  # noqa: BLE001
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(exc)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    dom = max(("contract", "project", "deflate_contract"), key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    ach = d["bytes"] / d["launches"] / (d["ms"] / d["launches"] * 1e-3) / 1e9 if d["launches"] else None
+    kernel_ms = sum(v["ms"] for v in prof.values())
+    roofline = {
+        "bound": "hbm", "kernel": {"contract": "colpass_kernel<PF_CONTRACT>", "project": "rowpass_kernel",
+                                   "deflate_contract": "colpass_kernel<PF_DEFLATE|PF_WRITE|PF_CONTRACT|PF_SUMSQ>"}[dom],
+        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None,
+        "peak_source": peak_src,
+        "bytes_per_launch": d["bytes"] / max(1, d["launches"]), "ms_per_launch": d["ms"] / max(1, d["launches"]),
+        "share_of_step": d["ms"] / (ms_total if world == 1 else kernel_ms),
+        "per_class": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                          "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None}
+                      for k, v in prof.items()},
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        Xc, Yc = make_sample_host(CPU_SAMPLE_ROWS)
+        cores, aff = cpu_threads()
+        dt, tr, b = cpu_fit_once(Xc, Yc)
+        cpu = cpu_baseline_block(b / dt / 1e9, cores, aff)
+        cpu["seconds"] = dt
+        cpu["trips"] = tr
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: coupled pair 2 x [1M x 64 x 64] fp32 + Y 1M x 4, 10 components, "
+                               "sample mode sharded over the ranks",
+                   "rows_total": n_total, "rows_per_gpu": n_loc, "responses": M, "latent": LATENT, "error": ERROR,
+                   "components": R, "storage": "fp32 X, fp64 accumulators/vectors", "tol": 1e-8, "max_iter": 100,
+                   "trips": n_iter_resident, "trips_total": trips,
+                   "l2": "every pass streams 2 x %.1f GB per GPU, far larger than the 126 MB L2 (no flush needed)"
+                         % (4.0 * n_loc * 4096 / 1e9),
+                   "fraction_of_hbm_peak": value / (world * peak), "fit_ms_device_last": fit_ms_device},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=0, help="override the total sample count (debugging)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,5 +11,16 @@ include/tpls_b200.h.  There is no CPU fallback.
 from .tpls import tPLS
 from .cmtf import ctPLS
 
+
+
+def trim_memory():
+    """Return the device buffers cached between fits (one working copy of X per
+    engine) to the CUDA driver."""
+    from . import _core
+    for eng in _core._engines.values():
+        if eng.h is not None:
+            eng.trim()
+
+
 __version__ = "0.1.0"
-__all__ = ["tPLS", "ctPLS"]
+__all__ = ["tPLS", "ctPLS", "trim_memory"]

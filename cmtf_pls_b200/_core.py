@@ -38,11 +38,28 @@ def _device_of(arrays, default=None) -> int:
     return 0
 
 
+def _torch_stream_handle(device: int) -> int:
+    """cudaStream_t of torch's current stream on ``device`` so that our kernels are
+    ordered after whatever produced the input tensors; the legacy default stream
+    (handle 0) is passed as cudaStreamLegacy (0x1).  0 = no torch / no CUDA: the
+    library then creates a private stream."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            hnd = int(torch.cuda.current_stream(device).cuda_stream)
+            return hnd if hnd != 0 else 1
+    except Exception:
+        pass
+    return 0
+
+
 def get_engine(device: int) -> _engine.Engine:
-    eng = _engines.get(device)
+    stream = _torch_stream_handle(device)
+    key = (device, stream)
+    eng = _engines.get(key)
     if eng is None or eng.h is None:
-        eng = _engine.Engine(device)
-        _engines[device] = eng
+        eng = _engine.Engine(device, stream or None)
+        _engines[key] = eng
     return eng
 
 
@@ -91,7 +108,7 @@ def np_dtype_of(a):
     return np.dtype(str(a.dtype).replace("torch.", ""))
 
 
-def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwrite=False, flags=0):
+def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwrite=False, flags=0, profile=False):
     """Upload (or adopt) the shards, run the device fit, fetch the state.
 
     Returns a dict with T, W (list per tensor of loading matrices), U, Q, coef,
@@ -109,6 +126,8 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
         fl = _engine.X_MAY_OVERWRITE if (overwrite and _is_torch(X) and X.is_cuda) else 0
         eng.set_x(i, X, fl)
     eng.set_y(Y2)
+    if profile:
+        flags |= _engine.FIT_PROFILE
     try:
         eng.fit(len(Xs), R, tol, max_iter, flags)
         out = dict(
@@ -124,6 +143,7 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
             has_miss=[eng.has_missing(i) for i in range(len(Xs))],
             trips=eng.trips(R),
             stats=eng.stats(),
+            profile=eng.profile() if profile else None,
             device=dev,
         )
     finally:

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libtpls_b200.so")
 F32, F64 = 0, 1
 X_MAY_OVERWRITE = 1
 FIT_NORMALIZE_ON_BREAK = 1
+FIT_PROFILE = 2
 MAX_TENSORS = 8
 MAX_MODES = 8
 
@@ -39,6 +40,13 @@ class Stats(C.Structure):
         ("collectives", C.c_int64),
         ("h2d_bytes", C.c_double),
     ]
+
+
+KERNEL_CLASSES = ["colstat", "contract", "project", "deflate_contract", "residual", "rank1", "yside", "other"]
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("bytes", C.c_double * 8)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/tpls_b200.h
@@ -64,7 +72,9 @@ SIGNATURES = {
     "tpls_get_has_missing": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int)]),
     "tpls_get_trips": (C.c_int, [_H, _P]),
     "tpls_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
+    "tpls_get_profile": (C.c_int, [_H, C.POINTER(Profile)]),
     "tpls_release_data": (C.c_int, [_H]),
+    "tpls_trim": (C.c_int, [_H]),
     "tpls_transform": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(C.c_int), C.c_int64,
                                  C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P]),
     "tpls_op_contract": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P, C.POINTER(C.c_float), C.c_int]),
@@ -213,6 +223,14 @@ class Engine:
         s = Stats()
         self._ck(self.lib.tpls_get_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def profile(self) -> dict:
+        p = Profile()
+        self._ck(self.lib.tpls_get_profile(self.h, C.byref(p)))
+        return {k: dict(ms=p.ms[i], launches=p.launches[i], bytes=p.bytes[i]) for i, k in enumerate(KERNEL_CLASSES)}
+
+    def trim(self):
+        self._ck(self.lib.tpls_trim(self.h))
 
     def release_data(self):
         self._ck(self.lib.tpls_release_data(self.h))

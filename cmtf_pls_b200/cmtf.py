@@ -44,14 +44,14 @@ class ctPLS(Mapping):
         return copy(self)
 
     # ---- fit (cmtf.py:44-140) ----
-    def fit(self, Xs, Y, tol=1e-8, max_iter=100, verbose=0, overwrite_x=False):
+    def fit(self, Xs, Y, tol=1e-8, max_iter=100, verbose=0, overwrite_x=False, profile=False):
         assert isinstance(Xs, list)
         for X in Xs:
             assert X.shape[0] == Y.shape[0]
             assert X.ndim >= 2
         assert Y.ndim <= 2, "Only a matrix (2-mode tensor) Y is acceptable."
         st = _core.run_fit(Xs, Y, self.n_components, tol, max_iter, device=self.device,
-                           group=self.process_group, overwrite=overwrite_x)
+                           group=self.process_group, overwrite=overwrite_x, profile=profile)
         self.Xs_len = len(Xs)
         self.Xs_dim = [X.ndim for X in Xs]
         self.Xs_shape = [tuple(X.shape) for X in Xs]
@@ -71,6 +71,7 @@ class ctPLS(Mapping):
         self._Xs_ref = Xs
         self.n_iter_ = st["trips"]
         self.stats_ = st["stats"]
+        self.profile_ = st["profile"]
         self._device = st["device"]
         if verbose:
             for a, k in enumerate(self.n_iter_):

@@ -37,7 +37,8 @@ struct Tensor {
     void* owned = nullptr;      // library-owned staging / work allocation(s)
     void* owned2 = nullptr;
     bool masked = false;
-    PassGeom g{};
+    PassGeom g{};   // column passes
+    PassGeom gr{};  // row passes (depends on `masked`, fixed after the statistics pass)
     // per-fit device buffers
     double *zpart = nullptr, *cntpart = nullptr, *sspart = nullptr;
     double *mean_d = nullptr, *wkron = nullptr, *tpart = nullptr, *cpart = nullptr, *r1_scratch = nullptr;
@@ -67,7 +68,7 @@ struct tpls_ctx {
     long long n = 0;
     int m = 0, pitch_y = 0;
     double *y_src = nullptr, *y_work = nullptr;
-    PassGeom gy{};
+    PassGeom gy{}, gy_row{};
     double h2d_bytes = 0;
     // fit state
     int L = 0, R = 0;
@@ -81,6 +82,14 @@ struct tpls_ctx {
     int* ymiss_flag = nullptr;
     Ctrl* ctrl = nullptr;
     int* h_done = nullptr;  // pinned
+    // cache of the large X-sized device buffers, reused across fits (cudaMalloc/cudaFree of tens of GB
+    // costs hundreds of ms); tpls_trim() returns them to the driver
+    struct PoolBuf {
+        void* p;
+        size_t bytes;
+        bool used;
+    };
+    std::vector<PoolBuf> pool;
     size_t arena_doubles = 0, off_ysum = 0, off_ycnt = 0, off_n = 0, off_stats_end = 0, off_zcat = 0, zcat_len = 0,
            off_q = 0, off_d2 = 0, off_dots = 0, off_ss = 0, ss_len = 0;
     std::vector<double> r2x[TPLS_MAX_TENSORS];
@@ -88,6 +97,16 @@ struct tpls_ctx {
     std::vector<int> trips;
     double n_total = 0;
     tpls_stats stats{};
+    // optional per-kernel-class timing (TPLS_FIT_PROFILE): event pairs on the launching stream
+    bool profile = false;
+    struct ProfRec {
+        int cls;
+        cudaEvent_t a, b;
+        double bytes;
+    };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    tpls_profile prof_sum{};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_trip[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -141,15 +160,49 @@ int dev_alloc(tpls_handle h, void** out, size_t bytes, std::vector<void*>* track
     return 0;
 }
 
+void pool_trim(tpls_handle h) {
+    std::vector<tpls_ctx::PoolBuf> keep;
+    for (auto& b : h->pool) {
+        if (b.used)
+            keep.push_back(b);
+        else
+            cudaFree(b.p);
+    }
+    h->pool.swap(keep);
+}
+
+int pool_get(tpls_handle h, void** out, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    for (auto& b : h->pool)
+        if (!b.used && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 + (1u << 20)) {
+            b.used = true;
+            *out = b.p;
+            return 0;
+        }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim(h);
+        CK(cudaMalloc(out, bytes));
+    }
+    h->pool.push_back({*out, bytes, true});
+    return 0;
+}
+
+void pool_put(tpls_handle h, void* p) {
+    for (auto& b : h->pool)
+        if (b.p == p) b.used = false;
+}
+
 void free_fit(tpls_handle h) {
     for (void* p : h->fit_allocs) cudaFree(p);
     h->fit_allocs.clear();
     h->fitted = false;
 }
 
-void free_tensor(Tensor& t) {
-    if (t.owned) cudaFree(t.owned);
-    if (t.owned2) cudaFree(t.owned2);
+void free_tensor(tpls_handle h, Tensor& t) {
+    if (t.owned) pool_put(h, t.owned);
+    if (t.owned2) pool_put(h, t.owned2);
     t = Tensor();
 }
 
@@ -160,19 +213,74 @@ int allreduce(tpls_handle h, double* buf, size_t count) {
     return 0;
 }
 
+// ---- per-class timing ----
+cudaEvent_t prof_event(tpls_handle h) {
+    cudaEvent_t e = nullptr;
+    if (!h->ev_pool.empty()) {
+        e = h->ev_pool.back();
+        h->ev_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+
+struct ProfScope {
+    tpls_handle h;
+    bool on;
+    tpls_ctx::ProfRec r{};
+    ProfScope(tpls_handle h_, int cls, double bytes) : h(h_), on(h_->profile) {
+        if (!on) return;
+        r.cls = cls;
+        r.bytes = bytes;
+        r.a = prof_event(h);
+        r.b = prof_event(h);
+        cudaEventRecord(r.a, h->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(r.b, h->stream);
+        h->prof.push_back(r);
+    }
+};
+
+void prof_collect(tpls_handle h) {
+    h->prof_sum = tpls_profile{};
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        h->prof_sum.ms[r.cls] += ms;
+        h->prof_sum.launches[r.cls] += 1;
+        h->prof_sum.bytes[r.cls] += r.bytes;
+        h->ev_pool.push_back(r.a);
+        h->ev_pool.push_back(r.b);
+    }
+    h->prof.clear();
+}
+
 // ---- pass wrappers that keep the launch / byte counters ----
-int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a) {
+int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a, int cls = -1) {
+    const double bytes = (double)a.g.n_rows * a.g.pitch * a.g.elem_size * ((flags & PF_WRITE) ? 2.0 : 1.0);
+    if (cls < 0) {
+        cls = TPLS_K_OTHER;
+        if (flags == PF_COLSTAT) cls = TPLS_K_COLSTAT;
+        if (flags == PF_CONTRACT) cls = TPLS_K_CONTRACT;
+        if (flags == (PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ)) cls = TPLS_K_DEFLATE_CONTRACT;
+        if (flags == (PF_DEFLATE | PF_SUMSQ)) cls = TPLS_K_RESIDUAL;
+    }
+    ProfScope ps(h, cls, bytes);
     CK(launch_colpass(dtype, masked, flags, a, h->stream));
     h->stats.kernel_launches++;
-    const double bytes = (double)a.g.n_rows * a.g.pitch * a.g.elem_size;
-    h->stats.streamed_bytes += bytes * ((flags & PF_WRITE) ? 2.0 : 1.0);
+    if (cls != TPLS_K_YSIDE) h->stats.streamed_bytes += bytes;
     return 0;
 }
 
-int row_pass(tpls_handle h, int dtype, bool masked, RowPassArgs& a) {
+int row_pass(tpls_handle h, int dtype, bool masked, RowPassArgs& a, int cls = TPLS_K_PROJECT) {
+    const double bytes = (double)a.g.n_rows * a.g.pitch * a.g.elem_size;
+    ProfScope ps(h, cls, bytes);
     CK(launch_rowpass(dtype, masked, a, h->stream));
     h->stats.kernel_launches++;
-    h->stats.streamed_bytes += (double)a.g.n_rows * a.g.pitch * a.g.elem_size;
+    if (cls != TPLS_K_YSIDE) h->stats.streamed_bytes += bytes;
     if (a.g.n_slabs > 1) {
         RowFinishArgs f{};
         f.n_rows = a.g.n_rows;
@@ -264,7 +372,8 @@ int tpls_destroy(tpls_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_fit(h);
-    for (auto& t : h->x) free_tensor(t);
+    for (auto& t : h->x) free_tensor(h, t);
+    pool_trim(h);
     if (h->y_src) cudaFree(h->y_src);
     if (h->y_work) cudaFree(h->y_work);
     if (h->comm) g_nccl.CommDestroy(h->comm);
@@ -272,6 +381,7 @@ int tpls_destroy(tpls_handle h) {
     cudaEventDestroy(h->ev_start);
     cudaEventDestroy(h->ev_stop);
     for (auto& e : h->ev_trip) cudaEventDestroy(e);
+    for (auto& e : h->ev_pool) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -312,7 +422,7 @@ int tpls_set_x(tpls_handle h, int index, const void* x, int dtype, int ndim, con
     if (dtype != TPLS_F32 && dtype != TPLS_F64) return fail(h, "tpls_set_x: dtype must be TPLS_F32 or TPLS_F64");
     CK(cudaSetDevice(h->device));
     Tensor& t = h->x[index];
-    free_tensor(t);
+    free_tensor(h, t);
     t.dtype = dtype;
     t.elem = dtype == TPLS_F32 ? 4 : 8;
     t.ndim = ndim;
@@ -334,11 +444,11 @@ int tpls_set_x(tpls_handle h, int index, const void* x, int dtype, int ndim, con
         if (flags & TPLS_X_MAY_OVERWRITE) {
             t.work = const_cast<void*>(x);
         } else {
-            TRY(dev_alloc(h, &t.owned, bytes, nullptr));
+            TRY(pool_get(h, &t.owned, bytes));
             t.work = t.owned;
         }
     } else {
-        TRY(dev_alloc(h, &t.owned, bytes, nullptr));
+        TRY(pool_get(h, &t.owned, bytes));
         if (t.pitch != t.p) CK(cudaMemsetAsync(t.owned, 0, bytes, h->stream));
         CK(cudaMemcpy2DAsync(t.owned, (size_t)t.pitch * t.elem, x, (size_t)t.p * t.elem, (size_t)t.p * t.elem, t.n,
                              cudaMemcpyDefault, h->stream));
@@ -382,6 +492,7 @@ static int alloc_fit(tpls_handle h, int L, int R) {
     h->L = L;
     h->R = R;
     h->gy = make_geom(n, h->m, h->pitch_y, 8, h->sm_count);
+    h->gy_row = make_row_geom(n, h->m, h->pitch_y, 8, h->sm_count, false);
     // arena layout
     size_t off = 0;
     for (int l = 0; l < L; ++l) {
@@ -513,6 +624,8 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     h->stats = tpls_stats{};
     h->stats.h2d_bytes = h2d;
     h->h2d_bytes = 0;
+    h->profile = (flags & TPLS_FIT_PROFILE) != 0;
+    h->prof.clear();
     TRY(alloc_fit(h, L, R));
     CK(cudaEventRecord(h->ev_start, st));
     const long long n = h->n;
@@ -536,7 +649,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         c.x_in = h->y_src;
         c.zpart = h->zpart_y;
         c.cntpart = h->cntpart_y;
-        TRY(col_pass(h, TPLS_F64, true, PF_COLSTAT, c));
+        TRY(col_pass(h, TPLS_F64, true, PF_COLSTAT, c, TPLS_K_YSIDE));
         TRY(reduce_cols(h, h->zpart_y, A + h->off_ysum, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, nullptr, 0));
         TRY(reduce_cols(h, h->cntpart_y, A + h->off_ycnt, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, nullptr, 0));
         CK(launch_fill(A + h->off_n, 1, (double)n, st));
@@ -558,7 +671,11 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             CK(cudaMemcpyAsync(&flagsh[l], h->x[l].miss_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h->n_total, A + h->off_n, sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        for (int l = 0; l < L; ++l) h->x[l].masked = flagsh[l] != 0;
+        for (int l = 0; l < L; ++l) {
+            Tensor& t = h->x[l];
+            t.masked = flagsh[l] != 0;
+            t.gr = make_row_geom(n, t.p, t.pitch, t.elem, h->sm_count, t.masked);
+        }
     }
 
     // ---- centre Y (tpls.py:71), u0 = first column (tpls.py:78) ----
@@ -570,7 +687,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         c.x_out = h->y_work;
         c.col_w = h->ymean_d;
         c.sspart = h->sspart_y;
-        TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c));
+        TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c, TPLS_K_YSIDE));
         TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
         CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U, st));
         h->stats.kernel_launches++;
@@ -637,6 +754,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 ra.ctrl = h->ctrl;
                 ra.trip = trip;
                 for (int l = 0; l < L; ++l) fill_rank1_task(h, h->x[l], a, ra.t[l], r1_use_smem);
+                ProfScope ps(h, TPLS_K_RANK1, 0.0);
                 CK(launch_rank1(ra, r1_smem, st));
                 h->stats.kernel_launches++;
             }
@@ -644,7 +762,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             for (int l = 0; l < L; ++l) {
                 Tensor& t = h->x[l];
                 RowPassArgs r{};
-                r.g = t.g;
+                r.g = t.gr;
                 r.x_in = t.work;
                 r.col_w = t.wkron + (size_t)a * t.pitch;
                 r.t_out = Ta;
@@ -665,13 +783,13 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 c.zpart = h->zpart_y;
                 c.ctrl = h->ctrl;
                 c.trip = trip;
-                TRY(col_pass(h, TPLS_F64, false, PF_CONTRACT, c));
+                TRY(col_pass(h, TPLS_F64, false, PF_CONTRACT, c, TPLS_K_YSIDE));
                 TRY(reduce_cols(h, h->zpart_y, A + h->off_q, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
                 TRY(allreduce(h, A + h->off_q, h->pitch_y));
                 CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, trip, st));
                 h->stats.kernel_launches++;
                 RowPassArgs r{};
-                r.g = h->gy;
+                r.g = h->gy_row;
                 r.x_in = h->y_work;
                 r.col_w = h->qvec;
                 r.t_out = Ua;
@@ -680,8 +798,8 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 r.d2part = h->d2part;
                 r.ctrl = h->ctrl;
                 r.trip = trip;
-                TRY(row_pass(h, TPLS_F64, false, r));
-                const int nd2 = d2_grid(h->gy);
+                TRY(row_pass(h, TPLS_F64, false, r, TPLS_K_YSIDE));
+                const int nd2 = d2_grid(h->gy_row);
                 if (h->world > 1) {
                     CK(launch_sum_small(h->d2part, nd2, A + h->off_d2, h->ctrl, trip, st));
                     h->stats.kernel_launches++;
@@ -726,7 +844,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             c.row_a = h->svec;
             c.col_w = h->qvec;
             c.sspart = h->sspart_y;
-            TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c));
+            TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c, TPLS_K_YSIDE));
             TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y + a + 1, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
         }
         // ---- X deflation (tpls.py:109) fused with the next component's first contraction ----
@@ -767,6 +885,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
     h->stats.fit_ms = ms;
+    prof_collect(h);
     for (int l = 0; l < L; ++l) {
         h->r2x[l].assign(R, 0.0);
         const double* s = ss.data() + (h->x[l].off_ss - h->off_ss);
@@ -876,6 +995,12 @@ int tpls_get_trips(tpls_handle h, int* out) {
     return 0;
 }
 
+int tpls_get_profile(tpls_handle h, tpls_profile* out) {
+    if (!h) return fail(nullptr, "NULL handle");
+    *out = h->prof_sum;
+    return 0;
+}
+
 int tpls_get_stats(tpls_handle h, tpls_stats* out) {
     if (!h) return fail(nullptr, "NULL handle");
     *out = h->stats;
@@ -890,8 +1015,8 @@ int tpls_release_data(tpls_handle h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     for (auto& t : h->x) {
-        if (t.owned) cudaFree(t.owned);
-        if (t.owned2) cudaFree(t.owned2);
+        if (t.owned) pool_put(h, t.owned);
+        if (t.owned2) pool_put(h, t.owned2);
         t.owned = t.owned2 = nullptr;
         t.src = nullptr;
         t.work = nullptr;
@@ -900,6 +1025,14 @@ int tpls_release_data(tpls_handle h) {
     if (h->y_src) cudaFree(h->y_src);
     if (h->y_work) cudaFree(h->y_work);
     h->y_src = h->y_work = nullptr;
+    return 0;
+}
+
+int tpls_trim(tpls_handle h) {
+    if (!h) return fail(nullptr, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    pool_trim(h);
     return 0;
 }
 
@@ -915,7 +1048,7 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
     double *S = nullptr, *sspart = nullptr;
     int rc = 0;
     std::vector<void*> xw(L, nullptr);
-    std::vector<PassGeom> gs(L);
+    std::vector<PassGeom> gs(L), grs(L);
     std::vector<double*> tpart(L, nullptr), cpart(L, nullptr), mean_d(L, nullptr), wk(L, nullptr);
     std::vector<int> pitch(L), elem(L);
     do {
@@ -952,6 +1085,7 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
                 break;
             }
             gs[l] = make_geom(n_new, p, pitch[l], elem[l], h->sm_count);
+            grs[l] = make_row_geom(n_new, p, pitch[l], elem[l], h->sm_count, true);
             if (gs[l].n_slabs > 1) {
                 if ((rc = dev_alloc(h, (void**)&tpart[l], sizeof(double) * n_new * gs[l].n_slabs, &tmp))) break;
                 if ((rc = dev_alloc(h, (void**)&cpart[l], sizeof(double) * n_new * gs[l].n_slabs, &tmp))) break;
@@ -971,7 +1105,7 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
             double* Sa = S + (size_t)a * n_new;
             for (int l = 0; l < L && !rc; ++l) {
                 RowPassArgs r{};
-                r.g = gs[l];
+                r.g = grs[l];
                 r.x_in = xw[l];
                 r.col_w = wk[l] + (size_t)a * pitch[l];
                 r.t_out = Sa;
@@ -1081,7 +1215,7 @@ int tpls_op_project(tpls_handle h, const void* x, int dtype, int64_t n, int64_t 
     TRY(op_check(h, dtype, n, p));
     CK(cudaSetDevice(h->device));
     const int elem = dtype == TPLS_F32 ? 4 : 8;
-    PassGeom g = make_geom(n, (int)p, (int)p, elem, h->sm_count);
+    PassGeom g = make_row_geom(n, (int)p, (int)p, elem, h->sm_count, masked != 0);
     double *tpart = nullptr, *cpart = nullptr;
     if (g.n_slabs > 1) {
         CK(cudaMalloc((void**)&tpart, sizeof(double) * n * g.n_slabs));

@@ -1,5 +1,6 @@
 // Streaming column/row passes over an X (or Y) shard -- see passes.cuh.
 #include "passes.cuh"
+#include "stream_common.cuh"
 
 #include <algorithm>
 
@@ -56,61 +57,6 @@ size_t colpass_smem(const PassGeom& g) {
     const size_t tiles = g.stages * stage_bytes_of(g);
     const size_t red = (size_t)kConsumers * 16 / g.elem_size * sizeof(double);  // rpt > 1 => cpt == 1
     return std::max(tiles, red) + 128;
-}
-
-size_t rowpass_smem(const PassGeom& g) {
-    size_t red = 0;
-    if (g.lpr > 32) red = (size_t)2 * g.tile_rows * (g.lpr / 32) * 2 * sizeof(double);
-    return g.stages * stage_bytes_of(g) + 128 + red;
-}
-
-// ---------------------------------------------------------------------------
-// device helpers
-// ---------------------------------------------------------------------------
-template <typename XT>
-struct VecOf;
-template <>
-struct VecOf<float> {
-    using type = float4;
-    static constexpr int N = 4;
-};
-template <>
-struct VecOf<double> {
-    using type = double2;
-    static constexpr int N = 2;
-};
-
-template <typename XT>
-union Pack {
-    typename VecOf<XT>::type v;
-    XT e[VecOf<XT>::N];
-};
-
-// Producer: one elected lane streams this CTA's row tiles into the smem ring.
-template <typename XT>
-__device__ __forceinline__ void produce_tiles(const PassGeom& g, const XT* __restrict__ x, XT* tiles, uint64_t* full,
-                                              uint64_t* empty, int c0, int slab_cols, int srow) {
-    const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
-    const size_t stage_elems = (size_t)g.tile_rows * srow;
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = (int)(it % g.stages);
-        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
-        if (it >= g.stages) mbar_wait(&empty[s], ph ^ 1u);
-        const long long r0 = tile * g.tile_rows;
-        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
-        XT* dst = tiles + s * stage_elems;
-        const XT* src = x + r0 * g.pitch + c0;
-        if (g.n_slabs == 1) {
-            const uint32_t bytes = (uint32_t)((size_t)rows * g.pitch * sizeof(XT));
-            mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_g2s(dst, src, bytes, &full[s]);
-        } else {
-            const uint32_t rb = (uint32_t)(slab_cols * sizeof(XT));
-            mbar_arrive_expect_tx(&full[s], rb * rows);
-            for (int r = 0; r < rows; ++r) bulk_g2s(dst + (size_t)r * srow, src + (size_t)r * g.pitch, rb, &full[s]);
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -270,166 +216,6 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------
-// row pass
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long grow, double v, double& d2) {
-    double* tp = a.t_out + grow;
-    const double old = *tp;
-    double nv = v;
-    if (a.epi == 1) nv = old + v;
-    if (a.epi == 2) nv = (old + v) / a.div;
-    *tp = nv;
-    if (a.d2part != nullptr) {
-        const double d = old - nv;
-        d2 = fma(d, d, d2);
-    }
-}
-
-template <typename XT, int CPT, bool MASKED>
-__global__ void __launch_bounds__(kThreads, 2) rowpass_kernel(const __grid_constant__ RowPassArgs a) {
-    constexpr int VEC = VecOf<XT>::N;
-    if (trip_is_dead(a.ctrl, a.trip)) return;
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    const PassGeom& g = a.g;
-    const int c0 = blockIdx.y * g.slab_w;
-    const int slab_cols = min(g.slab_w, g.pitch - c0);
-    const int srow = (g.n_slabs == 1) ? g.pitch : g.slab_w;
-    const size_t stage_elems = (size_t)g.tile_rows * srow;
-    XT* tiles = reinterpret_cast<XT*>(smem);
-    const size_t tile_area = (size_t)g.stages * stage_elems * sizeof(XT);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + tile_area);
-    uint64_t* empty = full + kMaxStages;
-    double* red = reinterpret_cast<double*>(smem + tile_area + 128);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < g.stages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumers / 32);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (threadIdx.x >= kConsumers) {
-        if (threadIdx.x == kConsumers)
-            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow);
-        return;
-    }
-
-    const int tid = threadIdx.x;
-    const int cl = tid & (g.lpr - 1);
-    const int rl = tid / g.lpr;
-    const int lane = tid & 31;
-    const int wpr = g.lpr >> 5;  // warps per row when lpr > 32
-    const bool slabbed = g.n_slabs > 1;
-    const double p_total = (double)g.p;
-
-    double wreg[CPT][VEC];
-    bool cvalid[CPT];
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        const int cg = cl + k * g.lpr;
-        cvalid[k] = cg * VEC < slab_cols;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) wreg[k][j] = cvalid[k] ? a.col_w[c0 + cg * VEC + j] : 0.0;
-    }
-    double d2 = 0.0;
-
-    const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = (int)(it % g.stages);
-        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
-        const long long r0 = tile * g.tile_rows;
-        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
-        mbar_wait(&full[s], ph);
-        const XT* tp = tiles + s * stage_elems;
-        double* redt = red + (size_t)(it & 1) * g.tile_rows * max(wpr, 1) * 2;
-        // every lane of a row group walks the same number of rounds so that the shuffles stay converged
-        for (int rb = 0; rb < rows; rb += g.rpt) {
-            const int r = rb + rl;
-            const bool live = r < rows;
-            double v = 0.0, cnt = 0.0;
-            if (live) {
-#pragma unroll
-                for (int k = 0; k < CPT; ++k) {
-                    if (!cvalid[k]) continue;
-                    const int cg = cl + k * g.lpr;
-                    Pack<XT> in;
-                    in.v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const XT xs = in.e[j];
-                        if (MASKED) {
-                            const bool ob = (xs == xs) && (c0 + cg * VEC + j < g.p);
-                            v = fma(ob ? (double)xs : 0.0, wreg[k][j], v);
-                            cnt += ob ? 1.0 : 0.0;
-                        } else {
-                            v = fma((double)xs, wreg[k][j], v);
-                        }
-                    }
-                }
-            }
-            // reduce over the lanes of this row
-            const int span = g.lpr < 32 ? g.lpr : 32;
-            for (int m = span >> 1; m >= 1; m >>= 1) {
-                v += shfl_xor_d(v, m);
-                if (MASKED) cnt += shfl_xor_d(cnt, m);
-            }
-            if (g.lpr <= 32) {
-                if (live && cl == 0) {
-                    const long long grow = r0 + r;
-                    if (slabbed) {
-                        a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
-                        if (MASKED) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
-                    } else {
-                        if (MASKED) v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
-                        row_epilogue(a, grow, v, d2);
-                    }
-                }
-            } else if (live && lane == 0) {
-                redt[((size_t)r * wpr + (cl >> 5)) * 2 + 0] = v;
-                redt[((size_t)r * wpr + (cl >> 5)) * 2 + 1] = cnt;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (g.lpr > 32) {
-            named_bar_sync(1, kConsumers);
-            for (int r = tid; r < rows; r += kConsumers) {
-                double v = 0.0, cnt = 0.0;
-                for (int w = 0; w < wpr; ++w) {
-                    v += redt[((size_t)r * wpr + w) * 2 + 0];
-                    cnt += redt[((size_t)r * wpr + w) * 2 + 1];
-                }
-                const long long grow = r0 + r;
-                if (slabbed) {
-                    a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
-                    if (MASKED) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
-                } else {
-                    if (MASKED) v = v / cnt * p_total;
-                    row_epilogue(a, grow, v, d2);
-                }
-            }
-        }
-    }
-
-    if (a.d2part != nullptr && !slabbed) {
-        double* r2 = reinterpret_cast<double*>(smem);  // tiles are drained
-        named_bar_sync(1, kConsumers);
-        d2 = warp_sum(d2);
-        if (lane == 0) r2[tid >> 5] = d2;
-        named_bar_sync(1, kConsumers);
-        if (tid == 0) {
-            double t = 0.0;
-            for (int w = 0; w < kConsumers / 32; ++w) t += r2[w];
-            a.d2part[blockIdx.x] = t;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
 // small finishing kernels
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
@@ -548,35 +334,6 @@ static cudaError_t colpass_cpt(bool masked, int flags, const ColPassArgs& a, cud
 
 cudaError_t launch_colpass(int dtype, bool masked, int flags, const ColPassArgs& a, cudaStream_t s) {
     return dtype == 0 ? colpass_cpt<float>(masked, flags, a, s) : colpass_cpt<double>(masked, flags, a, s);
-}
-
-template <typename XT, int CPT, bool MASKED>
-static cudaError_t run_rowpass(const RowPassArgs& a, cudaStream_t s) {
-    auto kern = rowpass_kernel<XT, CPT, MASKED>;
-    const size_t smem = rowpass_smem(a.g);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid(a.g.grid_x, a.g.n_slabs);
-    kern<<<grid, kThreads, smem, s>>>(a);
-    return cudaGetLastError();
-}
-
-template <typename XT>
-static cudaError_t rowpass_cpt(bool masked, const RowPassArgs& a, cudaStream_t s) {
-#define TPLS_RP(C) return masked ? run_rowpass<XT, C, true>(a, s) : run_rowpass<XT, C, false>(a, s)
-    switch (a.g.cpt) {
-        case 1:
-            TPLS_RP(1);
-        case 2:
-            TPLS_RP(2);
-        default:
-            TPLS_RP(4);
-    }
-#undef TPLS_RP
-}
-
-cudaError_t launch_rowpass(int dtype, bool masked, const RowPassArgs& a, cudaStream_t s) {
-    return dtype == 0 ? rowpass_cpt<float>(masked, a, s) : rowpass_cpt<double>(masked, a, s);
 }
 
 }  // namespace tpls

@@ -53,7 +53,9 @@ struct PassGeom {
 // Chooses slab width, thread layout, tile size and grid for a shard.
 PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count);
 size_t colpass_smem(const PassGeom& g);
-size_t rowpass_smem(const PassGeom& g);
+// Row passes use their own layout (fewer lanes per row, a slot ring for the reducer warp).
+PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked);
+size_t rowpass_smem(const PassGeom& g, bool masked);
 
 struct ColPassArgs {
     PassGeom g;

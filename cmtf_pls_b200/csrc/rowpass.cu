@@ -1,0 +1,325 @@
+// Row pass: t[i] = sum_c x[i,c] * w[c]  (projection, reference cmtf_pls/tpls.py:97-99,
+// masked variant missingvals.py:23-38; also u = Y q, tpls.py:102) -- see passes.cuh.
+//
+// Warp roles in one CTA (kRowThreads = 320):
+//   warps 0..7  consumers  each thread owns up to 4 sixteen-byte column groups of the
+//                          slab, keeps w for them in registers, and for every staged
+//                          row writes ONE fp64 partial into a shared-memory slot ring;
+//   warp  8     producer   one lane streams row tiles in with 1-D bulk async copies;
+//   warp  9     reducer    folds the per-thread partials of a tile into t[row], applies
+//                          the epilogue (coupled average, masked rescaling, ||dt||^2).
+// Consumers never meet at a CTA-wide barrier: tiles and slots are handed over with
+// mbarriers only.  Rows narrower than 32 column groups skip the slot ring and reduce
+// with sub-warp shuffles instead.
+#include "passes.cuh"
+#include "stream_common.cuh"
+
+#include <algorithm>
+
+namespace tpls {
+
+constexpr int kRowThreads = kConsumers + 64;
+constexpr int kSlots = 3;
+
+static int pow2_ceil_i(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static size_t row_stage_bytes(const PassGeom& g) {
+    return (size_t)g.tile_rows * (g.n_slabs == 1 ? g.pitch : g.slab_w) * g.elem_size;
+}
+
+static size_t row_slot_doubles(const PassGeom& g, bool masked) {
+    return g.lpr >= 32 ? (size_t)g.tile_rows * g.lpr * (masked ? 2 : 1) : 0;
+}
+
+PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked) {
+    PassGeom g{};
+    const int vec = 16 / elem_size;
+    g.n_rows = n_rows;
+    g.p = p;
+    g.pitch = pitch;
+    g.elem_size = elem_size;
+    const int cg_total = pitch / vec;
+    const int max_cg = kConsumers * kMaxCpt;
+    g.n_slabs = (cg_total + max_cg - 1) / max_cg;
+    const int slab_cg = (cg_total + g.n_slabs - 1) / g.n_slabs;
+    g.slab_w = slab_cg * vec;
+    if (slab_cg < 32) {
+        g.lpr = pow2_ceil_i(slab_cg);
+        g.cpt = 1;
+    } else {
+        g.lpr = std::min(kConsumers, std::max(32, pow2_ceil_i((slab_cg + kMaxCpt - 1) / kMaxCpt)));
+        const int need = (slab_cg + g.lpr - 1) / g.lpr;
+        g.cpt = need <= 1 ? 1 : (need <= 2 ? 2 : 4);
+    }
+    g.rpt = kConsumers / g.lpr;
+    const long long row_bytes = (long long)(g.n_slabs == 1 ? pitch : g.slab_w) * elem_size;
+    // budget: stages * tile + kSlots * slot <= ~108 KB so that two CTAs share an SM
+    const double slot_per_tile_byte = g.lpr >= 32 ? (masked ? 2.0 : 1.0) / (2.0 * g.cpt) : 0.0;
+    const double budget = 108.0 * 1024;
+    long long tile_max = (long long)(budget / (3.0 * (1.0 + slot_per_tile_byte)));
+    tile_max = std::min<long long>(tile_max, 32 * 1024);
+    long long tr = std::max<long long>(1, tile_max / row_bytes);
+    tr = std::min<long long>(tr, std::max<long long>(1, n_rows));
+    tr = std::min<long long>(tr, 4096);
+    g.tile_rows = (int)tr;
+    const size_t slots = kSlots * row_slot_doubles(g, masked) * sizeof(double);
+    const long long stage = (long long)row_stage_bytes(g);
+    g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
+    const long long n_tiles = (n_rows + tr - 1) / tr;
+    const long long want = std::max(1, (sm_count * 2) / g.n_slabs);
+    g.grid_x = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
+    return g;
+}
+
+size_t rowpass_smem(const PassGeom& g, bool masked) {
+    return g.stages * row_stage_bytes(g) + 256 + kSlots * row_slot_doubles(g, masked) * sizeof(double);
+}
+
+__device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long grow, double v, double& d2) {
+    double* tp = a.t_out + grow;
+    const double old = *tp;
+    double nv = v;
+    if (a.epi == 1) nv = old + v;
+    if (a.epi == 2) nv = (old + v) / a.div;
+    *tp = nv;
+    if (a.d2part != nullptr) {
+        const double d = old - nv;
+        d2 = fma(d, d, d2);
+    }
+}
+
+template <typename XT, int CPT, bool MASKED>
+__global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_constant__ RowPassArgs a) {
+    constexpr int VEC = VecOf<XT>::N;
+    if (trip_is_dead(a.ctrl, a.trip)) return;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PassGeom& g = a.g;
+    const int c0 = blockIdx.y * g.slab_w;
+    const int slab_cols = min(g.slab_w, g.pitch - c0);
+    const int srow = (g.n_slabs == 1) ? g.pitch : g.slab_w;
+    const size_t stage_elems = (size_t)g.tile_rows * srow;
+    XT* tiles = reinterpret_cast<XT*>(smem);
+    const size_t tile_area = (size_t)g.stages * stage_elems * sizeof(XT);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + tile_area);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* red_full = empty + kMaxStages;
+    uint64_t* red_empty = red_full + kSlots;
+    double* slots = reinterpret_cast<double*>(smem + tile_area + 256);
+    const bool use_slots = g.lpr >= 32;
+    const size_t slot_doubles = use_slots ? (size_t)g.tile_rows * g.lpr * (MASKED ? 2 : 1) : 0;
+    const bool slabbed = g.n_slabs > 1;
+    const double p_total = (double)g.p;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumers / 32);
+        }
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(&red_full[s], kConsumers / 32);
+            mbar_init(&red_empty[s], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    // ------------------------------------------------------------------ producer
+    if (tid >= kConsumers && tid < kConsumers + 32) {
+        if (tid == kConsumers)
+            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow);
+        return;
+    }
+
+    // ------------------------------------------------------------------ reducer
+    if (tid >= kConsumers + 32) {
+        if (!use_slots) return;
+        // G lanes cooperate on one row; 32/G rows per round
+        int G = 32;
+        while (G > 1 && (32 / G) * 2 <= g.tile_rows) G >>= 1;  // as many rows per round as the tile has
+        if (G > g.lpr) G = g.lpr;
+        const int rows_per_round = 32 / G;
+        const int rg = lane / G, gl = lane - rg * G;
+        double d2 = 0.0;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int sl = (int)(it % kSlots);
+            const uint32_t ph = (uint32_t)((it / kSlots) & 1);
+            const long long r0 = tile * g.tile_rows;
+            const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+            mbar_wait(&red_full[sl], ph);
+            const double* sp = slots + (size_t)sl * slot_doubles;
+            const double* cp = sp + (size_t)g.tile_rows * g.lpr;
+            for (int rb = 0; rb < rows; rb += rows_per_round) {
+                const int r = rb + rg;
+                double v = 0.0, cnt = 0.0;
+                if (r < rows) {
+                    const double* rowp = sp + (size_t)r * g.lpr;
+                    const double* rowc = cp + (size_t)r * g.lpr;
+                    const int skew = (G * rg) & (g.lpr - 1);
+                    for (int i = gl; i < g.lpr; i += G) {
+                        const int col = (i + skew) & (g.lpr - 1);
+                        v += rowp[col];
+                        if (MASKED) cnt += rowc[col];
+                    }
+                }
+                for (int m = G >> 1; m >= 1; m >>= 1) {
+                    v += shfl_xor_d(v, m);
+                    if (MASKED) cnt += shfl_xor_d(cnt, m);
+                }
+                if (r < rows && gl == 0) {
+                    const long long grow = r0 + r;
+                    if (slabbed) {
+                        a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
+                        if (MASKED) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
+                    } else {
+                        if (MASKED) v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
+                        row_epilogue(a, grow, v, d2);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&red_empty[sl]);
+        }
+        if (a.d2part != nullptr && !slabbed) {
+            d2 = warp_sum(d2);
+            if (lane == 0) a.d2part[blockIdx.x] = d2;
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------ consumers
+    const int cl = tid & (g.lpr - 1);
+    const int rl = tid / g.lpr;
+    double wreg[CPT][VEC];
+    bool cvalid[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int cg = cl + k * g.lpr;
+        cvalid[k] = cg * VEC < slab_cols;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) wreg[k][j] = cvalid[k] ? a.col_w[c0 + cg * VEC + j] : 0.0;
+    }
+    double d2 = 0.0;
+
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = (int)(it % g.stages);
+        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+        const long long r0 = tile * g.tile_rows;
+        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+        const int sl = (int)(it % kSlots);
+        double* sp = slots + (size_t)sl * slot_doubles;
+        double* cp = sp + (size_t)g.tile_rows * g.lpr;
+        if (use_slots && it >= kSlots) mbar_wait(&red_empty[sl], (uint32_t)(((it / kSlots) - 1) & 1));
+        mbar_wait(&full[s], ph);
+        const XT* tp = tiles + s * stage_elems;
+        // every lane of a row group walks the same number of rounds so that the shuffles stay converged
+        for (int rb = 0; rb < rows; rb += g.rpt) {
+            const int r = rb + rl;
+            const bool live = r < rows;
+            double v = 0.0, cnt = 0.0;
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    if (!cvalid[k]) continue;
+                    const int cg = cl + k * g.lpr;
+                    Pack<XT> in;
+                    in.v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const XT xs = in.e[j];
+                        if (MASKED) {
+                            const bool ob = (xs == xs) && (c0 + cg * VEC + j < g.p);
+                            v = fma(ob ? (double)xs : 0.0, wreg[k][j], v);
+                            cnt += ob ? 1.0 : 0.0;
+                        } else {
+                            v = fma((double)xs, wreg[k][j], v);
+                        }
+                    }
+                }
+            }
+            if (use_slots) {
+                if (live) {
+                    sp[(size_t)r * g.lpr + cl] = v;
+                    if (MASKED) cp[(size_t)r * g.lpr + cl] = cnt;
+                }
+            } else {
+                for (int m = g.lpr >> 1; m >= 1; m >>= 1) {
+                    v += shfl_xor_d(v, m);
+                    if (MASKED) cnt += shfl_xor_d(cnt, m);
+                }
+                if (live && cl == 0) {
+                    const long long grow = r0 + r;
+                    if (slabbed) {
+                        a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
+                        if (MASKED) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
+                    } else {
+                        if (MASKED) v = v / cnt * p_total;
+                        row_epilogue(a, grow, v, d2);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[s]);
+            if (use_slots) mbar_arrive(&red_full[sl]);
+        }
+    }
+
+    if (!use_slots && a.d2part != nullptr && !slabbed) {
+        double* r2 = reinterpret_cast<double*>(smem);  // tiles are drained
+        named_bar_sync(1, kConsumers);
+        d2 = warp_sum(d2);
+        if (lane == 0) r2[tid >> 5] = d2;
+        named_bar_sync(1, kConsumers);
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kConsumers / 32; ++w) t += r2[w];
+            a.d2part[blockIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------
+template <typename XT, int CPT, bool MASKED>
+static cudaError_t run_rowpass(const RowPassArgs& a, cudaStream_t s) {
+    auto kern = rowpass_kernel<XT, CPT, MASKED>;
+    const size_t smem = rowpass_smem(a.g, MASKED);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(a.g.grid_x, a.g.n_slabs);
+    kern<<<grid, kRowThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename XT>
+static cudaError_t rowpass_cpt(bool masked, const RowPassArgs& a, cudaStream_t s) {
+#define TPLS_RP(C) return masked ? run_rowpass<XT, C, true>(a, s) : run_rowpass<XT, C, false>(a, s)
+    switch (a.g.cpt) {
+        case 1:
+            TPLS_RP(1);
+        case 2:
+            TPLS_RP(2);
+        default:
+            TPLS_RP(4);
+    }
+#undef TPLS_RP
+}
+
+cudaError_t launch_rowpass(int dtype, bool masked, const RowPassArgs& a, cudaStream_t s) {
+    return dtype == 0 ? rowpass_cpt<float>(masked, a, s) : rowpass_cpt<double>(masked, a, s);
+}
+
+}  // namespace tpls

@@ -51,11 +51,11 @@ class tPLS(Mapping):
         return copy(self)
 
     # ---- fit (tpls.py:44-120) ----
-    def fit(self, X, Y, tol=1e-8, max_iter=100, verbose=0, overwrite_x=False):
+    def fit(self, X, Y, tol=1e-8, max_iter=100, verbose=0, overwrite_x=False, profile=False):
         assert X.shape[0] == Y.shape[0]
         assert Y.ndim <= 2, "Only a matrix (2-mode tensor) Y is acceptable."
         st = _core.run_fit([X], Y, self.n_components, tol, max_iter, device=self.device,
-                           group=self.process_group, overwrite=overwrite_x)
+                           group=self.process_group, overwrite=overwrite_x, profile=profile)
         self.X_dim = X.ndim
         self.X_shape = tuple(X.shape)
         self.Y_shape = (int(Y.shape[0]), 1) if Y.ndim == 1 else tuple(Y.shape)
@@ -72,6 +72,7 @@ class tPLS(Mapping):
         self.coef_ = st["coef"]
         self.n_iter_ = st["trips"]
         self.stats_ = st["stats"]
+        self.profile_ = st["profile"]
         self._device = st["device"]
         if verbose:
             for a, k in enumerate(self.n_iter_):

@@ -39,8 +39,22 @@ enum {
 
 /* tpls_fit flags */
 enum {
-    TPLS_FIT_NORMALIZE_ON_BREAK = 1 /* the other reading of tensorly's last ALS sweep, oracle/_cp.py */
+    TPLS_FIT_NORMALIZE_ON_BREAK = 1, /* the other reading of tensorly's last ALS sweep, oracle/_cp.py */
+    TPLS_FIT_PROFILE = 2             /* time every pass with CUDA events on the handle's stream (tpls_get_profile) */
 };
+
+/* kernel classes of tpls_get_profile */
+enum {
+    TPLS_K_COLSTAT = 0,          /* column sums / counts (np.nanmean, tpls.py:66) */
+    TPLS_K_CONTRACT = 1,         /* Z = X x_1 u (tpls.py:83) */
+    TPLS_K_PROJECT = 2,          /* t = X x_2 w2 x_3 w3 ... (tpls.py:97-99) */
+    TPLS_K_DEFLATE_CONTRACT = 3, /* centring or rank-1 deflation fused with the next contraction */
+    TPLS_K_RESIDUAL = 4,         /* read-only residual norm after the last component */
+    TPLS_K_RANK1 = 5,            /* single-CTA rank-1 step (tpls.py:84-88) */
+    TPLS_K_YSIDE = 6,            /* passes over Y (q, u, Y deflation) */
+    TPLS_K_OTHER = 7
+};
+#define TPLS_N_KERNEL_CLASSES 8
 
 #define TPLS_MAX_TENSORS 8
 #define TPLS_MAX_MODES 8
@@ -92,8 +106,18 @@ typedef struct tpls_stats {
 } tpls_stats;
 int tpls_get_stats(tpls_handle h, tpls_stats* out);
 
+typedef struct tpls_profile {
+    double ms[TPLS_N_KERNEL_CLASSES];        /* summed launch durations of the last profiled fit */
+    int64_t launches[TPLS_N_KERNEL_CLASSES];
+    double bytes[TPLS_N_KERNEL_CLASSES];     /* algorithmic bytes of X moved by those launches */
+} tpls_profile;
+int tpls_get_profile(tpls_handle h, tpls_profile* out);
+
 /* Frees the device copies of X and Y held by the handle (the fitted state stays readable). */
 int tpls_release_data(tpls_handle h);
+/* tpls_release_data keeps the X-sized buffers cached for the next fit on this handle (allocating tens
+ * of GB costs hundreds of ms); tpls_trim returns the cached buffers to the CUDA driver. */
+int tpls_trim(tpls_handle h);
 
 /* New data through a fitted model: scores (n_new, R) of transform (tpls.py:145-165,
  * cmtf.py:179-210) -- centre with the training mean, then per component project
