@@ -274,6 +274,8 @@ def run_ours(args):
     e2e = None
     n_iter_resident = est.n_iter_.tolist()
     try:
+        if args.e2e_steps <= 0:
+            raise RuntimeError("skipped (--e2e-steps 0)")
         Xh = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in Xs]
         for h, d in zip(Xh, Xs):
             h.copy_(d)

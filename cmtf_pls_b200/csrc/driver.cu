@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -47,7 +48,7 @@ struct Tensor {
     int* miss_flag = nullptr;
     int* sweeps = nullptr;
     size_t r1_ws = 0;
-    int r1_nmax = 1;
+    int r1_nmax = 1, r1_zs = 0, r1_mt = 0;
     // arena offsets (doubles)
     size_t off_colsum = 0, off_colcnt = 0, off_z = 0, off_ss = 0;
 };
@@ -582,7 +583,7 @@ static int alloc_fit(tpls_handle h, int L, int R) {
         TRY(dev_alloc(h, (void**)&t.sweeps, sizeof(int) * 4, tr));
         int dims[kMaxZModes];
         for (int k = 1; k < t.ndim; ++k) dims[k - 1] = (int)t.shape[k];
-        t.r1_ws = rank1_workspace_doubles(t.ndim - 1, dims, &t.r1_nmax);
+        t.r1_ws = rank1_workspace_doubles(t.ndim - 1, dims, &t.r1_nmax, &t.r1_zs, &t.r1_mt);
         TRY(dev_alloc(h, (void**)&t.r1_scratch, sizeof(double) * t.r1_ws, tr));
     }
     return 0;
@@ -603,6 +604,8 @@ static void fill_rank1_task(tpls_handle h, Tensor& t, int a, Rank1Task& k, bool 
     k.scratch = t.r1_scratch;
     k.use_smem = use_smem ? 1 : 0;
     k.nmax = t.r1_nmax;
+    k.zs_len = t.r1_zs;
+    k.mt_len = t.r1_mt;
     k.sweeps = t.sweeps;
 }
 
@@ -1291,15 +1294,24 @@ int tpls_op_rank1(tpls_handle h, const double* z, int nmodes, const int* dims, d
     k.pitch = (int)p;
     k.nmodes = nmodes;
     k.wkron = wkron_out;
-    int nmax = 1;
-    const size_t ws = rank1_workspace_doubles(nmodes, dims, &nmax);
+    int nmax = 1, zs_len = 0, mt_len = 0;
+    const size_t ws = rank1_workspace_doubles(nmodes, dims, &nmax, &zs_len, &mt_len);
     k.nmax = nmax;
+    k.zs_len = zs_len;
+    k.mt_len = mt_len;
     double* scratch = nullptr;
     int* sweeps = nullptr;
     CK(cudaMalloc((void**)&scratch, sizeof(double) * ws));
     CK(cudaMalloc((void**)&sweeps, sizeof(int) * 4));
     k.scratch = scratch;
     k.sweeps = sweeps;
+    long long* stamps = nullptr;
+    const bool want_stamps = getenv("TPLS_RANK1_STAMPS") != nullptr;
+    if (want_stamps) {
+        CK(cudaMalloc((void**)&stamps, sizeof(long long) * 8));
+        CK(cudaMemset(stamps, 0, sizeof(long long) * 8));
+        k.stamps = stamps;
+    }
     size_t smem = ws * sizeof(double);
     k.use_smem = smem <= 200 * 1024;
     if (!k.use_smem) smem = 0;
@@ -1310,6 +1322,13 @@ int tpls_op_rank1(tpls_handle h, const double* z, int nmodes, const int* dims, d
     });
     cudaStreamSynchronize(h->stream);
     if (!rc && sweeps_out) cudaMemcpy(sweeps_out, sweeps, sizeof(int), cudaMemcpyDeviceToHost);
+    if (want_stamps) {
+        long long hs[8];
+        cudaMemcpy(hs, stamps, sizeof hs, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "rank1 stamps (cycles): load->gram %lld  eig %lld  init-rest %lld  als %lld  publish %lld\n", hs[1] - hs[0],
+                hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4]);
+        cudaFree(stamps);
+    }
     cudaFree(scratch);
     cudaFree(sweeps);
     return rc;

@@ -218,23 +218,34 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
 // ---------------------------------------------------------------------------
 // small finishing kernels
 // ---------------------------------------------------------------------------
+// 32 columns x 8 part-groups per CTA: each thread folds every 8th partial of its column (coalesced 256-byte
+// rows, several loads in flight), the 8 groups meet in shared memory.  Fixed order => bit-reproducible.
 __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
     if (trip_is_dead(a.ctrl, a.trip)) return;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double fold[8][33];
+    __shared__ double red[40];
+    const int cl = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
     if (c < a.n_cols) {
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-        int b = 0;
-        for (; b + 4 <= a.n_parts; b += 4) {
+        int b = q;
+        for (; b + 24 < a.n_parts; b += 32) {
             t0 += a.part[(size_t)(b + 0) * a.stride + c];
-            t1 += a.part[(size_t)(b + 1) * a.stride + c];
-            t2 += a.part[(size_t)(b + 2) * a.stride + c];
-            t3 += a.part[(size_t)(b + 3) * a.stride + c];
+            t1 += a.part[(size_t)(b + 8) * a.stride + c];
+            t2 += a.part[(size_t)(b + 16) * a.stride + c];
+            t3 += a.part[(size_t)(b + 24) * a.stride + c];
         }
-        for (; b < a.n_parts; ++b) t0 += a.part[(size_t)b * a.stride + c];
-        a.out[c] = (t0 + t1) + (t2 + t3);
+        for (; b < a.n_parts; b += 8) t0 += a.part[(size_t)b * a.stride + c];
+    }
+    fold[q][cl] = (t0 + t1) + (t2 + t3);
+    __syncthreads();
+    if (q == 0 && c < a.n_cols) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += fold[k][cl];
+        a.out[c] = t;
     }
     if (a.ss_out != nullptr && blockIdx.x == 0) {
-        __shared__ double red[40];
         double t = 0.0;
         for (int i = threadIdx.x; i < a.n_ss; i += blockDim.x) t += a.sspart[i];
         t = block_sum(t, red);
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
 }
 
 cudaError_t launch_reduce_cols(const ReduceArgs& a, cudaStream_t s) {
-    const int blocks = std::max(1, (a.n_cols + 255) / 256);
+    const int blocks = std::max(1, (a.n_cols + 31) / 32);
     reduce_cols_kernel<<<blocks, 256, 0, s>>>(a);
     return cudaGetLastError();
 }

@@ -27,7 +27,9 @@ struct Rank1Task {
     double* scratch;        // global workspace (used when it does not fit in shared memory)
     int use_smem;
     int nmax;               // largest Gram order needed
+    int zs_len, mt_len;     // workspace segment lengths (doubles), from rank1_workspace_doubles
     int* sweeps;            // out (optional): ALS sweeps taken
+    long long* stamps;      // out (optional, diagnostics): clock64 at phase boundaries [8]
 };
 
 struct Rank1Args {
@@ -40,7 +42,7 @@ struct Rank1Args {
 };
 
 // doubles of workspace a task needs, and the Gram order it implies
-size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out);
+size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out);
 cudaError_t launch_rank1(const Rank1Args& a, size_t smem_bytes, cudaStream_t s);
 
 }  // namespace tpls
