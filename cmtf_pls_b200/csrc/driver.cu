@@ -91,6 +91,12 @@ struct tpls_ctx {
         bool used;
     };
     std::vector<PoolBuf> pool;
+    // slab of the per-fit buffers (see dev_alloc) and a grow-only bounce buffer for the getters
+    char* slab = nullptr;
+    size_t slab_cap = 0, slab_off = 0, slab_need = 0;
+    bool slab_dry = false;
+    void* tmp_buf = nullptr;
+    size_t tmp_cap = 0;
     size_t arena_doubles = 0, off_ysum = 0, off_ycnt = 0, off_n = 0, off_stats_end = 0, off_zcat = 0, zcat_len = 0,
            off_q = 0, off_d2 = 0, off_dots = 0, off_ss = 0, ss_len = 0;
     std::vector<double> r2x[TPLS_MAX_TENSORS];
@@ -154,9 +160,28 @@ bool is_device_ptr(const void* p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+int pool_get(tpls_handle h, void** out, size_t bytes);
+void pool_put(tpls_handle h, void* p);
+
+// Per-fit buffers are carved out of ONE cached slab (cudaMalloc / cudaFree cost milliseconds each once
+// NCCL has enabled peer access; a fit needs ~60 buffers).  `track == &h->fit_allocs` selects the slab:
+// a dry run adds up the sizes, the real run hands out 256-byte aligned pieces.  Any other `track` is a
+// list of pool buffers the caller returns with pool_put.
 int dev_alloc(tpls_handle h, void** out, size_t bytes, std::vector<void*>* track) {
     *out = nullptr;
-    CK(cudaMalloc(out, std::max<size_t>(bytes, 16)));
+    if (track == &h->fit_allocs) {
+        const size_t al = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+        if (h->slab_dry) {
+            h->slab_need += al;
+            *out = reinterpret_cast<void*>(256);
+            return 0;
+        }
+        if (h->slab_off + al > h->slab_cap) return fail(h, "fit slab overflow (internal error)");
+        *out = h->slab + h->slab_off;
+        h->slab_off += al;
+        return 0;
+    }
+    TRY(pool_get(h, out, bytes));
     if (track) track->push_back(*out);
     return 0;
 }
@@ -196,8 +221,8 @@ void pool_put(tpls_handle h, void* p) {
 }
 
 void free_fit(tpls_handle h) {
-    for (void* p : h->fit_allocs) cudaFree(p);
     h->fit_allocs.clear();
+    h->slab_off = 0;
     h->fitted = false;
 }
 
@@ -374,9 +399,11 @@ int tpls_destroy(tpls_handle h) {
     cudaStreamSynchronize(h->stream);
     free_fit(h);
     for (auto& t : h->x) free_tensor(h, t);
+    if (h->y_src) pool_put(h, h->y_src);
+    if (h->y_work) pool_put(h, h->y_work);
+    if (h->slab) pool_put(h, h->slab);
+    if (h->tmp_buf) pool_put(h, h->tmp_buf);
     pool_trim(h);
-    if (h->y_src) cudaFree(h->y_src);
-    if (h->y_work) cudaFree(h->y_work);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->h_done) cudaFreeHost(h->h_done);
     cudaEventDestroy(h->ev_start);
@@ -466,15 +493,15 @@ int tpls_set_y(tpls_handle h, const double* y, int64_t n, int64_t m) {
     if (!h) return fail(nullptr, "NULL handle");
     if (n <= 0 || m <= 0) return fail(h, "tpls_set_y: empty Y");
     CK(cudaSetDevice(h->device));
-    if (h->y_src) cudaFree(h->y_src);
-    if (h->y_work) cudaFree(h->y_work);
+    if (h->y_src) pool_put(h, h->y_src);
+    if (h->y_work) pool_put(h, h->y_work);
     h->y_src = h->y_work = nullptr;
     h->n = n;
     h->m = (int)m;
     h->pitch_y = (int)((m + 1) / 2 * 2);
     const size_t bytes = (size_t)n * h->pitch_y * sizeof(double);
-    CK(cudaMalloc((void**)&h->y_src, bytes));
-    CK(cudaMalloc((void**)&h->y_work, bytes));
+    TRY(pool_get(h, (void**)&h->y_src, bytes));
+    TRY(pool_get(h, (void**)&h->y_work, bytes));
     if (h->pitch_y != m) CK(cudaMemsetAsync(h->y_src, 0, bytes, h->stream));
     CK(cudaMemcpy2DAsync(h->y_src, (size_t)h->pitch_y * 8, y, (size_t)m * 8, (size_t)m * 8, n, cudaMemcpyDefault,
                          h->stream));
@@ -486,8 +513,29 @@ int tpls_set_y(tpls_handle h, const double* y, int64_t n, int64_t m) {
 // ---------------------------------------------------------------------------
 // fit
 // ---------------------------------------------------------------------------
+static int layout_fit(tpls_handle h, int L, int R);
+
 static int alloc_fit(tpls_handle h, int L, int R) {
     free_fit(h);
+    h->slab_dry = true;
+    h->slab_need = 0;
+    TRY(layout_fit(h, L, R));
+    h->slab_dry = false;
+    if (h->slab_need > h->slab_cap) {
+        if (h->slab) pool_put(h, h->slab);
+        h->slab = nullptr;
+        h->slab_cap = 0;
+        void* p = nullptr;
+        TRY(pool_get(h, &p, h->slab_need));
+        h->slab = static_cast<char*>(p);
+        h->slab_cap = h->slab_need;
+    }
+    CK(cudaMemsetAsync(h->slab, 0, h->slab_need, h->stream));
+    h->slab_off = 0;
+    return layout_fit(h, L, R);
+}
+
+static int layout_fit(tpls_handle h, int L, int R) {
     auto* tr = &h->fit_allocs;
     const long long n = h->n;
     h->L = L;
@@ -533,7 +581,6 @@ static int alloc_fit(tpls_handle h, int L, int R) {
     h->ss_len = off - h->off_ss;
     h->arena_doubles = off;
     TRY(dev_alloc(h, (void**)&h->arena, off * sizeof(double), tr));
-    CK(cudaMemsetAsync(h->arena, 0, off * sizeof(double), h->stream));
 
     TRY(dev_alloc(h, (void**)&h->T, sizeof(double) * n * R, tr));
     TRY(dev_alloc(h, (void**)&h->U, sizeof(double) * n * R, tr));
@@ -552,13 +599,6 @@ static int alloc_fit(tpls_handle h, int L, int R) {
     TRY(dev_alloc(h, (void**)&h->trips_dev, sizeof(int) * R, tr));
     TRY(dev_alloc(h, (void**)&h->ymiss_flag, sizeof(int) * 4, tr));
     TRY(dev_alloc(h, (void**)&h->ctrl, sizeof(Ctrl), tr));
-    CK(cudaMemsetAsync(h->T, 0, sizeof(double) * n * R, h->stream));
-    CK(cudaMemsetAsync(h->U, 0, sizeof(double) * n * R, h->stream));
-    CK(cudaMemsetAsync(h->Q, 0, sizeof(double) * h->m * R, h->stream));
-    CK(cudaMemsetAsync(h->coef, 0, sizeof(double) * R * R, h->stream));
-    CK(cudaMemsetAsync(h->gram, 0, sizeof(double) * R * R, h->stream));
-    CK(cudaMemsetAsync(h->trips_dev, 0, sizeof(int) * R, h->stream));
-    CK(cudaMemsetAsync(h->ymiss_flag, 0, sizeof(int) * 4, h->stream));
 
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
@@ -569,17 +609,14 @@ static int alloc_fit(tpls_handle h, int L, int R) {
         TRY(dev_alloc(h, (void**)&t.mean_d, sizeof(double) * t.pitch, tr));
         TRY(dev_alloc(h, &t.mean_native, (size_t)t.elem * t.pitch, tr));
         TRY(dev_alloc(h, (void**)&t.wkron, sizeof(double) * t.pitch * R, tr));
-        CK(cudaMemsetAsync(t.wkron, 0, sizeof(double) * t.pitch * R, h->stream));
         if (t.g.n_slabs > 1) {
             TRY(dev_alloc(h, (void**)&t.tpart, sizeof(double) * n * t.g.n_slabs, tr));
             TRY(dev_alloc(h, (void**)&t.cpart, sizeof(double) * n * t.g.n_slabs, tr));
         }
         for (int k = 1; k < t.ndim; ++k) {
             TRY(dev_alloc(h, (void**)&t.W[k], sizeof(double) * t.shape[k] * R, tr));
-            CK(cudaMemsetAsync(t.W[k], 0, sizeof(double) * t.shape[k] * R, h->stream));
         }
         TRY(dev_alloc(h, (void**)&t.miss_flag, sizeof(int) * 4, tr));
-        CK(cudaMemsetAsync(t.miss_flag, 0, sizeof(int) * 4, h->stream));
         TRY(dev_alloc(h, (void**)&t.sweeps, sizeof(int) * 4, tr));
         int dims[kMaxZModes];
         for (int k = 1; k < t.ndim; ++k) dims[k - 1] = (int)t.shape[k];
@@ -919,13 +956,18 @@ static int copy_out_transposed(tpls_handle h, const double* colmajor, long long 
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     }
-    double* tmp = nullptr;
-    CK(cudaMalloc((void**)&tmp, sizeof(double) * std::max<long long>(1, rows * cols)));
-    cudaError_t e = launch_transpose_out(colmajor, rows, rows, cols, tmp, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, sizeof(double) * rows * cols, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
-    CK(e);
+    const size_t need = sizeof(double) * std::max<long long>(1, rows * cols);
+    if (need > h->tmp_cap) {
+        if (h->tmp_buf) pool_put(h, h->tmp_buf);
+        h->tmp_buf = nullptr;
+        h->tmp_cap = 0;
+        TRY(pool_get(h, &h->tmp_buf, need));
+        h->tmp_cap = need;
+    }
+    double* tmp = static_cast<double*>(h->tmp_buf);
+    CK(launch_transpose_out(colmajor, rows, rows, cols, tmp, h->stream));
+    CK(cudaMemcpyAsync(out, tmp, sizeof(double) * rows * cols, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -1025,8 +1067,8 @@ int tpls_release_data(tpls_handle h) {
         t.work = nullptr;
         t.set = false;
     }
-    if (h->y_src) cudaFree(h->y_src);
-    if (h->y_work) cudaFree(h->y_work);
+    if (h->y_src) pool_put(h, h->y_src);
+    if (h->y_work) pool_put(h, h->y_work);
     h->y_src = h->y_work = nullptr;
     return 0;
 }
@@ -1133,7 +1175,7 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
         rc = copy_out_transposed(h, S, n_new, R, scores_out);
     } while (0);
     cudaStreamSynchronize(st);
-    for (void* p : tmp) cudaFree(p);
+    for (void* p : tmp) pool_put(h, p);
     return rc;
 }
 
