@@ -39,10 +39,13 @@ struct Tensor {
     void* owned2 = nullptr;
     bool masked = false;
     PassGeom g{};   // column passes
-    PassGeom gr{};  // row passes (depends on `masked`, fixed after the statistics pass)
+    PassGeom gr{};      // row passes
+    PassGeom gr_cnt{};  // the one counting row pass of a masked fit (needs twice the slot space)
     // per-fit device buffers
     double *zpart = nullptr, *cntpart = nullptr, *sspart = nullptr;
     double *mean_d = nullptr, *wkron = nullptr, *tpart = nullptr, *cpart = nullptr, *r1_scratch = nullptr;
+    double* rowcnt = nullptr;   // masked: observed entries per row (filled by the first projection of a fit)
+    bool rowcnt_ready = false;
     void* mean_native = nullptr;
     double* W[TPLS_MAX_MODES] = {nullptr};
     int* miss_flag = nullptr;
@@ -301,10 +304,11 @@ int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a, i
     return 0;
 }
 
-int row_pass(tpls_handle h, int dtype, bool masked, RowPassArgs& a, int cls = TPLS_K_PROJECT) {
+// mode: 0 dense, 1 masked with known row counts (a.rowcnt), 2 masked and counting (fills a.rowcnt)
+int row_pass(tpls_handle h, int dtype, int mode, RowPassArgs& a, int cls = TPLS_K_PROJECT) {
     const double bytes = (double)a.g.n_rows * a.g.pitch * a.g.elem_size;
     ProfScope ps(h, cls, bytes);
-    CK(launch_rowpass(dtype, masked, a, h->stream));
+    CK(launch_rowpass(dtype, mode, a, h->stream));
     h->stats.kernel_launches++;
     if (cls != TPLS_K_YSIDE) h->stats.streamed_bytes += bytes;
     if (a.g.n_slabs > 1) {
@@ -312,7 +316,9 @@ int row_pass(tpls_handle h, int dtype, bool masked, RowPassArgs& a, int cls = TP
         f.n_rows = a.g.n_rows;
         f.n_slabs = a.g.n_slabs;
         f.tpart = a.tpart;
-        f.cpart = masked ? a.cpart : nullptr;
+        f.cpart = mode == 2 ? a.cpart : nullptr;
+        f.rowcnt = mode != 0 ? a.rowcnt : nullptr;
+        f.pads = (double)(a.g.pitch - a.g.p);
         f.p_total = (double)a.g.p;
         f.t_out = a.t_out;
         f.epi = a.epi;
@@ -609,6 +615,8 @@ static int layout_fit(tpls_handle h, int L, int R) {
         TRY(dev_alloc(h, (void**)&t.mean_d, sizeof(double) * t.pitch, tr));
         TRY(dev_alloc(h, &t.mean_native, (size_t)t.elem * t.pitch, tr));
         TRY(dev_alloc(h, (void**)&t.wkron, sizeof(double) * t.pitch * R, tr));
+        TRY(dev_alloc(h, (void**)&t.rowcnt, sizeof(double) * n, tr));
+        t.rowcnt_ready = false;
         if (t.g.n_slabs > 1) {
             TRY(dev_alloc(h, (void**)&t.tpart, sizeof(double) * n * t.g.n_slabs, tr));
             TRY(dev_alloc(h, (void**)&t.cpart, sizeof(double) * n * t.g.n_slabs, tr));
@@ -714,7 +722,8 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         for (int l = 0; l < L; ++l) {
             Tensor& t = h->x[l];
             t.masked = flagsh[l] != 0;
-            t.gr = make_row_geom(n, t.p, t.pitch, t.elem, h->sm_count, t.masked);
+            t.gr = make_row_geom(n, t.p, t.pitch, t.elem, h->sm_count, false);
+            t.gr_cnt = make_row_geom(n, t.p, t.pitch, t.elem, h->sm_count, true);
         }
     }
 
@@ -802,17 +811,22 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             for (int l = 0; l < L; ++l) {
                 Tensor& t = h->x[l];
                 RowPassArgs r{};
-                r.g = t.gr;
+                const int rmode = !t.masked ? 0 : (t.rowcnt_ready ? 1 : 2);
+                r.g = rmode == 2 ? t.gr_cnt : t.gr;
                 r.x_in = t.work;
                 r.col_w = t.wkron + (size_t)a * t.pitch;
                 r.t_out = Ta;
                 r.tpart = t.tpart;
                 r.cpart = t.cpart;
+                r.rowcnt = t.rowcnt;
                 r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
                 r.div = (double)L;
                 r.ctrl = h->ctrl;
                 r.trip = trip;
-                TRY(row_pass(h, t.dtype, t.masked, r));
+                // the first projection of a masked tensor also counts the observed entries of every row
+                // (trip 0 of component 0 always executes, so the counts are there for every later trip)
+                TRY(row_pass(h, t.dtype, rmode, r));
+                t.rowcnt_ready = true;
             }
             // K4: q = Y't / ||.||, u = Y q, stop test (tpls.py:100-107)
             {
@@ -838,7 +852,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 r.d2part = h->d2part;
                 r.ctrl = h->ctrl;
                 r.trip = trip;
-                TRY(row_pass(h, TPLS_F64, false, r, TPLS_K_YSIDE));
+                TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
                 const int nd2 = d2_grid(h->gy_row);
                 if (h->world > 1) {
                     CK(launch_sum_small(h->d2part, nd2, A + h->off_d2, h->ctrl, trip, st));
@@ -1093,8 +1107,8 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
     double *S = nullptr, *sspart = nullptr;
     int rc = 0;
     std::vector<void*> xw(L, nullptr);
-    std::vector<PassGeom> gs(L), grs(L);
-    std::vector<double*> tpart(L, nullptr), cpart(L, nullptr), mean_d(L, nullptr), wk(L, nullptr);
+    std::vector<PassGeom> gs(L), grs(L), grs_cnt(L);
+    std::vector<double*> tpart(L, nullptr), cpart(L, nullptr), mean_d(L, nullptr), wk(L, nullptr), rowcnt(L, nullptr);
     std::vector<int> pitch(L), elem(L);
     do {
         if ((rc = dev_alloc(h, (void**)&S, sizeof(double) * n_new * R, &tmp))) break;
@@ -1112,6 +1126,7 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
             if ((rc = dev_alloc(h, &xw[l], bytes, &tmp))) break;
             if ((rc = dev_alloc(h, (void**)&mean_d[l], sizeof(double) * pitch[l], &tmp))) break;
             if ((rc = dev_alloc(h, (void**)&wk[l], sizeof(double) * pitch[l] * R, &tmp))) break;
+            if ((rc = dev_alloc(h, (void**)&rowcnt[l], sizeof(double) * n_new, &tmp))) break;
             void* mean_nat = nullptr;
             if ((rc = dev_alloc(h, &mean_nat, (size_t)elem[l] * pitch[l], &tmp))) break;
             cudaError_t e = cudaMemsetAsync(xw[l], 0, bytes, st);
@@ -1130,7 +1145,8 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
                 break;
             }
             gs[l] = make_geom(n_new, p, pitch[l], elem[l], h->sm_count);
-            grs[l] = make_row_geom(n_new, p, pitch[l], elem[l], h->sm_count, true);
+            grs[l] = make_row_geom(n_new, p, pitch[l], elem[l], h->sm_count, false);
+            grs_cnt[l] = make_row_geom(n_new, p, pitch[l], elem[l], h->sm_count, true);
             if (gs[l].n_slabs > 1) {
                 if ((rc = dev_alloc(h, (void**)&tpart[l], sizeof(double) * n_new * gs[l].n_slabs, &tmp))) break;
                 if ((rc = dev_alloc(h, (void**)&cpart[l], sizeof(double) * n_new * gs[l].n_slabs, &tmp))) break;
@@ -1150,15 +1166,16 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
             double* Sa = S + (size_t)a * n_new;
             for (int l = 0; l < L && !rc; ++l) {
                 RowPassArgs r{};
-                r.g = grs[l];
+                r.g = a == 0 ? grs_cnt[l] : grs[l];
                 r.x_in = xw[l];
                 r.col_w = wk[l] + (size_t)a * pitch[l];
                 r.t_out = Sa;
                 r.tpart = tpart[l];
                 r.cpart = cpart[l];
+                r.rowcnt = rowcnt[l];
                 r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
                 r.div = (double)L;
-                rc = row_pass(h, dtypes[l], true, r);
+                rc = row_pass(h, dtypes[l], a == 0 ? 2 : 1, r);
             }
             for (int l = 0; l < L && !rc && a + 1 < R; ++l) {
                 ColPassArgs c{};
@@ -1260,27 +1277,34 @@ int tpls_op_project(tpls_handle h, const void* x, int dtype, int64_t n, int64_t 
     TRY(op_check(h, dtype, n, p));
     CK(cudaSetDevice(h->device));
     const int elem = dtype == TPLS_F32 ? 4 : 8;
-    PassGeom g = make_row_geom(n, (int)p, (int)p, elem, h->sm_count, masked != 0);
-    double *tpart = nullptr, *cpart = nullptr;
+    PassGeom g = make_row_geom(n, (int)p, (int)p, elem, h->sm_count, false);
+    PassGeom g_cnt = make_row_geom(n, (int)p, (int)p, elem, h->sm_count, true);
+    double *tpart = nullptr, *cpart = nullptr, *rowcnt = nullptr;
+    bool counted = false;
+    CK(cudaMalloc((void**)&rowcnt, sizeof(double) * n));
     if (g.n_slabs > 1) {
         CK(cudaMalloc((void**)&tpart, sizeof(double) * n * g.n_slabs));
         CK(cudaMalloc((void**)&cpart, sizeof(double) * n * g.n_slabs));
     }
     int rc = time_loop(h, repeats, ms_out, [&]() -> int {
         RowPassArgs r{};
-        r.g = g;
+        r.g = (masked && !counted) ? g_cnt : g;
         r.x_in = x;
         r.col_w = w;
         r.t_out = t_out;
         r.tpart = tpart;
         r.cpart = cpart;
+        r.rowcnt = rowcnt;
         r.epi = 0;
         r.div = 1.0;
-        return row_pass(h, dtype, masked != 0, r);
+        const int mode = !masked ? 0 : (counted ? 1 : 2);
+        counted = true;
+        return row_pass(h, dtype, mode, r);
     });
     cudaStreamSynchronize(h->stream);
     if (tpart) cudaFree(tpart);
     if (cpart) cudaFree(cpart);
+    cudaFree(rowcnt);
     return rc;
 }
 

@@ -3,12 +3,20 @@
 #include "stream_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace tpls {
 
 // ---------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------
+// Tuning overrides for experiments (tools/opbench.py): TPLS_TILE_KB, TPLS_SMEM_KB (per-CTA staging budget),
+// TPLS_CTAS_PER_SM.  Unset in normal use.
+int tune_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v != nullptr && *v) ? atoi(v) : dflt;
+}
+
 static int pow2_ceil(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -37,14 +45,14 @@ PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_cou
     }
     g.rpt = kConsumers / g.lpr;
     const long long row_bytes = (long long)(g.n_slabs == 1 ? pitch : g.slab_w) * elem_size;
-    long long tr = std::max<long long>(1, (32 * 1024) / row_bytes);
+    long long tr = std::max<long long>(1, ((long long)tune_env("TPLS_TILE_KB", 32) * 1024) / row_bytes);
     tr = std::min<long long>(tr, std::max<long long>(1, n_rows));
     tr = std::min<long long>(tr, 4096);
     g.tile_rows = (int)tr;
     const long long stage_bytes = tr * row_bytes;
-    g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, (100 * 1024) / stage_bytes));
+    g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)tune_env("TPLS_SMEM_KB", 100) * 1024) / stage_bytes));
     const long long n_tiles = (n_rows + tr - 1) / tr;
-    const long long want = std::max(1, (sm_count * 2) / g.n_slabs);
+    const long long want = std::max(1, (sm_count * tune_env("TPLS_CTAS_PER_SM", 2)) / g.n_slabs);
     g.grid_x = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
     return g;
 }
@@ -270,7 +278,15 @@ __global__ void __launch_bounds__(256) row_finish_kernel(const RowFinishArgs a) 
             v += a.tpart[(size_t)s * a.n_rows + r];
             if (a.cpart != nullptr) cnt += a.cpart[(size_t)s * a.n_rows + r];
         }
-        if (a.cpart != nullptr) v = v / cnt * a.p_total;
+        if (a.rowcnt != nullptr) {
+            if (a.cpart != nullptr) {
+                cnt -= a.pads;
+                a.rowcnt[r] = cnt;
+            } else {
+                cnt = a.rowcnt[r];
+            }
+            v = v / cnt * a.p_total;
+        }
         const double old = a.t_out[r];
         double nv = v;
         if (a.epi == 1) nv = old + v;

@@ -53,6 +53,7 @@ struct PassGeom {
 // Chooses slab width, thread layout, tile size and grid for a shard.
 PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count);
 size_t colpass_smem(const PassGeom& g);
+int tune_env(const char* name, int dflt);
 // Row passes use their own layout (fewer lanes per row, a slot ring for the reducer warp).
 PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked);
 size_t rowpass_smem(const PassGeom& g, bool masked);
@@ -77,7 +78,8 @@ struct RowPassArgs {
     const double* col_w;    // [pitch]
     double* t_out;          // [n_rows]
     double* tpart;          // n_slabs > 1: [n_slabs][n_rows] partial dots
-    double* cpart;          // n_slabs > 1 and masked: [n_slabs][n_rows] observed counts
+    double* cpart;          // n_slabs > 1 and counting: [n_slabs][n_rows] observed counts
+    double* rowcnt;         // masked: [n_rows] observed entries per row (read in mode 1, written in mode 2)
     int epi;                // 0: t = v   1: t += v   2: t = (t + v) / div
     double div;
     double* d2part;         // optional [grid_x]: sum over rows of (t_old - t_new)^2
@@ -87,7 +89,8 @@ struct RowPassArgs {
 
 // dtype: 0 = float32, 1 = float64
 cudaError_t launch_colpass(int dtype, bool masked, int flags, const ColPassArgs& a, cudaStream_t s);
-cudaError_t launch_rowpass(int dtype, bool masked, const RowPassArgs& a, cudaStream_t s);
+// mode: 0 dense, 1 masked with known row counts, 2 masked and counting (writes a.rowcnt)
+cudaError_t launch_rowpass(int dtype, int mode, const RowPassArgs& a, cudaStream_t s);
 
 // out[c] = sum_b part[b*stride + c]  (fixed order => bit-reproducible); optionally
 // ss_out[0] = sum of sspart[0..n_ss).
@@ -110,7 +113,9 @@ struct RowFinishArgs {
     long long n_rows;
     int n_slabs;
     const double* tpart;
-    const double* cpart;    // nullptr when dense
+    const double* cpart;    // counting pass: per-slab observed counts (else nullptr)
+    double* rowcnt;         // masked: per-row observed counts (written when cpart != nullptr, else read); nullptr when dense
+    double pads;            // zero-filled pad columns per row (they look observed)
     double p_total;
     double* t_out;
     int epi;

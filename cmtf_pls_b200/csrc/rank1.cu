@@ -111,39 +111,35 @@ __device__ __forceinline__ int argmax_abs(const double* a, int n, Blk& b) {
 
 // C[i*n4 + j] = scale * sum_k Mt[k*n4 + i] * Mt[k*n4 + j]   (n4 % 4 == 0, pads of Mt are zero)
 __device__ __forceinline__ void syrk_fast(double* __restrict__ C, const double* __restrict__ Mt, int krows, int n4, double scale) {
+    // a thread owns rows i0..i0+3 (contiguous: two broadcast 16-byte loads) and columns tj, tj+nt, tj+2nt,
+    // tj+3nt (strided: the 16 lanes of a tile row read 16 consecutive doubles -- conflict-free)
     const int nt = n4 >> 2;
     for (int t = threadIdx.x; t < nt * nt; t += NTH) {
-        const int i0 = (t / nt) << 2, j0 = (t % nt) << 2;
+        const int i0 = (t / nt) << 2, tj = t % nt;
         double acc[4][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[q][r] = 0.0;
         const double* pa = Mt + i0;
-        const double* pb = Mt + j0;
-#pragma unroll 2
+        const double* pb = Mt + tj;
+#pragma unroll 4
         for (int k = 0; k < krows; ++k) {
             const double2 a01 = *reinterpret_cast<const double2*>(pa + (size_t)k * n4);
             const double2 a23 = *reinterpret_cast<const double2*>(pa + (size_t)k * n4 + 2);
-            const double2 b01 = *reinterpret_cast<const double2*>(pb + (size_t)k * n4);
-            const double2 b23 = *reinterpret_cast<const double2*>(pb + (size_t)k * n4 + 2);
             const double ai[4] = {a01.x, a01.y, a23.x, a23.y};
-            const double bj[4] = {b01.x, b01.y, b23.x, b23.y};
+            double bj[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) bj[r] = pb[(size_t)k * n4 + r * nt];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) acc[q][r] = fma(ai[q], bj[r], acc[q][r]);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double2 lo, hi;
-            lo.x = acc[q][0] * scale;
-            lo.y = acc[q][1] * scale;
-            hi.x = acc[q][2] * scale;
-            hi.y = acc[q][3] * scale;
-            *reinterpret_cast<double2*>(C + (size_t)(i0 + q) * n4 + j0) = lo;
-            *reinterpret_cast<double2*>(C + (size_t)(i0 + q) * n4 + j0 + 2) = hi;
-        }
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) C[(size_t)(i0 + q) * n4 + tj + r * nt] = acc[q][r] * scale;
     }
     __syncthreads();
 }
@@ -175,9 +171,19 @@ __device__ __forceinline__ void vec_div(double* a, double d, int n) {
     __syncthreads();
 }
 
+// dst = src / ||src||
+__device__ __forceinline__ void normalize_into(double* dst, const double* src, int n, Blk& blk) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += NTH) s = fma(src[i], src[i], s);
+    const double nv = sqrt(bsum(s, blk));
+    for (int i = threadIdx.x; i < n; i += NTH) dst[i] = src[i] / nv;
+    __syncthreads();
+}
+
 // Leading eigenpair of the symmetric PSD matrix G (n x n stored n4 x n4 with zero pads).
 // A, B: n4*n4 work buffers.  v (n) receives the unit eigenvector; returns the eigenvalue.
-__device__ __forceinline__ double lead_eig(const double* G, double* A, double* B, double* v, double* tmp, int n, Blk& blk) {
+__device__ __forceinline__ double lead_eig(const double* G, double* A, double* B, double* v, double* tmp, int n, Blk& blk, int polish,
+                                           bool want_lambda) {
     const int n4 = up4(n);
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += NTH) s += G[(size_t)i * n4 + i];
@@ -212,12 +218,13 @@ __device__ __forceinline__ double lead_eig(const double* G, double* A, double* B
     double nv = sqrt(vec_dot(v, v, n, blk));
     vec_div(v, nv, n);
     // polish against the original matrix
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < polish; ++q) {
         matvec8(tmp, G, n4, v, n, n);
         nv = sqrt(vec_dot(tmp, tmp, n, blk));
         for (int i = threadIdx.x; i < n; i += NTH) v[i] = tmp[i] / nv;
         __syncthreads();
     }
+    if (!want_lambda) return 0.0;
     matvec8(tmp, G, n4, v, n, n);
     return vec_dot(tmp, v, n, blk);
 }
@@ -351,14 +358,16 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
     double s = 0.0;
     if (nm == 2) {
         // padded row-major Z in zs and padded Z^T in mt
-        for (int i = threadIdx.x; i < d0 * ld1; i += NTH) zs[i] = 0.0;
-        for (int i = threadIdx.x; i < d1 * ld0; i += NTH) mt[i] = 0.0;
-        __syncthreads();
+        if (ld1 != d1)
+            for (int i = threadIdx.x; i < d0 * ld1; i += NTH) zs[i] = 0.0;
+        if (ld0 != d0)
+            for (int i = threadIdx.x; i < d1 * ld0; i += NTH) mt[i] = 0.0;
+        if (ld1 != d1 || ld0 != d0) __syncthreads();
     }
     for (int i = threadIdx.x; i < p; i += NTH) {
-        double z = T.z[i];
+        double z = __ldg(T.z + i);
         if (T.colcnt != nullptr) {
-            const double c = T.colcnt[i];
+            const double c = __ldg(T.colcnt + i);
             z = c > 0.0 ? z / c * T.n_total : 0.0;
         }
         s = fma(z, z, s);
@@ -373,25 +382,35 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
     const double normz2 = bsum(s, blk);
     const double normz = sqrt(normz2);
 
-    // ---- HOSVD start ----
-    double weight = 1.0;
     TPLS_STAMP(1);
+    int sweeps = 0;
     if (nm == 2) {
-        // one eigenproblem on the short side; the other vector follows from Z
-        const int ks = d0 <= d1 ? 0 : 1, ko = 1 - ks;
-        const int n = T.dims[ks], no = T.dims[ko];
+        // ---- matrix Z: the rank-1 CP is the leading singular pair ----
+        // tensorly starts ALS from the exact SVD, which is already the fixed point: its two sweeps leave
+        // the pair where it is and only settle the sign -- the LAST mode keeps the "largest-|entry|
+        // positive" convention of the start, mode 0 follows from Z.  So: one eigenproblem on the short
+        // side, the sign rule on f1, then one power step each way (= one ALS sweep) as a polish.
+        const int ks = d0 <= d1 ? 0 : 1;
+        const int n = T.dims[ks], no = T.dims[1 - ks];
         // rows of Mt are the columns of the mode-ks unfolding: Z^T for ks == 0, Z for ks == 1
         const double* Mt = ks == 0 ? mt : zs;
         syrk_fast(G, Mt, no, up4(n), 1.0);
-        lead_eig(G, A, B, f[ks], tmp, n, blk);
+        lead_eig(G, A, B, f[ks], tmp, n, blk, /*polish=*/1, /*want_lambda=*/false);
         TPLS_STAMP(2);
-        matvec8(f[ko], Mt, up4(n), f[ks], no, n);  // Z_(ko) f_ks = sigma * other vector
-        const double sigma = sqrt(vec_dot(f[ko], f[ko], no, blk));
-        vec_div(f[ko], sigma, no);
-        weight = sigma;
-        flip_to_positive_peak(f[0], d0, blk);
+        if (ks == 0) {
+            matvec8(tmp, mt, ld0, f[0], d1, d0);
+            normalize_into(f[1], tmp, d1, blk);
+        }
         flip_to_positive_peak(f[1], d1, blk);
+        matvec8(tmp, zs, ld1, f[1], d0, d1);
+        normalize_into(f[0], tmp, d0, blk);
+        matvec8(tmp, mt, ld0, f[0], d1, d0);
+        normalize_into(f[1], tmp, d1, blk);
+        sweeps = 2;
+        TPLS_STAMP(3);
     } else {
+        // ---- HOSVD start ----
+        double weight = 1.0;
         for (int k = 0; k < nm; ++k) {
             const Geo g = mode_geo(T, k);
             double lam;
@@ -403,7 +422,7 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
                 }
                 __syncthreads();
                 syrk_fast(G, mt, g.mk, n4, 1.0);
-                lam = lead_eig(G, A, B, f[k], tmp, g.dk, blk);
+                lam = lead_eig(G, A, B, f[k], tmp, g.dk, blk, 2, true);
                 if (k == 0) weight = sqrt(lam);
             } else {
                 const int n4 = up4(g.mk);
@@ -413,7 +432,7 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
                 }
                 __syncthreads();
                 syrk_fast(G, mt, g.dk, n4, 1.0);
-                lead_eig(G, A, B, tmp2, tmp, g.mk, blk);
+                lead_eig(G, A, B, tmp2, tmp, g.mk, blk, 2, false);
                 unf_matvec(f[k], zs, g, tmp2);
                 const double sigma = sqrt(vec_dot(f[k], f[k], g.dk, blk));
                 vec_div(f[k], sigma, g.dk);
@@ -421,68 +440,61 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
             }
             flip_to_positive_peak(f[k], g.dk, blk);
         }
-    }
+        TPLS_STAMP(2);
+        TPLS_STAMP(3);
 
-    TPLS_STAMP(3);
-    // ---- ALS sweeps (tensorly parafac, rank 1) ----
-    double nrm2[kMaxZModes];
-    for (int m = 0; m < nm; ++m) nrm2[m] = vec_dot(f[m], f[m], T.dims[m], blk);
-    double err_prev = 0.0;
-    int sweeps = 0;
-    double* kr = mt;  // nm >= 3 only (mt is the Z^T copy when nm == 2)
-    for (int it = 0; it < 100; ++it) {
-        ++sweeps;
-        double iprod = 0.0;
-        for (int k = 0; k < nm; ++k) {
-            const int dk = T.dims[k];
-            if (nm == 2) {
-                if (k == 0)
-                    matvec8(tmp, zs, ld1, f[1], d0, d1);
-                else
-                    matvec8(tmp, mt, ld0, f[0], d1, d0);
-            } else {
+        // ---- ALS sweeps (tensorly parafac, rank 1) ----
+        double nrm2[kMaxZModes];
+        for (int m = 0; m < nm; ++m) nrm2[m] = vec_dot(f[m], f[m], T.dims[m], blk);
+        double err_prev = 0.0;
+        double* kr = mt;
+        for (int it = 0; it < 100; ++it) {
+            ++sweeps;
+            double iprod = 0.0;
+            for (int k = 0; k < nm; ++k) {
+                const int dk = T.dims[k];
                 const Geo g = mode_geo(T, k);
                 other_modes_product(kr, T, k, f, g.mk);
                 unf_matvec(tmp, zs, g, kr);
+                double gram = weight * weight;
+                for (int m = 0; m < nm; ++m)
+                    if (m != k) gram *= nrm2[m];
+                // factor = (weight * Z x_others f) / gram; iprod = <mttkrp, factor> (last mode only)
+                double s1 = 0.0, s2 = 0.0;
+                for (int i = threadIdx.x; i < dk; i += NTH) {
+                    const double mt_i = tmp[i] * weight;
+                    const double fi = mt_i / gram;
+                    f[k][i] = fi;
+                    s1 = fma(fi, fi, s1);
+                    s2 = fma(mt_i, fi, s2);
+                }
+                bsum2(s1, s2, blk);
+                nrm2[k] = s1;
+                if (k == nm - 1) iprod = s2;
             }
-            double gram = weight * weight;
-            for (int m = 0; m < nm; ++m)
-                if (m != k) gram *= nrm2[m];
-            // factor = (weight * Z x_others f) / gram; iprod = <mttkrp, factor> (last mode only)
-            double s1 = 0.0, s2 = 0.0;
-            for (int i = threadIdx.x; i < dk; i += NTH) {
-                const double mt_i = tmp[i] * weight;
-                const double fi = mt_i / gram;
-                f[k][i] = fi;
-                s1 = fma(fi, fi, s1);
-                s2 = fma(mt_i, fi, s2);
+            double fn2 = weight * weight;
+            for (int m = 0; m < nm; ++m) fn2 *= nrm2[m];
+            const double err = sqrt(fabs(normz2 + fn2 - 2.0 * iprod)) / normz;
+            const bool stop = it >= 1 && fabs(err_prev - err) < tol;
+            err_prev = err;
+            if (stop && !normalize_on_break) break;
+            // cp_normalize: weights into factor 0, then every column norm back into the weights
+            const double w_in = weight;
+            weight = 1.0;
+            for (int m = 0; m < nm; ++m) {
+                const double sc = sqrt(nrm2[m]) * (m == 0 ? fabs(w_in) : 1.0);
+                const double dv = sc == 0.0 ? 1.0 : sc;
+                double s1 = 0.0;
+                for (int i = threadIdx.x; i < T.dims[m]; i += NTH) {
+                    const double v = (m == 0 ? f[m][i] * w_in : f[m][i]) / dv;
+                    f[m][i] = v;
+                    s1 = fma(v, v, s1);
+                }
+                weight *= sc;
+                nrm2[m] = bsum(s1, blk);
             }
-            bsum2(s1, s2, blk);
-            nrm2[k] = s1;
-            if (k == nm - 1) iprod = s2;
+            if (stop) break;
         }
-        double fn2 = weight * weight;
-        for (int m = 0; m < nm; ++m) fn2 *= nrm2[m];
-        const double err = sqrt(fabs(normz2 + fn2 - 2.0 * iprod)) / normz;
-        const bool stop = it >= 1 && fabs(err_prev - err) < tol;
-        err_prev = err;
-        if (stop && !normalize_on_break) break;
-        // cp_normalize: weights into factor 0, then every column norm back into the weights
-        const double w_in = weight;
-        weight = 1.0;
-        for (int m = 0; m < nm; ++m) {
-            const double sc = sqrt(nrm2[m]) * (m == 0 ? fabs(w_in) : 1.0);
-            const double dv = sc == 0.0 ? 1.0 : sc;
-            double s1 = 0.0;
-            for (int i = threadIdx.x; i < T.dims[m]; i += NTH) {
-                const double v = (m == 0 ? f[m][i] * w_in : f[m][i]) / dv;
-                f[m][i] = v;
-                s1 = fma(v, v, s1);
-            }
-            weight *= sc;
-            nrm2[m] = bsum(s1, blk);
-        }
-        if (stop) break;
     }
 
     TPLS_STAMP(4);
@@ -491,7 +503,10 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         for (int i = threadIdx.x; i < T.dims[m]; i += NTH) T.w[m][i] = f[m][i];
     for (int i = threadIdx.x; i < T.pitch; i += NTH) {
         double pr = 0.0;
-        if (i < p) {
+        if (i < p && nm == 2) {
+            const int a = i / d1;
+            pr = f[0][a] * f[1][i - a * d1];
+        } else if (i < p) {
             int rem = i;
             // kron(w_0, w_1, ...) built the way numpy.kron nests it: ((w0 * w1) * w2) ...
             int idx[kMaxZModes];

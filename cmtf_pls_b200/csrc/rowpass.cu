@@ -59,9 +59,9 @@ PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm
     const long long row_bytes = (long long)(g.n_slabs == 1 ? pitch : g.slab_w) * elem_size;
     // budget: stages * tile + kSlots * slot <= ~108 KB so that two CTAs share an SM
     const double slot_per_tile_byte = g.lpr >= 32 ? (masked ? 2.0 : 1.0) / (2.0 * g.cpt) : 0.0;
-    const double budget = 108.0 * 1024;
+    const double budget = tune_env("TPLS_SMEM_KB", 108) * 1024.0;
     long long tile_max = (long long)(budget / (3.0 * (1.0 + slot_per_tile_byte)));
-    tile_max = std::min<long long>(tile_max, 32 * 1024);
+    tile_max = std::min<long long>(tile_max, (long long)tune_env("TPLS_TILE_KB", 32) * 1024);
     long long tr = std::max<long long>(1, tile_max / row_bytes);
     tr = std::min<long long>(tr, std::max<long long>(1, n_rows));
     tr = std::min<long long>(tr, 4096);
@@ -70,7 +70,7 @@ PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm
     const long long stage = (long long)row_stage_bytes(g);
     g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
     const long long n_tiles = (n_rows + tr - 1) / tr;
-    const long long want = std::max(1, (sm_count * 2) / g.n_slabs);
+    const long long want = std::max(1, (sm_count * tune_env("TPLS_CTAS_PER_SM", 2)) / g.n_slabs);
     g.grid_x = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
     return g;
 }
@@ -92,9 +92,14 @@ __device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long gro
     }
 }
 
-template <typename XT, int CPT, bool MASKED>
+// MODE 0: dense.  MODE 1: masked, per-row observed counts read from a.rowcnt (they are constant
+// during a fit).  MODE 2: masked and counting -- the first masked pass over a tensor; writes a.rowcnt.
+template <typename XT, int CPT, int MODE>
 __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_constant__ RowPassArgs a) {
     constexpr int VEC = VecOf<XT>::N;
+    constexpr bool MASKED = MODE != 0;
+    constexpr bool COUNT = MODE == 2;
+    const double pads = (double)(a.g.pitch - a.g.p);  // zero-filled pad columns look "observed"
     if (trip_is_dead(a.ctrl, a.trip)) return;
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     uint64_t* red_empty = red_full + kSlots;
     double* slots = reinterpret_cast<double*>(smem + tile_area + 256);
     const bool use_slots = g.lpr >= 32;
-    const size_t slot_doubles = use_slots ? (size_t)g.tile_rows * g.lpr * (MASKED ? 2 : 1) : 0;
+    const size_t slot_doubles = use_slots ? (size_t)g.tile_rows * g.lpr * (COUNT ? 2 : 1) : 0;
     const bool slabbed = g.n_slabs > 1;
     const double p_total = (double)g.p;
 
@@ -168,20 +173,28 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                     for (int i = gl; i < g.lpr; i += G) {
                         const int col = (i + skew) & (g.lpr - 1);
                         v += rowp[col];
-                        if (MASKED) cnt += rowc[col];
+                        if (COUNT) cnt += rowc[col];
                     }
                 }
                 for (int m = G >> 1; m >= 1; m >>= 1) {
                     v += shfl_xor_d(v, m);
-                    if (MASKED) cnt += shfl_xor_d(cnt, m);
+                    if (COUNT) cnt += shfl_xor_d(cnt, m);
                 }
                 if (r < rows && gl == 0) {
                     const long long grow = r0 + r;
                     if (slabbed) {
                         a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
-                        if (MASKED) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
+                        if (COUNT) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
                     } else {
-                        if (MASKED) v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
+                        if (MASKED) {
+                            if (COUNT) {
+                                cnt -= pads;
+                                if (a.rowcnt != nullptr) a.rowcnt[grow] = cnt;
+                            } else {
+                                cnt = a.rowcnt[grow];
+                            }
+                            v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
+                        }
                         row_epilogue(a, grow, v, d2);
                     }
                 }
@@ -227,6 +240,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
             const int r = rb + rl;
             const bool live = r < rows;
             double v = 0.0, cnt = 0.0;
+            int icnt = 0;
             if (live) {
 #pragma unroll
                 for (int k = 0; k < CPT; ++k) {
@@ -238,32 +252,42 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                     for (int j = 0; j < VEC; ++j) {
                         const XT xs = in.e[j];
                         if (MASKED) {
-                            const bool ob = (xs == xs) && (c0 + cg * VEC + j < g.p);
-                            v = fma(ob ? (double)xs : 0.0, wreg[k][j], v);
-                            cnt += ob ? 1.0 : 0.0;
+                            const bool ob = (xs == xs);
+                            const XT xc = ob ? xs : (XT)0;  // select in the storage type, convert once
+                            v = fma((double)xc, wreg[k][j], v);
+                            if (COUNT) icnt += ob ? 1 : 0;
                         } else {
                             v = fma((double)xs, wreg[k][j], v);
                         }
                     }
                 }
             }
+            if (COUNT) cnt = (double)icnt;
             if (use_slots) {
                 if (live) {
                     sp[(size_t)r * g.lpr + cl] = v;
-                    if (MASKED) cp[(size_t)r * g.lpr + cl] = cnt;
+                    if (COUNT) cp[(size_t)r * g.lpr + cl] = cnt;
                 }
             } else {
                 for (int m = g.lpr >> 1; m >= 1; m >>= 1) {
                     v += shfl_xor_d(v, m);
-                    if (MASKED) cnt += shfl_xor_d(cnt, m);
+                    if (COUNT) cnt += shfl_xor_d(cnt, m);
                 }
                 if (live && cl == 0) {
                     const long long grow = r0 + r;
                     if (slabbed) {
                         a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
-                        if (MASKED) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
+                        if (COUNT) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
                     } else {
-                        if (MASKED) v = v / cnt * p_total;
+                        if (MASKED) {
+                            if (COUNT) {
+                                cnt -= pads;
+                                if (a.rowcnt != nullptr) a.rowcnt[grow] = cnt;
+                            } else {
+                                cnt = a.rowcnt[grow];
+                            }
+                            v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
+                        }
                         row_epilogue(a, grow, v, d2);
                     }
                 }
@@ -293,10 +317,10 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
 // ---------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------
-template <typename XT, int CPT, bool MASKED>
+template <typename XT, int CPT, int MODE>
 static cudaError_t run_rowpass(const RowPassArgs& a, cudaStream_t s) {
-    auto kern = rowpass_kernel<XT, CPT, MASKED>;
-    const size_t smem = rowpass_smem(a.g, MASKED);
+    auto kern = rowpass_kernel<XT, CPT, MODE>;
+    const size_t smem = rowpass_smem(a.g, MODE == 2);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
@@ -305,8 +329,9 @@ static cudaError_t run_rowpass(const RowPassArgs& a, cudaStream_t s) {
 }
 
 template <typename XT>
-static cudaError_t rowpass_cpt(bool masked, const RowPassArgs& a, cudaStream_t s) {
-#define TPLS_RP(C) return masked ? run_rowpass<XT, C, true>(a, s) : run_rowpass<XT, C, false>(a, s)
+static cudaError_t rowpass_cpt(int mode, const RowPassArgs& a, cudaStream_t s) {
+#define TPLS_RP(C)                                                                                     \
+    return mode == 0 ? run_rowpass<XT, C, 0>(a, s) : (mode == 1 ? run_rowpass<XT, C, 1>(a, s) : run_rowpass<XT, C, 2>(a, s))
     switch (a.g.cpt) {
         case 1:
             TPLS_RP(1);
@@ -318,8 +343,9 @@ static cudaError_t rowpass_cpt(bool masked, const RowPassArgs& a, cudaStream_t s
 #undef TPLS_RP
 }
 
-cudaError_t launch_rowpass(int dtype, bool masked, const RowPassArgs& a, cudaStream_t s) {
-    return dtype == 0 ? rowpass_cpt<float>(masked, a, s) : rowpass_cpt<double>(masked, a, s);
+cudaError_t launch_rowpass(int dtype, int mode, const RowPassArgs& a, cudaStream_t s) {
+    if (mode == 1 && a.rowcnt == nullptr) return cudaErrorInvalidValue;
+    return dtype == 0 ? rowpass_cpt<float>(mode, a, s) : rowpass_cpt<double>(mode, a, s);
 }
 
 }  // namespace tpls
