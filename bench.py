@@ -56,30 +56,35 @@ def measured_peak_gbs():
 # --------------------------------------------------------------------------
 # synthetic inputs
 # --------------------------------------------------------------------------
-def make_shard_device(n_rows, rank, device, rows_offset=0):
+GEN_BLOCK = 15625  # rows per generator block: 1M / 64, so 1/2/4/8-way shards start on block boundaries
+
+
+def make_shard_device(row_start, n_rows, device):
     """CP-structured coupled pair in the spirit of import_synthetic (synthetic.py:59-77):
     shared scores T, per-tensor mode factors, Gaussian noise; generated on the device
-    (a 32.8 GB numpy draw is impractical).  Mode factors are identical on all ranks."""
+    (a 32.8 GB numpy draw is impractical).  Mode factors come from seed 215; the rows are
+    drawn block by block from seeds that depend only on the GLOBAL block index, so the
+    data set is the same whatever the number of ranks."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(215)
     yf = torch.randn(M, LATENT, generator=g, device=device, dtype=torch.float64)
     modes = [[torch.randn(d, LATENT, generator=g, device=device, dtype=torch.float64) for d in DIMS] for _ in range(2)]
-    g.manual_seed(1000 + rank)
-    T = torch.randn(n_rows, LATENT, generator=g, device=device, dtype=torch.float64)
-    Xs = []
-    for a, b in modes:
-        kr = (a[:, None, :] * b[None, :, :]).reshape(-1, LATENT).float()      # (P, L)
-        X = torch.empty(n_rows, *DIMS, dtype=torch.float32, device=device)
-        Xf = X.view(n_rows, -1)
-        step = 65536
-        for r0 in range(0, n_rows, step):
-            r1 = min(n_rows, r0 + step)
-            blk = T[r0:r1].float() @ kr.T
-            blk += ERROR * torch.randn(r1 - r0, kr.shape[0], generator=g, device=device, dtype=torch.float32)
-            Xf[r0:r1] = blk
-        Xs.append(X)
-    Y = T @ yf.T + ERROR * torch.randn(n_rows, M, generator=g, device=device, dtype=torch.float64)
+    krs = [(a[:, None, :] * b[None, :, :]).reshape(-1, LATENT).float() for a, b in modes]      # (P, L) each
+    Xs = [torch.empty(n_rows, *DIMS, dtype=torch.float32, device=device) for _ in modes]
+    Y = torch.empty(n_rows, M, dtype=torch.float64, device=device)
+    row_stop = row_start + n_rows
+    for blk in range(row_start // GEN_BLOCK, (row_stop + GEN_BLOCK - 1) // GEN_BLOCK):
+        g.manual_seed(1000 + blk)
+        b0 = blk * GEN_BLOCK
+        lo, hi = max(b0, row_start), min(b0 + GEN_BLOCK, row_stop)
+        T = torch.randn(GEN_BLOCK, LATENT, generator=g, device=device, dtype=torch.float64)
+        Yb = T @ yf.T + ERROR * torch.randn(GEN_BLOCK, M, generator=g, device=device, dtype=torch.float64)
+        Y[lo - row_start:hi - row_start] = Yb[lo - b0:hi - b0]
+        for X, kr in zip(Xs, krs):
+            blkx = T.float() @ kr.T
+            blkx += ERROR * torch.randn(GEN_BLOCK, kr.shape[0], generator=g, device=device, dtype=torch.float32)
+            X.view(n_rows, -1)[lo - row_start:hi - row_start] = blkx[lo - b0:hi - b0]
     return Xs, Y
 
 
@@ -224,10 +229,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         group = True
     n_total = args.rows or N_TOTAL
-    base, rem = divmod(n_total, world)
-    n_loc = base + (1 if rank < rem else 0)
+    from cmtf_pls_b200.sharding import row_block
+    row_lo, row_hi = row_block(n_total, rank, world)
+    n_loc = row_hi - row_lo
 
-    Xs, Y = make_shard_device(n_loc, rank, dev)
+    Xs, Y = make_shard_device(row_lo, n_loc, dev)
     torch.cuda.synchronize()
 
     def barrier():
@@ -314,6 +320,7 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peak_gbs()
+    prof.pop("spare", None)
     dom = max(("contract", "project", "deflate_contract"), key=lambda k: prof[k]["ms"])
     d = prof[dom]
     ach = d["bytes"] / d["launches"] / (d["ms"] / d["launches"] * 1e-3) / 1e9 if d["launches"] else None

@@ -10,6 +10,7 @@ include/tpls_b200.h.  There is no CPU fallback.
 
 from .tpls import tPLS
 from .cmtf import ctPLS
+from .validate import get_q2y, q2y_sweep
 
 
 
@@ -23,4 +24,4 @@ def trim_memory():
 
 
 __version__ = "0.1.0"
-__all__ = ["tPLS", "ctPLS", "trim_memory"]
+__all__ = ["tPLS", "ctPLS", "get_q2y", "q2y_sweep", "trim_memory"]

@@ -108,7 +108,8 @@ def np_dtype_of(a):
     return np.dtype(str(a.dtype).replace("torch.", ""))
 
 
-def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwrite=False, flags=0, profile=False):
+def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwrite=False, flags=0, profile=False,
+            row_weights=None):
     """Upload (or adopt) the shards, run the device fit, fetch the state.
 
     Returns a dict with T, W (list per tensor of loading matrices), U, Q, coef,
@@ -126,6 +127,9 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
         fl = _engine.X_MAY_OVERWRITE if (overwrite and _is_torch(X) and X.is_cuda) else 0
         eng.set_x(i, X, fl)
     eng.set_y(Y2)
+    if row_weights is not None:
+        w = row_weights if _is_torch(row_weights) else np.ascontiguousarray(row_weights, dtype=np.float64)
+        eng.set_row_weights(w)
     if profile:
         flags |= _engine.FIT_PROFILE
     try:

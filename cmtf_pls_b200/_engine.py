@@ -42,11 +42,11 @@ class Stats(C.Structure):
     ]
 
 
-KERNEL_CLASSES = ["colstat", "contract", "project", "deflate_contract", "residual", "rank1", "yside", "other"]
+KERNEL_CLASSES = ["colstat", "contract", "project", "deflate_contract", "residual", "rank1", "yside", "other", "nccl", "spare"]
 
 
 class Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("bytes", C.c_double * 8)]
+    _fields_ = [("ms", C.c_double * 10), ("launches", C.c_int64 * 10), ("bytes", C.c_double * 10)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/tpls_b200.h
@@ -61,6 +61,7 @@ SIGNATURES = {
     "tpls_comm_init": (C.c_int, [_H, _P, C.c_int, C.c_int]),
     "tpls_set_x": (C.c_int, [_H, C.c_int, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "tpls_set_y": (C.c_int, [_H, _P, C.c_int64, C.c_int64]),
+    "tpls_set_row_weights": (C.c_int, [_H, _P, C.c_int64]),
     "tpls_fit": (C.c_int, [_H, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]),
     "tpls_get_x_factor": (C.c_int, [_H, C.c_int, C.c_int, _P]),
     "tpls_get_y_factor": (C.c_int, [_H, C.c_int, _P]),
@@ -168,6 +169,13 @@ class Engine:
     def set_y(self, y):
         self._keep.append(y)
         self._ck(self.lib.tpls_set_y(self.h, _ptr(y), int(y.shape[0]), int(y.shape[1])))
+
+    def set_row_weights(self, w):
+        if w is None:
+            self._ck(self.lib.tpls_set_row_weights(self.h, None, 0))
+            return
+        self._keep.append(w)
+        self._ck(self.lib.tpls_set_row_weights(self.h, _ptr(w), int(w.shape[0])))
 
     def fit(self, n_tensors, n_components, tol, max_iter, flags=0):
         self._ck(self.lib.tpls_fit(self.h, n_tensors, n_components, float(tol), int(max_iter), flags))

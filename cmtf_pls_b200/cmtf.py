@@ -69,6 +69,7 @@ class ctPLS(Mapping):
         if any(self.Xs_hasMiss):
             print("At least one X has missing values")
         self._Xs_ref = Xs
+        self._Y_ref = Y
         self.n_iter_ = st["trips"]
         self.stats_ = st["stats"]
         self.profile_ = st["profile"]

@@ -72,6 +72,7 @@ struct tpls_ctx {
     long long n = 0;
     int m = 0, pitch_y = 0;
     double *y_src = nullptr, *y_work = nullptr;
+    double* row_w = nullptr;  // optional 0/1 sample weights of the next fit (cross-validation folds)
     PassGeom gy{}, gy_row{};
     double h2d_bytes = 0;
     // fit state
@@ -235,12 +236,6 @@ void free_tensor(tpls_handle h, Tensor& t) {
     t = Tensor();
 }
 
-int allreduce(tpls_handle h, double* buf, size_t count) {
-    if (h->world <= 1 || count == 0) return 0;
-    CKN(g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream));
-    h->stats.collectives++;
-    return 0;
-}
 
 // ---- per-class timing ----
 cudaEvent_t prof_event(tpls_handle h) {
@@ -285,6 +280,14 @@ void prof_collect(tpls_handle h) {
         h->ev_pool.push_back(r.b);
     }
     h->prof.clear();
+}
+
+int allreduce(tpls_handle h, double* buf, size_t count) {
+    if (h->world <= 1 || count == 0) return 0;
+    ProfScope ps(h, TPLS_K_NCCL, 0.0);
+    CKN(g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream));
+    h->stats.collectives++;
+    return 0;
 }
 
 // ---- pass wrappers that keep the launch / byte counters ----
@@ -345,6 +348,7 @@ int reduce_cols(tpls_handle h, const double* part, double* out, int n_cols, int 
     r.n_ss = n_ss;
     r.ctrl = ctrl;
     r.trip = trip;
+    ProfScope ps(h, TPLS_K_OTHER, 0.0);
     CK(launch_reduce_cols(r, h->stream));
     h->stats.kernel_launches++;
     return 0;
@@ -407,6 +411,7 @@ int tpls_destroy(tpls_handle h) {
     for (auto& t : h->x) free_tensor(h, t);
     if (h->y_src) pool_put(h, h->y_src);
     if (h->y_work) pool_put(h, h->y_work);
+    if (h->row_w) pool_put(h, h->row_w);
     if (h->slab) pool_put(h, h->slab);
     if (h->tmp_buf) pool_put(h, h->tmp_buf);
     pool_trim(h);
@@ -687,6 +692,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         c.x_in = t.src;
         c.zpart = t.zpart;
         c.cntpart = t.cntpart;
+        c.row_sw = h->row_w;
         TRY(col_pass(h, t.dtype, true, PF_COLSTAT, c));
         TRY(reduce_cols(h, t.zpart, A + t.off_colsum, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, nullptr, 0));
         TRY(reduce_cols(h, t.cntpart, A + t.off_colcnt, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, nullptr, 0));
@@ -697,22 +703,43 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         c.x_in = h->y_src;
         c.zpart = h->zpart_y;
         c.cntpart = h->cntpart_y;
+        c.row_sw = h->row_w;
         TRY(col_pass(h, TPLS_F64, true, PF_COLSTAT, c, TPLS_K_YSIDE));
         TRY(reduce_cols(h, h->zpart_y, A + h->off_ysum, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, nullptr, 0));
         TRY(reduce_cols(h, h->cntpart_y, A + h->off_ycnt, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, nullptr, 0));
-        CK(launch_fill(A + h->off_n, 1, (double)n, st));
-        h->stats.kernel_launches++;
+        if (h->row_w == nullptr) {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_fill(A + h->off_n, 1, (double)n, st));
+            h->stats.kernel_launches++;
+        } else {
+            // sample count of the fold = sum of the 0/1 weights
+            DotPairs d{};
+            d.n = n;
+            d.npairs = 1;
+            d.a[0] = h->row_w;
+            d.b[0] = h->row_w;
+            int gx = 1;
+            CK(launch_multi_dot(d, h->dotpart, &gx, st));
+            h->stats.kernel_launches++;
+            TRY(reduce_cols(h, h->dotpart, A + h->off_n, 1, 1, gx, nullptr, nullptr, 0, nullptr, 0));
+        }
     }
     TRY(allreduce(h, A, h->off_stats_end));
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
-        CK(launch_finalize_mean(t.dtype, A + t.off_colsum, A + t.off_colcnt, A + h->off_n, t.p, t.pitch, t.mean_d,
+        {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_finalize_mean(t.dtype, A + t.off_colsum, A + t.off_colcnt, A + h->off_n, t.p, t.pitch, t.mean_d,
                                 t.mean_native, t.miss_flag, st));
+            h->stats.kernel_launches++;
+        }
+    }
+    {
+        ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+        CK(launch_finalize_mean(TPLS_F64, A + h->off_ysum, A + h->off_ycnt, A + h->off_n, h->m, h->pitch_y, h->ymean_d,
+                            nullptr, h->ymiss_flag, st));
         h->stats.kernel_launches++;
     }
-    CK(launch_finalize_mean(TPLS_F64, A + h->off_ysum, A + h->off_ycnt, A + h->off_n, h->m, h->pitch_y, h->ymean_d,
-                            nullptr, h->ymiss_flag, st));
-    h->stats.kernel_launches++;
     {
         int flagsh[TPLS_MAX_TENSORS] = {0};
         for (int l = 0; l < L; ++l)
@@ -736,10 +763,19 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         c.x_out = h->y_work;
         c.col_w = h->ymean_d;
         c.sspart = h->sspart_y;
+        c.row_sw = h->row_w;
         TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c, TPLS_K_YSIDE));
         TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
-        CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U, st));
-        h->stats.kernel_launches++;
+        if (h->row_w != nullptr) {
+            // held-out rows of the centred Y are zeroed: they then drop out of u, Z, q and the stop test
+            CK(launch_scale_rows(h->y_work, n, h->pitch_y, h->row_w, st));
+            h->stats.kernel_launches++;
+        }
+        {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U, st));
+            h->stats.kernel_launches++;
+        }
     }
     // ---- centre X fused with the first contraction ----
     for (int l = 0; l < L; ++l) {
@@ -752,6 +788,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         c.row_u = h->U;
         c.zpart = t.zpart;
         c.sspart = t.sspart;
+        c.row_sw = h->row_w;
         TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ, c));
         TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, t.sspart, A + t.off_ss,
                         t.g.grid_x * t.g.n_slabs, nullptr, 0));
@@ -770,8 +807,11 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     for (int a = 0; a < R; ++a) {
         double* Ta = h->T + (size_t)a * n;
         double* Ua = h->U + (size_t)a * n;
-        CK(launch_reset_ctrl(h->ctrl, st));
-        h->stats.kernel_launches++;
+        {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_reset_ctrl(h->ctrl, st));
+            h->stats.kernel_launches++;
+        }
         for (int trip = 0; trip < max_iter; ++trip) {
             if (trip >= 1 + LOOK) {
                 const int back = trip - 1 - LOOK;
@@ -840,8 +880,11 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 TRY(col_pass(h, TPLS_F64, false, PF_CONTRACT, c, TPLS_K_YSIDE));
                 TRY(reduce_cols(h, h->zpart_y, A + h->off_q, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
                 TRY(allreduce(h, A + h->off_q, h->pitch_y));
-                CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, trip, st));
-                h->stats.kernel_launches++;
+                {
+                    ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+                    CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, trip, st));
+                    h->stats.kernel_launches++;
+                }
                 RowPassArgs r{};
                 r.g = h->gy_row;
                 r.x_in = h->y_work;
@@ -855,8 +898,11 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
                 const int nd2 = d2_grid(h->gy_row);
                 if (h->world > 1) {
-                    CK(launch_sum_small(h->d2part, nd2, A + h->off_d2, h->ctrl, trip, st));
-                    h->stats.kernel_launches++;
+                    {
+                        ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+                        CK(launch_sum_small(h->d2part, nd2, A + h->off_d2, h->ctrl, trip, st));
+                        h->stats.kernel_launches++;
+                    }
                     TRY(allreduce(h, A + h->off_d2, 1));
                     CK(launch_stop(h->ctrl, trip, A + h->off_d2, 1, tol, st));
                 } else {
@@ -873,6 +919,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             DotPairs d{};
             d.n = n;
             d.npairs = 2 * (a + 1);
+            d.w = h->row_w;
             for (int b = 0; b <= a; ++b) {
                 d.a[b] = h->T + (size_t)b * n;
                 d.b[b] = Ta;
@@ -880,17 +927,26 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 d.b[a + 1 + b] = Ua;
             }
             int gx = 1;
-            CK(launch_multi_dot(d, h->dotpart, &gx, st));
-            h->stats.kernel_launches++;
+            {
+                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+                CK(launch_multi_dot(d, h->dotpart, &gx, st));
+                h->stats.kernel_launches++;
+            }
             TRY(reduce_cols(h, h->dotpart, A + h->off_dots, d.npairs, d.npairs, gx, nullptr, nullptr, 0, nullptr, 0));
             TRY(allreduce(h, A + h->off_dots, d.npairs));
-            CK(launch_solve_coef(A + h->off_dots, h->gram, h->coef, R, a, h->ctrl, h->trips_dev, st));
-            h->stats.kernel_launches++;
+            {
+                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+                CK(launch_solve_coef(A + h->off_dots, h->gram, h->coef, R, a, h->ctrl, h->trips_dev, st));
+                h->stats.kernel_launches++;
+            }
         }
         // ---- Y deflation (tpls.py:113) + ||Y||^2 for R2Y ----
         {
-            CK(launch_lincomb(h->T, n, n, h->coef, R, a, h->svec, st));
-            h->stats.kernel_launches++;
+            {
+                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+                CK(launch_lincomb(h->T, n, n, h->coef, R, a, h->row_w, h->svec, st));
+                h->stats.kernel_launches++;
+            }
             ColPassArgs c{};
             c.g = h->gy;
             c.x_in = h->y_work;
@@ -898,13 +954,17 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             c.row_a = h->svec;
             c.col_w = h->qvec;
             c.sspart = h->sspart_y;
+            c.row_sw = h->row_w;
             TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c, TPLS_K_YSIDE));
             TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y + a + 1, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
         }
         // ---- X deflation (tpls.py:109) fused with the next component's first contraction ----
         if (a + 1 < R) {
-            CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U + (size_t)(a + 1) * n, st));
-            h->stats.kernel_launches++;
+            {
+                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+                CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U + (size_t)(a + 1) * n, st));
+                h->stats.kernel_launches++;
+            }
         }
         for (int l = 0; l < L; ++l) {
             Tensor& t = h->x[l];
@@ -915,6 +975,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             c.row_a = Ta;
             c.col_w = t.wkron + (size_t)a * t.pitch;
             c.sspart = t.sspart;
+            c.row_sw = h->row_w;
             if (a + 1 < R) {
                 c.row_u = h->U + (size_t)(a + 1) * n;
                 c.zpart = t.zpart;
@@ -1083,7 +1144,21 @@ int tpls_release_data(tpls_handle h) {
     }
     if (h->y_src) pool_put(h, h->y_src);
     if (h->y_work) pool_put(h, h->y_work);
-    h->y_src = h->y_work = nullptr;
+    if (h->row_w) pool_put(h, h->row_w);
+    h->y_src = h->y_work = h->row_w = nullptr;
+    return 0;
+}
+
+int tpls_set_row_weights(tpls_handle h, const double* w, int64_t n) {
+    if (!h) return fail(nullptr, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    if (h->row_w) pool_put(h, h->row_w);
+    h->row_w = nullptr;
+    if (w == nullptr) return 0;
+    if (n != h->n) return fail(h, "tpls_set_row_weights: %lld weights for %lld samples (call tpls_set_y first)", (long long)n, h->n);
+    TRY(pool_get(h, (void**)&h->row_w, sizeof(double) * n));
+    CK(cudaMemcpyAsync(h->row_w, w, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+    h->fitted = false;
     return 0;
 }
 

@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
             double ar = 1.0, ur = 0.0;
             if (DEFLATE && a.row_a != nullptr) ar = __ldg(a.row_a + grow);
             if (CONTRACT) ur = __ldg(a.row_u + grow);
+            // optional 0/1 sample weights (cross-validation folds): weighted column statistics and
+            // weighted residual norm; the row's own sum of squares is folded in once per row
+            const double sw = ((COLSTAT || SUMSQ) && a.row_sw != nullptr) ? __ldg(a.row_sw + grow) : 1.0;
+            const double ss_before = ss;
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
                 if (!cvalid[k]) continue;
@@ -164,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
                     if (MASKED && !ob) xd = 0.0;
                     if (CONTRACT) zacc[k][j] = fma(xd, ur, zacc[k][j]);
                     if (COLSTAT) {
-                        zacc[k][j] += xd;
-                        cacc[k][j] += ob ? 1.0 : 0.0;
+                        zacc[k][j] = fma(xd, sw, zacc[k][j]);
+                        cacc[k][j] += ob ? sw : 0.0;
                     }
                     if (SUMSQ) ss = fma(xd, xd, ss);
                 }
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
                     __stcs(reinterpret_cast<typename VecOf<XT>::type*>(xo + grow * g.pitch + c0 + cg * VEC), out.v);
                 }
             }
+            if (SUMSQ && a.row_sw != nullptr) ss = fma(sw, ss - ss_before, ss_before);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);

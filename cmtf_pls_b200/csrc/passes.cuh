@@ -65,6 +65,7 @@ struct ColPassArgs {
     const double* row_a;    // PF_DEFLATE per-row scalar, nullptr => 1
     const double* col_w;    // PF_DEFLATE per-column vector [pitch]
     const double* row_u;    // PF_CONTRACT per-row weights
+    const double* row_sw;   // optional 0/1 sample weights for PF_COLSTAT / PF_SUMSQ (nullptr => 1)
     double* zpart;          // [grid_x][pitch] per-CTA column partials
     double* cntpart;        // PF_COLSTAT [grid_x][pitch]
     double* sspart;         // PF_SUMSQ [n_slabs * grid_x]

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) multi_dot_kernel(const __grid_constant__ 
     const double* b = d.b[j];
     double s = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += (long long)gridDim.x * blockDim.x)
-        s = fma(a[i], b[i], s);
+        s = fma(d.w != nullptr ? a[i] * d.w[i] : a[i], b[i], s);
     s = block_sum(s, red);
     if (threadIdx.x == 0) part[(size_t)blockIdx.x * d.npairs + j] = s;
 }
@@ -167,18 +167,32 @@ cudaError_t launch_solve_coef(const double* dots, double* gram, double* coef, in
 }
 
 __global__ void lincomb_kernel(const double* T, long long n, long long ldt, const double* coef, int R, int a,
-                               double* out) {
+                               const double* row_w, double* out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int b = 0; b <= a; ++b) s = fma(T[b * ldt + i], coef[b * R + a], s);
-        out[i] = s;
+        out[i] = row_w != nullptr ? s * row_w[i] : s;
     }
 }
 
-cudaError_t launch_lincomb(const double* T, long long n, long long ldt, const double* coef, int R, int a, double* out,
-                           cudaStream_t s) {
+cudaError_t launch_lincomb(const double* T, long long n, long long ldt, const double* coef, int R, int a,
+                           const double* row_w, double* out, cudaStream_t s) {
     const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
-    lincomb_kernel<<<blocks, 256, 0, s>>>(T, n, ldt, coef, R, a, out);
+    lincomb_kernel<<<blocks, 256, 0, s>>>(T, n, ldt, coef, R, a, row_w, out);
+    return cudaGetLastError();
+}
+
+__global__ void scale_rows_kernel(double* y, long long n, int pitch, const double* w) {
+    const long long total = n * pitch;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x)
+        y[e] *= w[e / pitch];
+}
+
+cudaError_t launch_scale_rows(double* y, long long n, int pitch, const double* w, cudaStream_t s) {
+    const long long total = n * pitch;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (total + 255) / 256));
+    scale_rows_kernel<<<blocks, 256, 0, s>>>(y, n, pitch, w);
     return cudaGetLastError();
 }
 

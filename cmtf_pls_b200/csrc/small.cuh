@@ -30,6 +30,7 @@ cudaError_t launch_reset_ctrl(Ctrl* ctrl, cudaStream_t s);
 struct DotPairs {
     const double* a[64];
     const double* b[64];
+    const double* w;  // optional per-row weights (nullptr => 1)
     int npairs;
     long long n;
 };
@@ -42,8 +43,11 @@ cudaError_t launch_solve_coef(const double* dots, double* gram, double* coef, in
                               int* trips_out, cudaStream_t s);
 
 // s[i] = sum_{b<=a} T_b[i] * coef[b*R + a]      (T column-major, column stride ldt)
-cudaError_t launch_lincomb(const double* T, long long n, long long ldt, const double* coef, int R, int a, double* out,
-                           cudaStream_t s);
+cudaError_t launch_lincomb(const double* T, long long n, long long ldt, const double* coef, int R, int a,
+                           const double* row_w, double* out, cudaStream_t s);
+
+// y[i, :] *= w[i]   (zeroes the held-out rows of the centred Y in a cross-validation fold)
+cudaError_t launch_scale_rows(double* y, long long n, int pitch, const double* w, cudaStream_t s);
 
 // out (n x cols, C order) = in^T where `in` is column-major with column stride ld
 cudaError_t launch_transpose_out(const double* in, long long n, long long ld, int cols, double* out, cudaStream_t s);

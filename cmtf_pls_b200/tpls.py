@@ -67,6 +67,7 @@ class tPLS(Mapping):
         if self.X_hasMiss:
             print("X has missing values")
         self._X_ref = X
+        self._Y_ref = Y
         self.X_mean = st["X_mean"][0]
         self.Y_mean = st["Y_mean"]
         self.coef_ = st["coef"]

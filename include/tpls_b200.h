@@ -52,9 +52,10 @@ enum {
     TPLS_K_RESIDUAL = 4,         /* read-only residual norm after the last component */
     TPLS_K_RANK1 = 5,            /* single-CTA rank-1 step (tpls.py:84-88) */
     TPLS_K_YSIDE = 6,            /* passes over Y (q, u, Y deflation) */
-    TPLS_K_OTHER = 7
+    TPLS_K_OTHER = 7,            /* second reduction stages and the scalar tail of a trip */
+    TPLS_K_NCCL = 8              /* all-reduces */
 };
-#define TPLS_N_KERNEL_CLASSES 8
+#define TPLS_N_KERNEL_CLASSES 10
 
 #define TPLS_MAX_TENSORS 8
 #define TPLS_MAX_MODES 8
@@ -79,6 +80,14 @@ int tpls_comm_init(tpls_handle h, const void* id128, int rank, int world);
  * Caller memory is never modified unless TPLS_X_MAY_OVERWRITE is given. */
 int tpls_set_x(tpls_handle h, int index, const void* x, int dtype, int ndim, const int64_t* shape, int flags);
 int tpls_set_y(tpls_handle h, const double* y, int64_t n, int64_t m);
+
+/* Optional 0/1 sample weights for the NEXT fit (n = this rank's sample count; NULL clears them).  Rows with
+ * weight 0 are held out: they contribute to no sample-mode reduction (means, Z, q, the stop test, the
+ * regression, R2), but they are still centred, projected and deflated with their own projections -- so their
+ * rows of the score matrix are exactly transform() of the held-out data under the fold's model
+ * (tpls.py:145-165).  This is how a K-fold Q2Y sweep runs without copying X (validate.py:24-37 refits on
+ * sliced copies).  Call after tpls_set_y; cleared by tpls_release_data. */
+int tpls_set_row_weights(tpls_handle h, const double* w, int64_t n);
 
 /* The NIPALS fit: preprocess (tpls.py:44-71) + the component loop (tpls.py:76-120,
  * cmtf.py:88-140).  n_tensors = how many tpls_set_x slots are in use. */

@@ -265,6 +265,28 @@ def predict(state, Xs):
     return transform(state, Xs) @ state["coef"] @ state["Q"].T + state["Y_mean"]
 
 
+def q2y_kfold(Xs, Y, n_components, folds):
+    """Cross-validated Q2Y for 1..R components, the slow way: for every fold a refit on
+    the sliced training rows and a prediction of the held-out rows with the model
+    truncated to k components (formula of validate.py:35-37).  Also returns the
+    cross-validated scores."""
+    if not isinstance(Xs, list):
+        Xs = [Xs]
+    Y2 = Y.reshape(Y.shape[0], -1)
+    R = n_components
+    press = np.zeros(R)
+    cv = np.zeros((Y2.shape[0], R))
+    for held in folds:
+        train = np.setdiff1d(np.arange(Y2.shape[0]), held)
+        st = fit([x[train] for x in Xs], Y2[train], R, r2_mode="residual")
+        S = transform(st, [x[held] for x in Xs])
+        cv[held] = S
+        for k in range(1, R + 1):
+            pred = S[:, :k] @ st["coef"][:k, :k] @ st["Q"][:, :k].T + st["Y_mean"]
+            press[k - 1] += np.sum((pred - Y2[held]) ** 2)
+    return 1 - press / np.sum(Y2 ** 2), cv
+
+
 # --------------------------------------------------------------------------
 # virtual shards: the multi-GPU collective contract, on the CPU
 # --------------------------------------------------------------------------
