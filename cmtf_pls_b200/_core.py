@@ -9,6 +9,7 @@ final ``scores @ coef_ @ Q.T`` of predict).
 
 from __future__ import annotations
 
+import os
 from functools import reduce
 
 import numpy as np
@@ -76,6 +77,27 @@ def _ensure_comm(eng, group):
     box = [eng.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=dist.get_global_rank(pg, 0) if pg is not None else 0, group=pg)
     eng.init_comm(box[0], rank, world)
+    # one-shot peer-memory exchange for the per-trip all-reduces (NCCL stays the fallback)
+    if os.environ.get("TPLS_NO_XCHG", "") == "":
+        ok, why = True, ""
+        try:
+            mine = eng.xchg_handle()
+        except Exception as exc:  # noqa: BLE001
+            mine, ok, why = b"\0" * 64, False, str(exc)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=pg)
+        if ok:
+            try:
+                eng.xchg_open(handles)
+            except Exception as exc:  # noqa: BLE001 -- e.g. CUDA IPC unavailable in this container
+                ok, why = False, str(exc)
+        oks = [None] * world
+        dist.all_gather_object(oks, ok, group=pg)
+        if not all(oks):  # all ranks or none: a mixed set-up would deadlock
+            eng.xchg_open(None)
+            if rank == 0:
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({why or 'on another rank'}); NCCL is used for every all-reduce")
     _comm_ready.add(key)
     return rank, world
 

@@ -59,6 +59,8 @@ SIGNATURES = {
     "tpls_destroy": (C.c_int, [_H]),
     "tpls_comm_unique_id": (C.c_int, [_P]),
     "tpls_comm_init": (C.c_int, [_H, _P, C.c_int, C.c_int]),
+    "tpls_comm_xchg_handle": (C.c_int, [_H, _P]),
+    "tpls_comm_xchg_open": (C.c_int, [_H, _P]),
     "tpls_set_x": (C.c_int, [_H, C.c_int, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "tpls_set_y": (C.c_int, [_H, _P, C.c_int64, C.c_int64]),
     "tpls_set_row_weights": (C.c_int, [_H, _P, C.c_int64]),
@@ -159,6 +161,16 @@ class Engine:
 
     def init_comm(self, uid: bytes, rank: int, world: int):
         self._ck(self.lib.tpls_comm_init(self.h, C.c_char_p(uid), rank, world))
+
+    def xchg_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.tpls_comm_xchg_handle(self.h, buf))
+        return buf.raw
+
+    def xchg_open(self, handles):
+        """handles: list of the ranks' 64-byte IPC handles in rank order, or None to switch the exchange off."""
+        arg = None if handles is None else C.c_char_p(b"".join(handles))
+        self._ck(self.lib.tpls_comm_xchg_open(self.h, arg))
 
     # ---- data ----
     def set_x(self, index, x, flags=0):

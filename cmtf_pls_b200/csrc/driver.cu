@@ -19,6 +19,7 @@
 #include "passes.cuh"
 #include "rank1.cuh"
 #include "small.cuh"
+#include "xchg.cuh"
 
 using namespace tpls;
 
@@ -67,6 +68,12 @@ struct tpls_ctx {
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory exchange (xchg.cuh): own buffer + the peers' mappings
+    void* xchg_buf = nullptr;
+    void* xchg_peer[kXchgMaxRanks] = {nullptr};
+    int xchg_cap = 0;
+    bool xchg_ready = false;
+    unsigned long long xchg_seq = 0;
     // data
     Tensor x[TPLS_MAX_TENSORS];
     long long n = 0;
@@ -282,12 +289,45 @@ void prof_collect(tpls_handle h) {
     h->prof.clear();
 }
 
-int allreduce(tpls_handle h, double* buf, size_t count) {
+int allreduce_nccl(tpls_handle h, double* buf, size_t count) {
     if (h->world <= 1 || count == 0) return 0;
     ProfScope ps(h, TPLS_K_NCCL, 0.0);
     CKN(g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream));
     h->stats.collectives++;
     return 0;
+}
+
+// fills the communicator part of an exchange and launches it (never skipped: see xchg.cuh)
+int xchg_launch(tpls_handle h, XchgArgs& a) {
+    ProfScope ps(h, TPLS_K_NCCL, 0.0);
+    a.cap = h->xchg_cap;
+    a.rank = h->rank;
+    a.world = h->world;
+    a.seq = ++h->xchg_seq;
+    for (int r = 0; r < h->world; ++r) {
+        char* base = static_cast<char*>(h->xchg_peer[r]);
+        a.flags[r] = reinterpret_cast<unsigned long long*>(base);
+        a.data[r] = reinterpret_cast<double*>(base + kXchgHeaderBytes);
+    }
+    char* mine = static_cast<char*>(h->xchg_buf);
+    a.done_ctr = reinterpret_cast<unsigned int*>(mine + 512);
+    a.err = reinterpret_cast<int*>(mine + 520);
+    CK(launch_xchg(a, h->stream));
+    h->stats.kernel_launches++;
+    h->stats.collectives++;
+    return 0;
+}
+
+// Sum of a small replicated vector over the ranks: the one-shot peer-memory exchange when it is set up
+// (and the vector fits its slots), NCCL otherwise.
+int allreduce(tpls_handle h, double* buf, size_t count) {
+    if (h->world <= 1 || count == 0) return 0;
+    if (!h->xchg_ready || count > (size_t)h->xchg_cap) return allreduce_nccl(h, buf, count);
+    XchgArgs a{};
+    a.in = buf;
+    a.out = buf;
+    a.count = (int)count;
+    return xchg_launch(h, a);
 }
 
 // ---- pass wrappers that keep the launch / byte counters ----
@@ -415,6 +455,11 @@ int tpls_destroy(tpls_handle h) {
     if (h->slab) pool_put(h, h->slab);
     if (h->tmp_buf) pool_put(h, h->tmp_buf);
     pool_trim(h);
+    if (h->xchg_buf) {
+        for (int r = 0; r < h->world; ++r)
+            if (r != h->rank && h->xchg_peer[r]) cudaIpcCloseMemHandle(h->xchg_peer[r]);
+        cudaFree(h->xchg_buf);
+    }
     if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->h_done) cudaFreeHost(h->h_done);
     cudaEventDestroy(h->ev_start);
@@ -451,6 +496,47 @@ int tpls_comm_init(tpls_handle h, const void* id128, int rank, int world) {
     CKN(g_nccl.CommInitRank(&h->comm, world, id, rank));
     h->rank = rank;
     h->world = world;
+    return 0;
+}
+
+int tpls_comm_xchg_handle(tpls_handle h, void* handle64) {
+    if (!h) return fail(nullptr, "NULL handle");
+    if (h->world <= 1) return fail(h, "tpls_comm_xchg_handle: no communicator (call tpls_comm_init first)");
+    if (h->world > kXchgMaxRanks) return fail(h, "tpls_comm_xchg_handle: at most %d ranks", kXchgMaxRanks);
+    CK(cudaSetDevice(h->device));
+    if (!h->xchg_buf) {
+        h->xchg_cap = 1 << 17;  // doubles per slot (1 MiB): Z of all coupled tensors fits
+        const size_t bytes = kXchgHeaderBytes + 2 * sizeof(double) * (size_t)h->xchg_cap;
+        CK(cudaMalloc(&h->xchg_buf, bytes));
+        CK(cudaMemset(h->xchg_buf, 0, bytes));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t hnd;
+    CK(cudaIpcGetMemHandle(&hnd, h->xchg_buf));
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &hnd, sizeof hnd);
+    return 0;
+}
+
+int tpls_comm_xchg_open(tpls_handle h, const void* handles) {
+    if (!h) return fail(nullptr, "NULL handle");
+    if (handles == nullptr) {  // switch the exchange off again (every rank must do the same)
+        h->xchg_ready = false;
+        return 0;
+    }
+    if (!h->xchg_buf) return fail(h, "tpls_comm_xchg_open: call tpls_comm_xchg_handle first");
+    CK(cudaSetDevice(h->device));
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) {
+            h->xchg_peer[r] = h->xchg_buf;
+            continue;
+        }
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, static_cast<const char*>(handles) + 64 * (size_t)r, sizeof hnd);
+        CK(cudaIpcOpenMemHandle(&h->xchg_peer[r], hnd, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->xchg_seq = 0;
+    h->xchg_ready = true;
     return 0;
 }
 
@@ -804,6 +890,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     }
 
     const int LOOK = 1;
+    const bool fused_xchg = h->world > 1 && h->xchg_ready && h->zcat_len <= (size_t)h->xchg_cap;
     for (int a = 0; a < R; ++a) {
         double* Ta = h->T + (size_t)a * n;
         double* Ua = h->U + (size_t)a * n;
@@ -830,10 +917,24 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                     c.ctrl = h->ctrl;
                     c.trip = trip;
                     TRY(col_pass(h, t.dtype, t.masked, PF_CONTRACT, c));
-                    TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
+                    if (!fused_xchg)
+                        TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
                 }
             }
-            TRY(allreduce(h, A + h->off_zcat, h->zcat_len));
+            if (fused_xchg && trip > 0) {
+                // second reduction stage of every tensor + the cross-GPU sum in ONE kernel
+                XchgArgs xa{};
+                xa.n_sets = L;
+                for (int l = 0; l < L; ++l) {
+                    Tensor& t = h->x[l];
+                    xa.sets[l] = XchgSet{t.zpart, t.g.grid_x, t.pitch, t.pitch, (int)(t.off_z - h->off_zcat)};
+                }
+                xa.out = A + h->off_zcat;
+                xa.count = (int)h->zcat_len;
+                TRY(xchg_launch(h, xa));
+            } else {
+                TRY(allreduce(h, A + h->off_zcat, h->zcat_len));
+            }
             // K3: rank-1 weight vectors, one CTA per tensor
             {
                 Rank1Args ra{};
@@ -878,8 +979,17 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 c.ctrl = h->ctrl;
                 c.trip = trip;
                 TRY(col_pass(h, TPLS_F64, false, PF_CONTRACT, c, TPLS_K_YSIDE));
-                TRY(reduce_cols(h, h->zpart_y, A + h->off_q, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
-                TRY(allreduce(h, A + h->off_q, h->pitch_y));
+                if (fused_xchg) {
+                    XchgArgs xa{};
+                    xa.n_sets = 1;
+                    xa.sets[0] = XchgSet{h->zpart_y, h->gy.grid_x, h->pitch_y, h->pitch_y, 0};
+                    xa.out = A + h->off_q;
+                    xa.count = h->pitch_y;
+                    TRY(xchg_launch(h, xa));
+                } else {
+                    TRY(reduce_cols(h, h->zpart_y, A + h->off_q, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
+                    TRY(allreduce(h, A + h->off_q, h->pitch_y));
+                }
                 {
                     ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
                     CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, trip, st));
@@ -897,7 +1007,19 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 r.trip = trip;
                 TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
                 const int nd2 = d2_grid(h->gy_row);
-                if (h->world > 1) {
+                if (fused_xchg) {
+                    // partial sums of ||u_old - u_new||^2 -> global sum -> stop test, one kernel
+                    XchgArgs xa{};
+                    xa.n_sets = 1;
+                    xa.sets[0] = XchgSet{h->d2part, nd2, 1, 1, 0};
+                    xa.out = A + h->off_d2;
+                    xa.count = 1;
+                    xa.ctrl = h->ctrl;
+                    xa.trip = trip;
+                    xa.tol = tol;
+                    xa.do_stop = 1;
+                    TRY(xchg_launch(h, xa));
+                } else if (h->world > 1) {
                     {
                         ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
                         CK(launch_sum_small(h->d2part, nd2, A + h->off_d2, h->ctrl, trip, st));
@@ -905,10 +1027,11 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                     }
                     TRY(allreduce(h, A + h->off_d2, 1));
                     CK(launch_stop(h->ctrl, trip, A + h->off_d2, 1, tol, st));
+                    h->stats.kernel_launches++;
                 } else {
                     CK(launch_stop(h->ctrl, trip, h->d2part, nd2, tol, st));
+                    h->stats.kernel_launches++;
                 }
-                h->stats.kernel_launches++;
             }
             CK(cudaMemcpyAsync(&h->h_done[trip], &h->ctrl->done_trip, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(h->ev_trip[trip & 3], st));
@@ -990,7 +1113,9 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     }
 
     // ---- R2X / R2Y from the residual norms ----
-    TRY(allreduce(h, A + h->off_ss, h->ss_len));
+    // through NCCL on purpose: it cannot complete before every peer has finished all earlier exchanges,
+    // so no rank can leave the fit (and possibly free its exchange buffer) while a peer still reads it
+    TRY(allreduce_nccl(h, A + h->off_ss, h->ss_len));
     std::vector<double> ss(h->ss_len);
     h->trips.assign(R, 0);
     CK(cudaMemcpyAsync(ss.data(), A + h->off_ss, sizeof(double) * h->ss_len, cudaMemcpyDeviceToHost, st));
@@ -1001,6 +1126,11 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
     h->stats.fit_ms = ms;
     prof_collect(h);
+    if (h->xchg_ready) {
+        int xerr = 0;
+        CK(cudaMemcpy(&xerr, static_cast<char*>(h->xchg_buf) + 520, sizeof(int), cudaMemcpyDeviceToHost));
+        if (xerr) return fail(h, "tpls_fit: a peer-memory exchange timed out (a rank died or fell out of step)");
+    }
     for (int l = 0; l < L; ++l) {
         h->r2x[l].assign(R, 0.0);
         const double* s = ss.data() + (h->x[l].off_ss - h->off_ss);

@@ -1,0 +1,118 @@
+// One-shot peer-memory all-reduce fused with the local second-stage reduction -- see xchg.cuh.
+#include "xchg.cuh"
+
+#include <algorithm>
+
+namespace tpls {
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// chunk = 32 consecutive elements of the exchanged vector; 256 threads = 32 columns x 8 groups
+__global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgArgs a) {
+    __shared__ double fold[8][33];
+    const int slot = (int)(a.seq & 1ull);
+    const size_t base = (size_t)slot * a.cap;
+    double* mine = a.data[a.rank] + base;
+    const int cl = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int n_chunks = (a.count + 31) >> 5;
+
+    // ---- phase 1: fold the local partials of my chunks into the local slot ----
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int idx = chunk * 32 + cl;
+        double v = 0.0;
+        if (a.n_sets == 0) {
+            if (q == 0 && idx < a.count) v = a.in[idx];
+        } else if (idx < a.count) {
+            // which block of partials does this element belong to?
+            int s = 0;
+            while (s + 1 < a.n_sets && idx >= a.sets[s + 1].off) ++s;
+            const XchgSet& S = a.sets[s];
+            const int c = idx - S.off;
+            if (c < S.n_cols) {
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                int b = q;
+                for (; b + 24 < S.n_parts; b += 32) {
+                    t0 += S.part[(size_t)(b + 0) * S.stride + c];
+                    t1 += S.part[(size_t)(b + 8) * S.stride + c];
+                    t2 += S.part[(size_t)(b + 16) * S.stride + c];
+                    t3 += S.part[(size_t)(b + 24) * S.stride + c];
+                }
+                for (; b < S.n_parts; b += 8) t0 += S.part[(size_t)b * S.stride + c];
+                v = (t0 + t1) + (t2 + t3);
+            }
+        }
+        __syncthreads();
+        fold[q][cl] = v;
+        __syncthreads();
+        if (q == 0 && idx < a.count) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += fold[k][cl];
+            mine[idx] = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // cumulative: the CTA's slot writes (ordered by the barrier) become visible first
+        const unsigned int old = atomicAdd(a.done_ctr, 1u);
+        if (old == gridDim.x - 1) {
+            atomicExch(a.done_ctr, 0u);
+            __threadfence_system();
+            for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, a.seq);
+        }
+        // ---- phase 2: wait for every rank's announcement in the LOCAL flag words ----
+        const long long t0 = clock64();
+        for (int r = 0; r < a.world; ++r) {
+            while (ld_acquire_sys(a.flags[a.rank] + r) < a.seq) {
+                if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died
+                    atomicExch(a.err, 1);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int idx = chunk * 32 + cl;
+        double v = 0.0;
+        if (idx < a.count)
+            for (int r = q; r < a.world; r += 8) v += ld_relaxed_sys(a.data[r] + base + idx);
+        __syncthreads();
+        fold[q][cl] = v;
+        __syncthreads();
+        if (q == 0 && idx < a.count) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += fold[k][cl];
+            a.out[idx] = t;
+            if (a.do_stop && idx == 0 && !trip_is_dead(a.ctrl, a.trip)) {
+                a.ctrl->trips_taken = a.trip + 1;
+                a.ctrl->last_d2 = t;
+                if (a.trip >= 1 && sqrt(t) < a.tol) a.ctrl->done_trip = a.trip;
+            }
+        }
+    }
+}
+
+cudaError_t launch_xchg(const XchgArgs& a, cudaStream_t s) {
+    const int n_chunks = (a.count + 31) / 32;
+    const int blocks = std::max(1, std::min(444, n_chunks));  // all CTAs must be co-resident: 3 per SM is safe
+    xchg_kernel<<<blocks, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace tpls

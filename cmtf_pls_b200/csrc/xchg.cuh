@@ -1,0 +1,56 @@
+// One-shot all-reduce of small replicated vectors over NVLink peer memory, fused with the second
+// stage of the local reduction that produces them.
+//
+// Every rank owns an exchange buffer (cudaMalloc + cudaIpc handle, mapped by all peers):
+//   flags[r]      sequence number of the latest exchange rank r has published here
+//   data[2][cap]  two slots, used alternately
+// One kernel per exchange and rank:
+//   (1) fold this rank's per-CTA partials (or copy a ready vector) straight into the local slot,
+//       fence at system scope, and let the last CTA announce `seq` in every peer's flag word with
+//       a remote store;
+//   (2) wait until every rank's flag here reached `seq`, then add the W slots (own + peers',
+//       remote loads issued in parallel) in rank order -- every rank adds in the same order, so
+//       the result is bit-identical everywhere -- and, for the stop test, update the control block.
+// Two slots are enough: finishing exchange k+1 needs every peer's flag k+1, which a peer only
+// raises after it finished reading slot k.  Exchange kernels are never skipped (not even in the
+// empty trips enqueued past convergence), so sequence numbers and slots stay aligned on all ranks.
+// Replaces reduce_cols + ncclAllReduce (+ stop) on the per-trip critical path.
+#pragma once
+
+#include "common.cuh"
+
+namespace tpls {
+
+constexpr int kXchgMaxRanks = 16;
+constexpr int kXchgMaxSets = 8;
+constexpr size_t kXchgHeaderBytes = 1024;
+
+struct XchgSet {          // one block of per-CTA partials to fold: out[off + c] = sum_b part[b*stride + c]
+    const double* part;
+    int n_parts, stride, n_cols, off;
+};
+
+struct XchgArgs {
+    // input: either `n_sets` partial blocks, or (n_sets == 0) the ready vector `in`
+    XchgSet sets[kXchgMaxSets];
+    int n_sets;
+    const double* in;
+    double* out;             // summed vector [count] (may alias in)
+    int count;
+    int cap;                 // doubles per slot
+    int rank, world;
+    unsigned long long seq;  // 1, 2, 3, ... identical on all ranks
+    unsigned long long* flags[kXchgMaxRanks];  // flags[r] = rank r's flag array (flags[rank] is local)
+    double* data[kXchgMaxRanks];               // data[r] = rank r's slots
+    unsigned int* done_ctr;                    // local: CTAs that finished phase 1
+    int* err;                                  // local: set to 1 on a wait timeout
+    // optional stop test on out[0] (tpls.py:103): trip >= 1 and sqrt(out[0]) < tol
+    Ctrl* ctrl;
+    int trip;
+    double tol;
+    int do_stop;
+};
+
+cudaError_t launch_xchg(const XchgArgs& a, cudaStream_t s);
+
+}  // namespace tpls

@@ -74,6 +74,13 @@ int tpls_destroy(tpls_handle h);
 int tpls_comm_unique_id(void* id128);
 int tpls_comm_init(tpls_handle h, const void* id128, int rank, int world);
 
+/* Optional, after tpls_comm_init: replace the small per-trip all-reduces (Z, q, the stop norm; a few KB each)
+ * by a one-shot exchange over NVLink peer memory (csrc/xchg.cuh).  Every rank obtains the 64-byte CUDA IPC
+ * handle of its exchange buffer, the caller all-gathers the handles in rank order, every rank opens them.
+ * Without these two calls NCCL is used throughout. */
+int tpls_comm_xchg_handle(tpls_handle h, void* handle64);
+int tpls_comm_xchg_open(tpls_handle h, const void* handles /* world x 64 bytes */);
+
 /* Training data.  X number `index` of `n_tensors` coupled tensors, C-ordered,
  * shape[0] = this rank's sample count; Y is (n, m) float64 C-ordered.
  * Replaces the array arguments of tPLS.fit (tpls.py:73) / ctPLS.fit (cmtf.py:85).
