@@ -131,7 +131,7 @@ def np_dtype_of(a):
 
 
 def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwrite=False, flags=0, profile=False,
-            row_weights=None):
+            row_weights=None, algorithm="stream"):
     """Upload (or adopt) the shards, run the device fit, fetch the state.
 
     Returns a dict with T, W (list per tensor of loading matrices), U, Q, coef,
@@ -152,6 +152,10 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
     if row_weights is not None:
         w = row_weights if _is_torch(row_weights) else np.ascontiguousarray(row_weights, dtype=np.float64)
         eng.set_row_weights(w)
+    if algorithm == "covariance":
+        flags |= _engine.FIT_COVARIANCE
+    elif algorithm != "stream":
+        raise ValueError("algorithm must be 'stream' or 'covariance'")
     if profile:
         flags |= _engine.FIT_PROFILE
     try:

@@ -20,6 +20,7 @@ F32, F64 = 0, 1
 X_MAY_OVERWRITE = 1
 FIT_NORMALIZE_ON_BREAK = 1
 FIT_PROFILE = 2
+FIT_COVARIANCE = 4
 MAX_TENSORS = 8
 MAX_MODES = 8
 
@@ -39,6 +40,7 @@ class Stats(C.Structure):
         ("total_trips", C.c_int64),
         ("collectives", C.c_int64),
         ("h2d_bytes", C.c_double),
+        ("covariance_mode", C.c_int64),
     ]
 
 

@@ -15,11 +15,14 @@ from . import _core
 class ctPLS(Mapping):
     """Coupled tensor PLS (cmtf_pls/cmtf.py:15)."""
 
-    def __init__(self, n_components: int, device=None, process_group=None):
+    def __init__(self, n_components: int, device=None, process_group=None, algorithm="stream"):
         super().__init__()
         self.n_components = n_components
         self.device = device
         self.process_group = process_group
+        # "stream": two passes over X per inner trip (the reference's loop, the benchmark contract);
+        # "covariance": one cross-covariance pass per component, inner loop on (P x M) data -- same results
+        self.algorithm = algorithm
 
     # ---- Mapping protocol (cmtf.py:23-42) ----
     def __getitem__(self, index):
@@ -51,7 +54,8 @@ class ctPLS(Mapping):
             assert X.ndim >= 2
         assert Y.ndim <= 2, "Only a matrix (2-mode tensor) Y is acceptable."
         st = _core.run_fit(Xs, Y, self.n_components, tol, max_iter, device=self.device,
-                           group=self.process_group, overwrite=overwrite_x, profile=profile)
+                           group=self.process_group, overwrite=overwrite_x, profile=profile,
+                           algorithm=self.algorithm)
         self.Xs_len = len(Xs)
         self.Xs_dim = [X.ndim for X in Xs]
         self.Xs_shape = [tuple(X.shape) for X in Xs]

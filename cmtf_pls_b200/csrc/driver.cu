@@ -42,6 +42,10 @@ struct Tensor {
     PassGeom g{};   // column passes
     PassGeom gr{};      // row passes
     PassGeom gr_cnt{};  // the one counting row pass of a masked fit (needs twice the slot space)
+    PassGeom gc{};      // cross-covariance passes (covariance mode)
+    double *covpart = nullptr, *zscratch = nullptr, *sspart_cov = nullptr;
+    int cov_mr = 0;     // accumulators per column of the cross-covariance pass
+    size_t off_c = 0;   // arena offset of C [cov_mr][pitch]
     // per-fit device buffers
     double *zpart = nullptr, *cntpart = nullptr, *sspart = nullptr;
     double *mean_d = nullptr, *wkron = nullptr, *tpart = nullptr, *cpart = nullptr, *r1_scratch = nullptr;
@@ -114,6 +118,9 @@ struct tpls_ctx {
     std::vector<double> r2y;
     std::vector<int> trips;
     double n_total = 0;
+    bool cov_alloc = false;  // the last alloc_fit reserved the covariance-mode buffers
+    size_t off_cov = 0, cov_len = 0, off_gram_y = 0;
+    double* grampart = nullptr;
     tpls_stats stats{};
     // optional per-kernel-class timing (TPLS_FIT_PROFILE): event pairs on the launching stream
     bool profile = false;
@@ -676,6 +683,19 @@ static int layout_fit(tpls_handle h, int L, int R) {
     }
     off += R + 1;  // Y
     h->ss_len = off - h->off_ss;
+    // covariance mode: C of every tensor followed by Y'Y, one all-reduce per component
+    off = (off + 1) / 2 * 2;
+    h->off_cov = off;
+    if (h->cov_alloc) {
+        const int mr_alloc = h->m <= 1 ? 2 : (h->m <= 2 ? 4 : 8);  // room for the masked (row-rescaled) block when m <= 4
+        for (int l = 0; l < L; ++l) {
+            h->x[l].off_c = off;
+            off += (size_t)mr_alloc * h->x[l].pitch;
+        }
+        h->off_gram_y = off;
+        off += 64;
+    }
+    h->cov_len = off - h->off_cov;
     h->arena_doubles = off;
     TRY(dev_alloc(h, (void**)&h->arena, off * sizeof(double), tr));
 
@@ -692,6 +712,7 @@ static int layout_fit(tpls_handle h, int L, int R) {
     TRY(dev_alloc(h, (void**)&h->sspart_y, sizeof(double) * h->gy.grid_x * h->gy.n_slabs, tr));
     TRY(dev_alloc(h, (void**)&h->d2part, sizeof(double) * 2048, tr));
     TRY(dev_alloc(h, (void**)&h->dotpart, sizeof(double) * 148 * 64, tr));
+    TRY(dev_alloc(h, (void**)&h->grampart, sizeof(double) * 148 * 64, tr));
     TRY(dev_alloc(h, (void**)&h->scratch_ss, sizeof(double) * 8, tr));
     TRY(dev_alloc(h, (void**)&h->trips_dev, sizeof(int) * R, tr));
     TRY(dev_alloc(h, (void**)&h->ymiss_flag, sizeof(int) * 4, tr));
@@ -708,6 +729,13 @@ static int layout_fit(tpls_handle h, int L, int R) {
         TRY(dev_alloc(h, (void**)&t.wkron, sizeof(double) * t.pitch * R, tr));
         TRY(dev_alloc(h, (void**)&t.rowcnt, sizeof(double) * n, tr));
         t.rowcnt_ready = false;
+        if (h->cov_alloc) {
+            const int mr_alloc = h->m <= 1 ? 2 : (h->m <= 2 ? 4 : 8);
+            t.gc = make_cov_geom(n, t.p, t.pitch, t.elem, h->sm_count);
+            TRY(dev_alloc(h, (void**)&t.covpart, sizeof(double) * (size_t)t.gc.grid_x * mr_alloc * t.pitch, tr));
+            TRY(dev_alloc(h, (void**)&t.sspart_cov, sizeof(double) * (size_t)t.gc.grid_x * t.gc.n_slabs, tr));
+            TRY(dev_alloc(h, (void**)&t.zscratch, sizeof(double) * t.pitch, tr));
+        }
         if (t.g.n_slabs > 1) {
             TRY(dev_alloc(h, (void**)&t.tpart, sizeof(double) * n * t.g.n_slabs, tr));
             TRY(dev_alloc(h, (void**)&t.cpart, sizeof(double) * n * t.g.n_slabs, tr));
@@ -745,6 +773,220 @@ static void fill_rank1_task(tpls_handle h, Tensor& t, int a, Rank1Task& k, bool 
     k.sweeps = t.sweeps;
 }
 
+
+// Regression of u_a on the scores so far and the Y deflation that follows (tpls.py:110-113), shared by the
+// streaming and the covariance component loops.  stream_mode: the trip count comes from the control block.
+static int component_tail(tpls_handle h, int R, int a, double* ss_y, bool stream_mode) {
+    cudaStream_t st = h->stream;
+    const long long n = h->n;
+    double* A = h->arena;
+    double* Ta = h->T + (size_t)a * n;
+    double* Ua = h->U + (size_t)a * n;
+    // ---- regression on the scores so far (tpls.py:110-112) ----
+    {
+        DotPairs d{};
+        d.n = n;
+        d.npairs = 2 * (a + 1);
+        d.w = h->row_w;
+        for (int b = 0; b <= a; ++b) {
+            d.a[b] = h->T + (size_t)b * n;
+            d.b[b] = Ta;
+            d.a[a + 1 + b] = h->T + (size_t)b * n;
+            d.b[a + 1 + b] = Ua;
+        }
+        int gx = 1;
+        {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_multi_dot(d, h->dotpart, &gx, st));
+            h->stats.kernel_launches++;
+        }
+        TRY(reduce_cols(h, h->dotpart, A + h->off_dots, d.npairs, d.npairs, gx, nullptr, nullptr, 0, nullptr, 0));
+        TRY(allreduce(h, A + h->off_dots, d.npairs));
+        {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_solve_coef(A + h->off_dots, h->gram, h->coef, R, a, h->ctrl, stream_mode ? h->trips_dev : nullptr, st));
+            h->stats.kernel_launches++;
+        }
+    }
+    // ---- Y deflation (tpls.py:113) + ||Y||^2 for R2Y ----
+    {
+        {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_lincomb(h->T, n, n, h->coef, R, a, h->row_w, h->svec, st));
+            h->stats.kernel_launches++;
+        }
+        ColPassArgs c{};
+        c.g = h->gy;
+        c.x_in = h->y_work;
+        c.x_out = h->y_work;
+        c.row_a = h->svec;
+        c.col_w = h->qvec;
+        c.sspart = h->sspart_y;
+        c.row_sw = h->row_w;
+        TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c, TPLS_K_YSIDE));
+        TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y + a + 1, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// covariance-mode component loop: per component one cross-covariance pass
+// (centring / deflation fused in), the inner iteration on (P x M)-sized data in a single kernel,
+// one projection pass; no per-trip pass over X and no per-trip collective.
+// ---------------------------------------------------------------------------
+static int pow2_at_least(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static bool cov_supported(tpls_handle h, int L) {
+    if (!h->cov_alloc || h->m > 8) return false;
+    for (int l = 0; l < L; ++l)
+        if (h->x[l].masked && h->m > 4) return false;
+    return true;
+}
+
+static int fit_covariance(tpls_handle h, int L, int R, double tol, int max_iter, int flags, double* ss_y) {
+    cudaStream_t st = h->stream;
+    const long long n = h->n;
+    double* A = h->arena;
+    const int M = h->m;
+
+    size_t r1_smem = 0;
+    bool r1_use_smem = true;
+    for (int l = 0; l < L; ++l) r1_smem = std::max(r1_smem, h->x[l].r1_ws * sizeof(double));
+    if (r1_smem > 200 * 1024) {
+        r1_use_smem = false;
+        r1_smem = 0;
+    }
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        t.cov_mr = t.masked ? pow2_at_least(2 * M) : pow2_at_least(M);
+        if (t.masked) {
+            // observed entries per row (constant during the fit): one counting row pass with zero weights
+            RowPassArgs r{};
+            r.g = t.gr_cnt;
+            r.x_in = t.src;
+            r.col_w = t.wkron;  // still all zero
+            r.t_out = h->svec;
+            r.tpart = t.tpart;
+            r.cpart = t.cpart;
+            r.rowcnt = t.rowcnt;
+            r.epi = 0;
+            r.div = 1.0;
+            TRY(row_pass(h, t.dtype, 2, r));
+            t.rowcnt_ready = true;
+        }
+    }
+
+    for (int a = 0; a < R; ++a) {
+        double* Ta = h->T + (size_t)a * n;
+        double* Ua = h->U + (size_t)a * n;
+        // ---- cross-covariance pass: centring (a == 0) or the deflation by component a-1 fused in ----
+        for (int l = 0; l < L; ++l) {
+            Tensor& t = h->x[l];
+            CovPassArgs c{};
+            c.g = t.gc;
+            c.x_in = a == 0 ? t.src : t.work;
+            c.x_out = t.work;
+            c.row_a = a == 0 ? nullptr : h->T + (size_t)(a - 1) * n;
+            c.col_w = a == 0 ? t.mean_d : t.wkron + (size_t)(a - 1) * t.pitch;
+            c.row_sw = h->row_w;
+            c.y = h->y_work;
+            c.pitch_y = h->pitch_y;
+            c.m = M;
+            c.rowcnt = t.rowcnt;
+            c.cpart = t.covpart;
+            c.c_stride = (size_t)t.cov_mr * t.pitch;
+            c.sspart = t.sspart_cov;
+            {
+                const double bytes = 2.0 * (double)n * t.pitch * t.elem;
+                ProfScope ps(h, TPLS_K_DEFLATE_CONTRACT, bytes);
+                CK(launch_covpass(t.dtype, t.masked, t.cov_mr, c, st));
+                h->stats.kernel_launches++;
+                h->stats.streamed_bytes += bytes;
+            }
+            TRY(reduce_cols(h, t.covpart, A + t.off_c, (int)c.c_stride, (int)c.c_stride, t.gc.grid_x, t.sspart_cov,
+                            A + t.off_ss + a, t.gc.grid_x * t.gc.n_slabs, nullptr, 0));
+        }
+        // ---- Y'Y of the current Y for the stop test ----
+        {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            int gx = 1;
+            CK(launch_gram_rows(h->y_work, n, h->pitch_y, M, h->grampart, &gx, st));
+            h->stats.kernel_launches++;
+            TRY(reduce_cols(h, h->grampart, A + h->off_gram_y, M * M, M * M, gx, nullptr, nullptr, 0, nullptr, 0));
+        }
+        TRY(allreduce(h, A + h->off_cov, h->cov_len));
+        // ---- the whole inner iteration of this component, on the device ----
+        {
+            CovLoopArgs la{};
+            la.n_tasks = L;
+            la.m = M;
+            la.gram_y = A + h->off_gram_y;
+            la.tol = tol;
+            la.max_iter = max_iter;
+            la.normalize_on_break = (flags & TPLS_FIT_NORMALIZE_ON_BREAK) ? 1 : 0;
+            la.q_out = h->Q + (size_t)a * M;
+            la.qvec = h->qvec;
+            la.pitch_y = h->pitch_y;
+            la.trips_out = h->trips_dev + a;
+            for (int l = 0; l < L; ++l) {
+                Tensor& t = h->x[l];
+                fill_rank1_task(h, t, a, la.t[l], r1_use_smem);
+                la.t[l].z = t.zscratch;
+                la.C[l] = A + t.off_c;
+                la.masked[l] = t.masked ? t.cov_mr / 2 : 0;
+            }
+            ProfScope ps(h, TPLS_K_RANK1, 0.0);
+            CK(launch_cov_loop(la, r1_smem, r1_use_smem, st));
+            h->stats.kernel_launches++;
+        }
+        // ---- scores of the converged component: t = X x_2 w2 ..., u = Y q ----
+        for (int l = 0; l < L; ++l) {
+            Tensor& t = h->x[l];
+            RowPassArgs r{};
+            r.g = t.gr;
+            r.x_in = t.work;
+            r.col_w = t.wkron + (size_t)a * t.pitch;
+            r.t_out = Ta;
+            r.tpart = t.tpart;
+            r.cpart = t.cpart;
+            r.rowcnt = t.rowcnt;
+            r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
+            r.div = (double)L;
+            TRY(row_pass(h, t.dtype, t.masked ? 1 : 0, r));
+        }
+        {
+            RowPassArgs r{};
+            r.g = h->gy_row;
+            r.x_in = h->y_work;
+            r.col_w = h->qvec;
+            r.t_out = Ua;
+            r.epi = 0;
+            r.div = 1.0;
+            TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
+        }
+        TRY(component_tail(h, R, a, ss_y, false));
+    }
+    // ---- residual norm after the last component ----
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        ColPassArgs c{};
+        c.g = t.g;
+        c.x_in = t.work;
+        c.x_out = t.work;
+        c.row_a = h->T + (size_t)(R - 1) * n;
+        c.col_w = t.wkron + (size_t)(R - 1) * t.pitch;
+        c.sspart = t.sspart;
+        c.row_sw = h->row_w;
+        TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_SUMSQ, c));
+        TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, t.sspart, A + t.off_ss + R, t.g.grid_x * t.g.n_slabs, nullptr, 0));
+    }
+    return 0;
+}
+
 int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max_iter, int flags) {
     if (!h) return fail(nullptr, "NULL handle");
     const int L = n_tensors, R = n_components;
@@ -765,6 +1007,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     h->h2d_bytes = 0;
     h->profile = (flags & TPLS_FIT_PROFILE) != 0;
     h->prof.clear();
+    h->cov_alloc = (flags & TPLS_FIT_COVARIANCE) != 0 && h->m <= 8;
     TRY(alloc_fit(h, L, R));
     CK(cudaEventRecord(h->ev_start, st));
     const long long n = h->n;
@@ -863,6 +1106,11 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             h->stats.kernel_launches++;
         }
     }
+    const bool cov_mode = (flags & TPLS_FIT_COVARIANCE) != 0 && cov_supported(h, L);
+    h->stats.covariance_mode = cov_mode ? 1 : 0;
+    if (cov_mode) {
+        TRY(fit_covariance(h, L, R, tol, max_iter, flags, ss_y));
+    } else {
     // ---- centre X fused with the first contraction ----
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
@@ -1037,50 +1285,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             CK(cudaEventRecord(h->ev_trip[trip & 3], st));
         }
 
-        // ---- regression on the scores so far (tpls.py:110-112) ----
-        {
-            DotPairs d{};
-            d.n = n;
-            d.npairs = 2 * (a + 1);
-            d.w = h->row_w;
-            for (int b = 0; b <= a; ++b) {
-                d.a[b] = h->T + (size_t)b * n;
-                d.b[b] = Ta;
-                d.a[a + 1 + b] = h->T + (size_t)b * n;
-                d.b[a + 1 + b] = Ua;
-            }
-            int gx = 1;
-            {
-                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                CK(launch_multi_dot(d, h->dotpart, &gx, st));
-                h->stats.kernel_launches++;
-            }
-            TRY(reduce_cols(h, h->dotpart, A + h->off_dots, d.npairs, d.npairs, gx, nullptr, nullptr, 0, nullptr, 0));
-            TRY(allreduce(h, A + h->off_dots, d.npairs));
-            {
-                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                CK(launch_solve_coef(A + h->off_dots, h->gram, h->coef, R, a, h->ctrl, h->trips_dev, st));
-                h->stats.kernel_launches++;
-            }
-        }
-        // ---- Y deflation (tpls.py:113) + ||Y||^2 for R2Y ----
-        {
-            {
-                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                CK(launch_lincomb(h->T, n, n, h->coef, R, a, h->row_w, h->svec, st));
-                h->stats.kernel_launches++;
-            }
-            ColPassArgs c{};
-            c.g = h->gy;
-            c.x_in = h->y_work;
-            c.x_out = h->y_work;
-            c.row_a = h->svec;
-            c.col_w = h->qvec;
-            c.sspart = h->sspart_y;
-            c.row_sw = h->row_w;
-            TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c, TPLS_K_YSIDE));
-            TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y + a + 1, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
-        }
+        TRY(component_tail(h, R, a, ss_y, true));
         // ---- X deflation (tpls.py:109) fused with the next component's first contraction ----
         if (a + 1 < R) {
             {
@@ -1111,6 +1316,8 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             }
         }
     }
+
+    }  // streaming mode
 
     // ---- R2X / R2Y from the residual norms ----
     // through NCCL on purpose: it cannot complete before every peer has finished all earlier exchanges,

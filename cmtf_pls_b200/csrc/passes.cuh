@@ -93,6 +93,27 @@ cudaError_t launch_colpass(int dtype, bool masked, int flags, const ColPassArgs&
 // mode: 0 dense, 1 masked with known row counts, 2 masked and counting (writes a.rowcnt)
 cudaError_t launch_rowpass(int dtype, int mode, const RowPassArgs& a, cudaStream_t s);
 
+// Cross-covariance pass (covpass.cu): centre/deflate + write + C[m][col] = sum_rows xn * Y[row, m] + ||xn||^2.
+struct CovPassArgs {
+    PassGeom g;             // make_cov_geom
+    const void* x_in;
+    void* x_out;            // may alias x_in
+    const double* row_a;    // per-row deflation scalar, nullptr => 1 (centring)
+    const double* col_w;    // per-column vector [pitch]
+    const double* row_sw;   // optional 0/1 sample weights for the residual norm
+    const double* y;        // responses [n_rows][pitch_y] (centred / deflated work copy)
+    int pitch_y;
+    int m;                  // response columns
+    const double* rowcnt;   // masked: observed entries per row
+    double* cpart;          // [grid_x][c_stride] per-CTA partials, layout [mr][pitch]
+    size_t c_stride;
+    double* sspart;         // [n_slabs * grid_x]
+};
+PassGeom make_cov_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count);
+size_t covpass_smem(const PassGeom& g, int pitch_y, int mr);
+// mr = accumulators per column: next power of two >= m (dense) or >= 2m (masked: second block row-rescaled)
+cudaError_t launch_covpass(int dtype, bool masked, int mr, const CovPassArgs& a, cudaStream_t s);
+
 // out[c] = sum_b part[b*stride + c]  (fixed order => bit-reproducible); optionally
 // ss_out[0] = sum of sspart[0..n_ss).
 struct ReduceArgs {

@@ -365,7 +365,7 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         if (ld1 != d1 || ld0 != d0) __syncthreads();
     }
     for (int i = threadIdx.x; i < p; i += NTH) {
-        double z = __ldg(T.z + i);
+        double z = T.z[i];  // plain load: the covariance loop rewrites Z between calls
         if (T.colcnt != nullptr) {
             const double c = __ldg(T.colcnt + i);
             z = c > 0.0 ? z / c * T.n_total : 0.0;
@@ -536,7 +536,91 @@ __global__ void __launch_bounds__(kRank1Threads, 1) rank1_kernel(const __grid_co
         rank1_task(T, a.tol, a.normalize_on_break, T.scratch);
 }
 
+template <bool SMEM>
+__global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid_constant__ CovLoopArgs a) {
+    extern __shared__ __align__(16) double dyn[];
+    __shared__ double q_last[8], q_new[8], r_acc[8], lred[4 * NWARP];
+    __shared__ int lired[2 * NWARP];
+    Blk blk{lred, lired, 0};
+    const int M = a.m, L = a.n_tasks;
+    if (threadIdx.x < 8) q_last[threadIdx.x] = threadIdx.x == 0 ? 1.0 : 0.0;  // u_0 = Y[:, 0] = Y e_0 (tpls.py:78)
+    __syncthreads();
+    int trips = 0;
+    for (int trip = 0; trip < a.max_iter; ++trip) {
+        trips = trip + 1;
+        if (threadIdx.x < 8) r_acc[threadIdx.x] = 0.0;
+        for (int l = 0; l < L; ++l) {
+            const Rank1Task& T = a.t[l];
+            const double* Cl = a.C[l];
+            // Z = X x_1 u with u = Y q_last  ==  sum_m q_last[m] * C[m][:]
+            double* z = const_cast<double*>(T.z);
+            for (int i = threadIdx.x; i < T.p; i += NTH) {
+                double v = 0.0;
+                for (int m = 0; m < M; ++m) v = fma(q_last[m], Cl[(size_t)m * T.pitch + i], v);
+                z[i] = v;
+            }
+            __syncthreads();
+            if (SMEM)
+                rank1_task(T, a.tol, a.normalize_on_break, dyn);
+            else
+                rank1_task(T, a.tol, a.normalize_on_break, T.scratch);
+            __syncthreads();
+            // Y't for this tensor = C'^T kron(w): the row-rescaled block when masked (missingvals.py:23-38)
+            const double* Cq = Cl + (size_t)a.masked[l] * T.pitch;
+            for (int m = 0; m < M; ++m) {
+                double s = 0.0;
+                for (int i = threadIdx.x; i < T.p; i += NTH) s = fma(Cq[(size_t)m * T.pitch + i], T.wkron[i], s);
+                s = bsum(s, blk);
+                if (threadIdx.x == 0) r_acc[m] += s;
+            }
+            __syncthreads();
+        }
+        // q = Y't / ||Y't||, t = average of the tensors' projections (cmtf.py:120-122)
+        if (threadIdx.x == 0) {
+            double nrm = 0.0;
+            for (int m = 0; m < M; ++m) {
+                r_acc[m] /= (double)L;
+                nrm = fma(r_acc[m], r_acc[m], nrm);
+            }
+            nrm = sqrt(nrm);
+            for (int m = 0; m < M; ++m) q_new[m] = r_acc[m] / nrm;
+        }
+        __syncthreads();
+        bool stop = false;
+        if (trip >= 1) {
+            double d2 = 0.0;
+            for (int i = 0; i < M; ++i) {
+                const double di = q_last[i] - q_new[i];
+                for (int j = 0; j < M; ++j) d2 = fma(di * a.gram_y[i * M + j], q_last[j] - q_new[j], d2);
+            }
+            stop = sqrt(fabs(d2)) < a.tol;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) q_last[threadIdx.x] = threadIdx.x < M ? q_new[threadIdx.x] : 0.0;
+        __syncthreads();
+        if (stop) break;
+    }
+    for (int i = threadIdx.x; i < a.pitch_y; i += NTH) {
+        const double v = i < M ? q_last[i] : 0.0;
+        a.qvec[i] = v;
+        if (i < M) a.q_out[i] = v;
+    }
+    if (threadIdx.x == 0) *a.trips_out = trips;
+}
+
 }  // namespace
+
+cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_smem, cudaStream_t s) {
+    if (use_smem && smem_bytes > 0) {
+        cudaError_t e =
+            cudaFuncSetAttribute(cov_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        cov_loop_kernel<true><<<1, kRank1Threads, smem_bytes, s>>>(a);
+    } else {
+        cov_loop_kernel<false><<<1, kRank1Threads, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
 
 size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out) {
     long long p = 1;

@@ -41,6 +41,27 @@ struct Rank1Args {
     int trip;
 };
 
+// Covariance-mode inner iteration: the whole NIPALS loop of one component on
+// (P x M)-sized data, in ONE single-CTA launch with the convergence test on the device:
+//   Z_l = C_l q_prev;  w_l = rank-1(Z_l);  q = normalise(mean_l C'_l^T kron(w_l));
+//   stop when trip >= 1 and sqrt(dq^T (Y'Y) dq) < tol   (= ||u_old - u_new|| of tpls.py:103, u = Y q)
+struct CovLoopArgs {
+    Rank1Task t[kMaxTensors];          // t[l].z must point at a scratch vector [p] this kernel fills
+    const double* C[kMaxTensors];      // all-reduced cross-covariance, layout [mr][pitch]
+    int masked[kMaxTensors];           // 0 when dense, else the first row of the row-rescaled block of C (= mr / 2)
+    int n_tasks;
+    int m;                             // response columns (<= 8)
+    const double* gram_y;              // [m][m] all-reduced Y'Y of the current (deflated) Y
+    double tol;
+    int max_iter;
+    int normalize_on_break;
+    double* q_out;                     // [m] unit q of the last trip
+    double* qvec;                      // [pitch_y] the same, zero-padded
+    int pitch_y;
+    int* trips_out;                    // inner trips taken
+};
+cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_smem, cudaStream_t s);
+
 // doubles of workspace a task needs, and the Gram order it implies
 size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out);
 cudaError_t launch_rank1(const Rank1Args& a, size_t smem_bytes, cudaStream_t s);

@@ -224,6 +224,42 @@ cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) gram_rows_kernel(const double* y, long long n, int pitch, int m, double* part) {
+    __shared__ double red[40];
+    double acc[36];  // upper triangle of an 8 x 8 matrix
+#pragma unroll
+    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = i < m ? y[r * pitch + i] : 0.0;
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = i; j < 8; ++j) {
+                acc[k] = fma(v[i], v[j], acc[k]);
+                ++k;
+            }
+    }
+    int k = 0;
+    for (int i = 0; i < 8; ++i)
+        for (int j = i; j < 8; ++j) {
+            const double t = block_sum(acc[k++], red);
+            if (threadIdx.x == 0 && i < m && j < m) {
+                part[(size_t)blockIdx.x * m * m + i * m + j] = t;
+                part[(size_t)blockIdx.x * m * m + j * m + i] = t;
+            }
+        }
+}
+
+cudaError_t launch_gram_rows(const double* y, long long n, int pitch, int m, double* part, int* grid_out, cudaStream_t s) {
+    const int gx = (int)std::max<long long>(1, std::min<long long>(148, (n + 1023) / 1024));
+    if (grid_out) *grid_out = gx;
+    gram_rows_kernel<<<gx, 256, 0, s>>>(y, n, pitch, m, part);
+    return cudaGetLastError();
+}
+
 __global__ void count_rescale_kernel(double* z, const double* cnt, double n_total, int p) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < p) z[c] = cnt[c] > 0.0 ? z[c] / cnt[c] * n_total : 0.0;

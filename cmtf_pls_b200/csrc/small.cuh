@@ -54,6 +54,9 @@ cudaError_t launch_transpose_out(const double* in, long long n, long long ld, in
 
 cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t s);
 
+// part[bx*m*m + i*m + j] = partial of sum_rows y[row,i] * y[row,j]   (m <= 8)
+cudaError_t launch_gram_rows(const double* y, long long n, int pitch, int m, double* part, int* grid_out, cudaStream_t s);
+
 // z[c] = cnt[c] > 0 ? z[c] / cnt[c] * n_total : 0     (missingvals.py:18)
 cudaError_t launch_count_rescale(double* z, const double* cnt, double n_total, int p, cudaStream_t s);
 

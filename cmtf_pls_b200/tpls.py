@@ -22,11 +22,14 @@ from . import _core
 class tPLS(Mapping):
     """Tensor PLS (cmtf_pls/tpls.py:15)."""
 
-    def __init__(self, n_components: int, device=None, process_group=None):
+    def __init__(self, n_components: int, device=None, process_group=None, algorithm="stream"):
         super().__init__()
         self.n_components = n_components
         self.device = device
         self.process_group = process_group
+        # "stream": two passes over X per inner trip (the reference's loop, the benchmark contract);
+        # "covariance": one cross-covariance pass per component, inner loop on (P x M) data -- same results
+        self.algorithm = algorithm
 
     # ---- Mapping protocol (tpls.py:23-42) ----
     def __getitem__(self, index):
@@ -55,7 +58,8 @@ class tPLS(Mapping):
         assert X.shape[0] == Y.shape[0]
         assert Y.ndim <= 2, "Only a matrix (2-mode tensor) Y is acceptable."
         st = _core.run_fit([X], Y, self.n_components, tol, max_iter, device=self.device,
-                           group=self.process_group, overwrite=overwrite_x, profile=profile)
+                           group=self.process_group, overwrite=overwrite_x, profile=profile,
+                           algorithm=self.algorithm)
         self.X_dim = X.ndim
         self.X_shape = tuple(X.shape)
         self.Y_shape = (int(Y.shape[0]), 1) if Y.ndim == 1 else tuple(Y.shape)

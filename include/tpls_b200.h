@@ -40,7 +40,12 @@ enum {
 /* tpls_fit flags */
 enum {
     TPLS_FIT_NORMALIZE_ON_BREAK = 1, /* the other reading of tensorly's last ALS sweep, oracle/_cp.py */
-    TPLS_FIT_PROFILE = 2             /* time every pass with CUDA events on the handle's stream (tpls_get_profile) */
+    TPLS_FIT_PROFILE = 2,            /* time every pass with CUDA events on the handle's stream (tpls_get_profile) */
+    TPLS_FIT_COVARIANCE = 4          /* cross-covariance mode: per component ONE pass forms C = X'Y
+                                        (all responses at once), the inner NIPALS iteration then runs on (P x M)-sized
+                                        data in a single kernel -- no pass over X and no collective per inner trip.
+                                        Same results to rounding; needs <= 8 responses (<= 4 with NaNs), else the
+                                        streaming loop is used.  tpls_stats.covariance_mode tells which one ran. */
 };
 
 /* kernel classes of tpls_get_profile */
@@ -119,6 +124,7 @@ typedef struct tpls_stats {
     int64_t total_trips;
     int64_t collectives;        /* NCCL all-reduces issued by the last fit */
     double h2d_bytes;           /* bytes staged host->device by tpls_set_x / tpls_set_y since the last fit */
+    int64_t covariance_mode;    /* 1 when the last fit ran the cross-covariance loop */
 } tpls_stats;
 int tpls_get_stats(tpls_handle h, tpls_stats* out);
 

@@ -183,3 +183,43 @@ def test_large_shape_properties_fp32():
     est2.fit([X0, X1], Y)
     assert col_err(est2.factor_T, est.factor_T[:, :2]) < 1e-9
     assert est.stats_["alg_bytes"] > 0 and est.stats_["fit_ms"] > 0
+
+
+# ---------------------------------------------------------------------------
+# covariance mode: same results, ~2.5 passes over X per component
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [c for c in golden_cases() if "same_xy" not in c])
+def test_covariance_mode_matches_reference_golden(case):
+    from cmtf_pls_b200 import tPLS, ctPLS
+    g = load_golden(case)
+    R = int(g["n_components"])
+    kw = {"max_iter": 4} if "maxiter" in case else {}
+    if bool(g["coupled"]):
+        est = ctPLS(R, algorithm="covariance")
+        est.fit([x.copy() for x in g["Xs"]], g["Y"].copy(), **kw)
+    else:
+        est = tPLS(R, algorithm="covariance")
+        est.fit(g["Xs"][0].copy(), g["Y"].copy(), **kw)
+    M = 1 if g["Y"].ndim == 1 else g["Y"].shape[1]
+    expect_cov = M <= 8 and not (M > 4 and any(np.isnan(x).any() for x in g["Xs"]))
+    assert bool(est.stats_["covariance_mode"]) == expect_cov
+    tol = FP32_TOL if "f32" in case else FP64_TOL
+    assert est.n_iter_.tolist() == g["trips"].tolist()
+    for k, e in aligned_errors(_state(est, bool(g["coupled"])), g).items():
+        assert e < tol, (case, k, e)
+
+
+def test_covariance_mode_streams_far_fewer_bytes():
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import tPLS
+    X, Y, _ = orc.synthetic((2000, 64, 64), 4, 6, error=0.7, seed=3)
+    X = X.astype(np.float32)
+    a = tPLS(4)
+    a.fit(X, Y)
+    b = tPLS(4, algorithm="covariance")
+    b.fit(X, Y)
+    assert b.stats_["covariance_mode"] == 1 and a.stats_["covariance_mode"] == 0
+    assert a.n_iter_.tolist() == b.n_iter_.tolist()
+    assert b.stats_["streamed_bytes"] < 0.25 * a.stats_["streamed_bytes"]
+    for k, e in aligned_errors(_state(b, False), _state(a, False) | {"R2X": [a.R2X]}).items():
+        assert e < 1e-7, (k, e)
