@@ -70,7 +70,9 @@ size_t colpass_smem(const PassGeom& g) {
 // ---------------------------------------------------------------------------
 // column pass
 // ---------------------------------------------------------------------------
-template <typename XT, int CPT, bool MASKED, int FLAGS>
+// FULL: one slab, every thread owns CPT valid column groups of every row (pitch == kConsumers * VEC * CPT,
+// e.g. 4096 fp32 columns): layout constants fold at compile time and the row loop carries no bounds checks.
+template <typename XT, int CPT, bool MASKED, int FLAGS, bool FULL>
 __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_constant__ ColPassArgs a) {
     constexpr int VEC = VecOf<XT>::N;
     constexpr bool DEFLATE = (FLAGS & PF_DEFLATE) != 0;
@@ -86,7 +88,9 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
     const PassGeom& g = a.g;
     const int c0 = blockIdx.y * g.slab_w;
     const int slab_cols = min(g.slab_w, g.pitch - c0);
-    const int srow = (g.n_slabs == 1) ? g.pitch : g.slab_w;
+    const int lpr = FULL ? kConsumers : g.lpr;
+    const int rpt = FULL ? 1 : g.rpt;
+    const int srow = FULL ? kConsumers * VecOf<XT>::N * CPT : ((g.n_slabs == 1) ? g.pitch : g.slab_w);
     const size_t stage_elems = (size_t)g.tile_rows * srow;
     XT* tiles = reinterpret_cast<XT*>(smem);
     const size_t tile_area = max((size_t)g.stages * stage_elems * sizeof(XT), (size_t)kConsumers * VEC * sizeof(double));
@@ -109,8 +113,8 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
     }
 
     const int tid = threadIdx.x;
-    const int cl = tid & (g.lpr - 1);
-    const int rl = tid / g.lpr;
+    const int cl = tid & (lpr - 1);
+    const int rl = tid / lpr;
     const int lane = tid & 31;
 
     double wreg[CPT][VEC];
@@ -119,8 +123,8 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
     bool cvalid[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        const int cg = cl + k * g.lpr;
-        cvalid[k] = cg * VEC < slab_cols;
+        const int cg = cl + k * lpr;
+        cvalid[k] = FULL ? true : (cg * VEC < slab_cols);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             zacc[k][j] = 0.0;
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
         const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
         mbar_wait(&full[s], ph);
         const XT* tp = tiles + s * stage_elems;
-        for (int r = rl; r < rows; r += g.rpt) {
+        for (int r = rl; r < rows; r += rpt) {
             const long long grow = r0 + r;
             double ar = 1.0, ur = 0.0;
             if (DEFLATE && a.row_a != nullptr) ar = __ldg(a.row_a + grow);
@@ -151,8 +155,8 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
             const double ss_before = ss;
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
-                if (!cvalid[k]) continue;
-                const int cg = cl + k * g.lpr;
+                if (!FULL && !cvalid[k]) continue;
+                const int cg = cl + k * lpr;
                 Pack<XT> in, out;
                 in.v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
 #pragma unroll
@@ -186,11 +190,11 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
     // ---- epilogue: fold row lanes, publish this CTA's column partials ----
     if (ZACC) {
         double* red = reinterpret_cast<double*>(smem);
-        const int wcols = g.lpr * VEC;  // rpt > 1 => CPT == 1
+        const int wcols = lpr * VEC;  // rpt > 1 => CPT == 1
         for (int pass = 0; pass < (COLSTAT ? 2 : 1); ++pass) {
             double(*acc)[VEC] = pass == 0 ? zacc : cacc;
             double* outp = (pass == 0 ? a.zpart : a.cntpart) + (size_t)blockIdx.x * g.pitch + c0;
-            if (g.rpt > 1) {
+            if (rpt > 1) {
                 named_bar_sync(1, kConsumers);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) red[(size_t)rl * wcols + cl * VEC + j] = acc[0][j];
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) {
                         double t = 0.0;
-                        for (int q = 0; q < g.rpt; ++q) t += red[(size_t)q * wcols + cl * VEC + j];
+                        for (int q = 0; q < rpt; ++q) t += red[(size_t)q * wcols + cl * VEC + j];
                         outp[cl * VEC + j] = t;
                     }
                 }
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
 #pragma unroll
                 for (int k = 0; k < CPT; ++k) {
                     if (!cvalid[k]) continue;
-                    const int cg = cl + k * g.lpr;
+                    const int cg = cl + k * lpr;
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) outp[cg * VEC + j] = acc[k][j];
                 }
@@ -320,15 +324,22 @@ cudaError_t launch_row_finish(const RowFinishArgs& a, int* grid_out, cudaStream_
 // ---------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------
-template <typename XT, int CPT, bool MASKED, int FLAGS>
-static cudaError_t run_colpass(const ColPassArgs& a, cudaStream_t s) {
-    auto kern = colpass_kernel<XT, CPT, MASKED, FLAGS>;
+template <typename XT, int CPT, bool MASKED, int FLAGS, bool FULL>
+static cudaError_t run_colpass_impl(const ColPassArgs& a, cudaStream_t s) {
+    auto kern = colpass_kernel<XT, CPT, MASKED, FLAGS, FULL>;
     const size_t smem = colpass_smem(a.g);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
     kern<<<grid, kThreads, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+template <typename XT, int CPT, bool MASKED, int FLAGS>
+static cudaError_t run_colpass(const ColPassArgs& a, cudaStream_t s) {
+    const bool full = a.g.n_slabs == 1 && a.g.lpr == kConsumers && a.g.cpt == CPT &&
+                      a.g.pitch == kConsumers * (16 / (int)sizeof(XT)) * CPT;
+    return full ? run_colpass_impl<XT, CPT, MASKED, FLAGS, true>(a, s) : run_colpass_impl<XT, CPT, MASKED, FLAGS, false>(a, s);
 }
 
 template <typename XT, int CPT, bool MASKED>

@@ -79,9 +79,11 @@ size_t rowpass_smem(const PassGeom& g, bool masked) {
     return g.stages * row_stage_bytes(g) + 256 + kSlots * row_slot_doubles(g, masked) * sizeof(double);
 }
 
-__device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long grow, double v, double& d2) {
+// `old` = previous t[row]; only read by the caller when the epilogue needs it (coupled accumulation, ||dt||^2)
+__device__ __forceinline__ bool epilogue_needs_old(const RowPassArgs& a) { return a.epi != 0 || a.d2part != nullptr; }
+
+__device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long grow, double v, double old, double& d2) {
     double* tp = a.t_out + grow;
-    const double old = *tp;
     double nv = v;
     if (a.epi == 1) nv = old + v;
     if (a.epi == 2) nv = (old + v) / a.div;
@@ -94,7 +96,8 @@ __device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long gro
 
 // MODE 0: dense.  MODE 1: masked, per-row observed counts read from a.rowcnt (they are constant
 // during a fit).  MODE 2: masked and counting -- the first masked pass over a tensor; writes a.rowcnt.
-template <typename XT, int CPT, int MODE>
+// FULL: one slab, every consumer thread owns CPT valid column groups of every row (see colpass_kernel).
+template <typename XT, int CPT, int MODE, bool FULL>
 __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_constant__ RowPassArgs a) {
     constexpr int VEC = VecOf<XT>::N;
     constexpr bool MASKED = MODE != 0;
@@ -106,7 +109,9 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     const PassGeom& g = a.g;
     const int c0 = blockIdx.y * g.slab_w;
     const int slab_cols = min(g.slab_w, g.pitch - c0);
-    const int srow = (g.n_slabs == 1) ? g.pitch : g.slab_w;
+    const int lpr = FULL ? kConsumers : g.lpr;
+    const int rpt = FULL ? 1 : g.rpt;
+    const int srow = FULL ? kConsumers * VEC * CPT : ((g.n_slabs == 1) ? g.pitch : g.slab_w);
     const size_t stage_elems = (size_t)g.tile_rows * srow;
     XT* tiles = reinterpret_cast<XT*>(smem);
     const size_t tile_area = (size_t)g.stages * stage_elems * sizeof(XT);
@@ -115,8 +120,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     uint64_t* red_full = empty + kMaxStages;
     uint64_t* red_empty = red_full + kSlots;
     double* slots = reinterpret_cast<double*>(smem + tile_area + 256);
-    const bool use_slots = g.lpr >= 32;
-    const size_t slot_doubles = use_slots ? (size_t)g.tile_rows * g.lpr * (COUNT ? 2 : 1) : 0;
+    const bool use_slots = FULL ? true : (g.lpr >= 32);
+    const size_t slot_doubles = use_slots ? (size_t)g.tile_rows * lpr * (COUNT ? 2 : 1) : 0;
     const bool slabbed = g.n_slabs > 1;
     const double p_total = (double)g.p;
 
@@ -146,13 +151,14 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
 
     // ------------------------------------------------------------------ reducer
     if (tid >= kConsumers + 32) {
-        if (!use_slots) return;
+        if (!use_slots || a.dbg == 1) return;
         // G lanes cooperate on one row; 32/G rows per round
         int G = 32;
         while (G > 1 && (32 / G) * 2 <= g.tile_rows) G >>= 1;  // as many rows per round as the tile has
-        if (G > g.lpr) G = g.lpr;
+        if (G > lpr) G = lpr;
         const int rows_per_round = 32 / G;
         const int rg = lane / G, gl = lane - rg * G;
+        const bool need_old = epilogue_needs_old(a);
         double d2 = 0.0;
         long long it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -160,27 +166,47 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
             const uint32_t ph = (uint32_t)((it / kSlots) & 1);
             const long long r0 = tile * g.tile_rows;
             const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+            // what the first round's epilogue reads from global memory is requested BEFORE the wait, so that
+            // its latency (microseconds while the HBM is saturated) overlaps the consumers' work on the tile
+            double old_pf = 0.0, cnt_pf = 1.0;
+            if (gl == 0 && rg < rows && !slabbed) {
+                if (need_old) old_pf = a.t_out[r0 + rg];
+                if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + rg];
+            }
             mbar_wait(&red_full[sl], ph);
             const double* sp = slots + (size_t)sl * slot_doubles;
-            const double* cp = sp + (size_t)g.tile_rows * g.lpr;
+            const double* cp = sp + (size_t)g.tile_rows * lpr;
             for (int rb = 0; rb < rows; rb += rows_per_round) {
                 const int r = rb + rg;
                 double v = 0.0, cnt = 0.0;
                 if (r < rows) {
-                    const double* rowp = sp + (size_t)r * g.lpr;
-                    const double* rowc = cp + (size_t)r * g.lpr;
-                    const int skew = (G * rg) & (g.lpr - 1);
-                    for (int i = gl; i < g.lpr; i += G) {
-                        const int col = (i + skew) & (g.lpr - 1);
+                    const double* rowp = sp + (size_t)r * lpr;
+                    const double* rowc = cp + (size_t)r * lpr;
+                    const int skew = (G * rg) & (lpr - 1);
+                    // lpr / G partials per lane: four independent chains
+                    double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                    int i = gl;
+                    for (; i + 3 * G < lpr; i += 4 * G) {
+                        v += rowp[(i + skew) & (lpr - 1)];
+                        v1 += rowp[(i + G + skew) & (lpr - 1)];
+                        v2 += rowp[(i + 2 * G + skew) & (lpr - 1)];
+                        v3 += rowp[(i + 3 * G + skew) & (lpr - 1)];
+                        if (COUNT)
+                            cnt += (rowc[(i + skew) & (lpr - 1)] + rowc[(i + G + skew) & (lpr - 1)]) +
+                                   (rowc[(i + 2 * G + skew) & (lpr - 1)] + rowc[(i + 3 * G + skew) & (lpr - 1)]);
+                    }
+                    for (; i < lpr; i += G) {
+                        const int col = (i + skew) & (lpr - 1);
                         v += rowp[col];
                         if (COUNT) cnt += rowc[col];
                     }
+                    v = (v + v1) + (v2 + v3);
                 }
                 for (int m = G >> 1; m >= 1; m >>= 1) {
                     v += shfl_xor_d(v, m);
                     if (COUNT) cnt += shfl_xor_d(cnt, m);
                 }
-                if (r < rows && gl == 0) {
+                if (r < rows && gl == 0 && a.dbg != 2) {
                     const long long grow = r0 + r;
                     if (slabbed) {
                         a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
@@ -191,11 +217,12 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                                 cnt -= pads;
                                 if (a.rowcnt != nullptr) a.rowcnt[grow] = cnt;
                             } else {
-                                cnt = a.rowcnt[grow];
+                                cnt = rb == 0 ? cnt_pf : a.rowcnt[grow];
                             }
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        row_epilogue(a, grow, v, d2);
+                        const double old = !need_old ? 0.0 : (rb == 0 ? old_pf : a.t_out[grow]);
+                        row_epilogue(a, grow, v, old, d2);
                     }
                 }
             }
@@ -210,14 +237,14 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     }
 
     // ------------------------------------------------------------------ consumers
-    const int cl = tid & (g.lpr - 1);
-    const int rl = tid / g.lpr;
+    const int cl = tid & (lpr - 1);
+    const int rl = tid / lpr;
     double wreg[CPT][VEC];
     bool cvalid[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        const int cg = cl + k * g.lpr;
-        cvalid[k] = cg * VEC < slab_cols;
+        const int cg = cl + k * lpr;
+        cvalid[k] = FULL ? true : (cg * VEC < slab_cols);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) wreg[k][j] = cvalid[k] ? a.col_w[c0 + cg * VEC + j] : 0.0;
     }
@@ -231,21 +258,26 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
         const int sl = (int)(it % kSlots);
         double* sp = slots + (size_t)sl * slot_doubles;
-        double* cp = sp + (size_t)g.tile_rows * g.lpr;
-        if (use_slots && it >= kSlots) mbar_wait(&red_empty[sl], (uint32_t)(((it / kSlots) - 1) & 1));
+        double* cp = sp + (size_t)g.tile_rows * lpr;
+        if (use_slots && a.dbg != 1 && it >= kSlots) mbar_wait(&red_empty[sl], (uint32_t)(((it / kSlots) - 1) & 1));
         mbar_wait(&full[s], ph);
         const XT* tp = tiles + s * stage_elems;
         // every lane of a row group walks the same number of rounds so that the shuffles stay converged
-        for (int rb = 0; rb < rows; rb += g.rpt) {
+        for (int rb = 0; rb < rows; rb += rpt) {
             const int r = rb + rl;
-            const bool live = r < rows;
+            const bool live = FULL ? true : (r < rows);
             double v = 0.0, cnt = 0.0;
             int icnt = 0;
             if (live) {
+                // one accumulator per (column group, element): CPT * VEC independent chains instead of
+                // one chain of CPT * VEC dependent fp64 FMAs
+                double acc[CPT][VEC];
 #pragma unroll
                 for (int k = 0; k < CPT; ++k) {
-                    if (!cvalid[k]) continue;
-                    const int cg = cl + k * g.lpr;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[k][j] = 0.0;
+                    if (!FULL && !cvalid[k]) continue;
+                    const int cg = cl + k * lpr;
                     Pack<XT> in;
                     in.v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
 #pragma unroll
@@ -254,22 +286,30 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                         if (MASKED) {
                             const bool ob = (xs == xs);
                             const XT xc = ob ? xs : (XT)0;  // select in the storage type, convert once
-                            v = fma((double)xc, wreg[k][j], v);
+                            acc[k][j] = (double)xc * wreg[k][j];
                             if (COUNT) icnt += ob ? 1 : 0;
                         } else {
-                            v = fma((double)xs, wreg[k][j], v);
+                            acc[k][j] = (double)xs * wreg[k][j];
                         }
                     }
+                }
+                // fixed-shape tree
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    double t = acc[k][0];
+#pragma unroll
+                    for (int j = 1; j < VEC; ++j) t += acc[k][j];
+                    v += t;
                 }
             }
             if (COUNT) cnt = (double)icnt;
             if (use_slots) {
                 if (live) {
-                    sp[(size_t)r * g.lpr + cl] = v;
-                    if (COUNT) cp[(size_t)r * g.lpr + cl] = cnt;
+                    sp[(size_t)r * lpr + cl] = v;
+                    if (COUNT) cp[(size_t)r * lpr + cl] = cnt;
                 }
             } else {
-                for (int m = g.lpr >> 1; m >= 1; m >>= 1) {
+                for (int m = lpr >> 1; m >= 1; m >>= 1) {
                     v += shfl_xor_d(v, m);
                     if (COUNT) cnt += shfl_xor_d(cnt, m);
                 }
@@ -288,7 +328,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                             }
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        row_epilogue(a, grow, v, d2);
+                        row_epilogue(a, grow, v, epilogue_needs_old(a) ? a.t_out[grow] : 0.0, d2);
                     }
                 }
             }
@@ -296,7 +336,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty[s]);
-            if (use_slots) mbar_arrive(&red_full[sl]);
+            if (use_slots && a.dbg != 1) mbar_arrive(&red_full[sl]);
         }
     }
 
@@ -317,15 +357,24 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
 // ---------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------
-template <typename XT, int CPT, int MODE>
-static cudaError_t run_rowpass(const RowPassArgs& a, cudaStream_t s) {
-    auto kern = rowpass_kernel<XT, CPT, MODE>;
+template <typename XT, int CPT, int MODE, bool FULL>
+static cudaError_t run_rowpass_impl(const RowPassArgs& a, cudaStream_t s) {
+    auto kern = rowpass_kernel<XT, CPT, MODE, FULL>;
     const size_t smem = rowpass_smem(a.g, MODE == 2);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
-    kern<<<grid, kRowThreads, smem, s>>>(a);
+    RowPassArgs a2 = a;
+    a2.dbg = tune_env("TPLS_ROWDBG", 0);
+    kern<<<grid, kRowThreads, smem, s>>>(a2);
     return cudaGetLastError();
+}
+
+template <typename XT, int CPT, int MODE>
+static cudaError_t run_rowpass(const RowPassArgs& a, cudaStream_t s) {
+    const bool full = a.g.n_slabs == 1 && a.g.lpr == kConsumers && a.g.cpt == CPT &&
+                      a.g.pitch == kConsumers * (16 / (int)sizeof(XT)) * CPT;
+    return full ? run_rowpass_impl<XT, CPT, MODE, true>(a, s) : run_rowpass_impl<XT, CPT, MODE, false>(a, s);
 }
 
 template <typename XT>
