@@ -35,13 +35,13 @@ PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_cou
     g.n_slabs = (cg_total + max_cg - 1) / max_cg;
     const int slab_cg = (cg_total + g.n_slabs - 1) / g.n_slabs;
     g.slab_w = slab_cg * vec;
-    if (slab_cg >= kConsumers) {
-        g.lpr = kConsumers;
-        const int need = (slab_cg + kConsumers - 1) / kConsumers;
+    // as few lanes per row as kMaxCpt groups per lane allow: more work per thread and row
+    g.lpr = std::min(kConsumers, pow2_ceil((slab_cg + kMaxCpt - 1) / kMaxCpt));
+    if (slab_cg % kConsumers == 0 && (slab_cg / kConsumers == 1 || slab_cg / kConsumers == 2))
+        g.lpr = kConsumers;  // exact fit: the compile-time FULL path applies
+    {
+        const int need = (slab_cg + g.lpr - 1) / g.lpr;
         g.cpt = need <= 1 ? 1 : (need <= 2 ? 2 : 4);
-    } else {
-        g.lpr = pow2_ceil(slab_cg);
-        g.cpt = 1;
     }
     g.rpt = kConsumers / g.lpr;
     const long long row_bytes = (long long)(g.n_slabs == 1 ? pitch : g.slab_w) * elem_size;
@@ -63,7 +63,7 @@ static size_t stage_bytes_of(const PassGeom& g) {
 
 size_t colpass_smem(const PassGeom& g) {
     const size_t tiles = g.stages * stage_bytes_of(g);
-    const size_t red = (size_t)kConsumers * 16 / g.elem_size * sizeof(double);  // rpt > 1 => cpt == 1
+    const size_t red = (size_t)kConsumers * g.cpt * (16 / g.elem_size) * sizeof(double);  // row-lane fold
     return std::max(tiles, red) + 128;
 }
 
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
     const int srow = FULL ? kConsumers * VecOf<XT>::N * CPT : ((g.n_slabs == 1) ? g.pitch : g.slab_w);
     const size_t stage_elems = (size_t)g.tile_rows * srow;
     XT* tiles = reinterpret_cast<XT*>(smem);
-    const size_t tile_area = max((size_t)g.stages * stage_elems * sizeof(XT), (size_t)kConsumers * VEC * sizeof(double));
+    const size_t tile_area = max((size_t)g.stages * stage_elems * sizeof(XT), (size_t)kConsumers * CPT * VEC * sizeof(double));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + tile_area);
     uint64_t* empty = full + kMaxStages;
 
@@ -190,22 +190,26 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
     // ---- epilogue: fold row lanes, publish this CTA's column partials ----
     if (ZACC) {
         double* red = reinterpret_cast<double*>(smem);
-        const int wcols = lpr * VEC;  // rpt > 1 => CPT == 1
+        // red[row lane][column group slot k][lane column][element]: kConsumers * CPT * VEC doubles in total
+        const int wcols = lpr * VEC;
         for (int pass = 0; pass < (COLSTAT ? 2 : 1); ++pass) {
             double(*acc)[VEC] = pass == 0 ? zacc : cacc;
             double* outp = (pass == 0 ? a.zpart : a.cntpart) + (size_t)blockIdx.x * g.pitch + c0;
             if (rpt > 1) {
                 named_bar_sync(1, kConsumers);
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) red[(size_t)rl * wcols + cl * VEC + j] = acc[0][j];
-                named_bar_sync(1, kConsumers);
-                if (rl == 0 && cvalid[0]) {
+                for (int k = 0; k < CPT; ++k)
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        double t = 0.0;
-                        for (int q = 0; q < rpt; ++q) t += red[(size_t)q * wcols + cl * VEC + j];
-                        outp[cl * VEC + j] = t;
-                    }
+                    for (int j = 0; j < VEC; ++j) red[((size_t)rl * CPT + k) * wcols + cl * VEC + j] = acc[k][j];
+                named_bar_sync(1, kConsumers);
+                // every thread folds a share of the (column, element) pairs over the row lanes
+                for (int e = tid; e < CPT * wcols; e += kConsumers) {
+                    const int k = e / wcols, ce = e - k * wcols;       // ce = cl * VEC + j
+                    const int cg = ce / VEC + k * lpr;
+                    if (cg * VEC >= slab_cols) continue;
+                    double t = 0.0;
+                    for (int q = 0; q < rpt; ++q) t += red[((size_t)q * CPT + k) * wcols + ce];
+                    outp[cg * VEC + (ce % VEC)] = t;
                 }
             } else {
 #pragma unroll

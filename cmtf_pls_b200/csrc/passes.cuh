@@ -86,7 +86,6 @@ struct RowPassArgs {
     double* d2part;         // optional [grid_x]: sum over rows of (t_old - t_new)^2
     const Ctrl* ctrl;
     int trip;
-    int dbg;                // experiments only (TPLS_ROWDBG): 1 = no slot hand-over, 2 = no epilogue
 };
 
 // dtype: 0 = float32, 1 = float64

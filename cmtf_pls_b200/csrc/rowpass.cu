@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
 
     // ------------------------------------------------------------------ reducer
     if (tid >= kConsumers + 32) {
-        if (!use_slots || a.dbg == 1) return;
+        if (!use_slots) return;
         // G lanes cooperate on one row; 32/G rows per round
         int G = 32;
         while (G > 1 && (32 / G) * 2 <= g.tile_rows) G >>= 1;  // as many rows per round as the tile has
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                     v += shfl_xor_d(v, m);
                     if (COUNT) cnt += shfl_xor_d(cnt, m);
                 }
-                if (r < rows && gl == 0 && a.dbg != 2) {
+                if (r < rows && gl == 0) {
                     const long long grow = r0 + r;
                     if (slabbed) {
                         a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         const int sl = (int)(it % kSlots);
         double* sp = slots + (size_t)sl * slot_doubles;
         double* cp = sp + (size_t)g.tile_rows * lpr;
-        if (use_slots && a.dbg != 1 && it >= kSlots) mbar_wait(&red_empty[sl], (uint32_t)(((it / kSlots) - 1) & 1));
+        if (use_slots && it >= kSlots) mbar_wait(&red_empty[sl], (uint32_t)(((it / kSlots) - 1) & 1));
         mbar_wait(&full[s], ph);
         const XT* tp = tiles + s * stage_elems;
         // every lane of a row group walks the same number of rounds so that the shuffles stay converged
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty[s]);
-            if (use_slots && a.dbg != 1) mbar_arrive(&red_full[sl]);
+            if (use_slots) mbar_arrive(&red_full[sl]);
         }
     }
 
@@ -364,9 +364,7 @@ static cudaError_t run_rowpass_impl(const RowPassArgs& a, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
-    RowPassArgs a2 = a;
-    a2.dbg = tune_env("TPLS_ROWDBG", 0);
-    kern<<<grid, kRowThreads, smem, s>>>(a2);
+    kern<<<grid, kRowThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 
