@@ -120,7 +120,7 @@ struct tpls_ctx {
     double n_total = 0;
     bool cov_alloc = false;  // the last alloc_fit reserved the covariance-mode buffers
     size_t off_cov = 0, cov_len = 0, off_gram_y = 0;
-    double* grampart = nullptr;
+    double *grampart = nullptr, *q_prev = nullptr;
     tpls_stats stats{};
     // optional per-kernel-class timing (TPLS_FIT_PROFILE): event pairs on the launching stream
     bool profile = false;
@@ -692,9 +692,9 @@ static int layout_fit(tpls_handle h, int L, int R) {
             h->x[l].off_c = off;
             off += (size_t)mr_alloc * h->x[l].pitch;
         }
-        h->off_gram_y = off;
-        off += 64;
     }
+    h->off_gram_y = off;
+    off += 64;
     h->cov_len = off - h->off_cov;
     h->arena_doubles = off;
     TRY(dev_alloc(h, (void**)&h->arena, off * sizeof(double), tr));
@@ -713,6 +713,7 @@ static int layout_fit(tpls_handle h, int L, int R) {
     TRY(dev_alloc(h, (void**)&h->d2part, sizeof(double) * 2048, tr));
     TRY(dev_alloc(h, (void**)&h->dotpart, sizeof(double) * 148 * 64, tr));
     TRY(dev_alloc(h, (void**)&h->grampart, sizeof(double) * 148 * 64, tr));
+    TRY(dev_alloc(h, (void**)&h->q_prev, sizeof(double) * 8, tr));
     TRY(dev_alloc(h, (void**)&h->scratch_ss, sizeof(double) * 8, tr));
     TRY(dev_alloc(h, (void**)&h->trips_dev, sizeof(int) * R, tr));
     TRY(dev_alloc(h, (void**)&h->ymiss_flag, sizeof(int) * 4, tr));
@@ -1139,6 +1140,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
 
     const int LOOK = 1;
     const bool fused_xchg = h->world > 1 && h->xchg_ready && h->zcat_len <= (size_t)h->xchg_cap;
+    const bool gram_stop = h->m <= 8 && getenv("TPLS_NO_GRAM_STOP") == nullptr;
     for (int a = 0; a < R; ++a) {
         double* Ta = h->T + (size_t)a * n;
         double* Ua = h->U + (size_t)a * n;
@@ -1146,6 +1148,18 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
             CK(launch_reset_ctrl(h->ctrl, st));
             h->stats.kernel_launches++;
+        }
+        if (gram_stop) {
+            // Y'Y of the current (deflated) Y: the stop test then needs no pass over the samples and no
+            // collective of its own (||u_old - u_new||^2 = dq^T Y'Y dq, u = Y q)
+            int gx = 1;
+            {
+                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+                CK(launch_gram_rows(h->y_work, n, h->pitch_y, h->m, h->grampart, &gx, st));
+                h->stats.kernel_launches++;
+            }
+            TRY(reduce_cols(h, h->grampart, A + h->off_gram_y, h->m * h->m, h->m * h->m, gx, nullptr, nullptr, 0, nullptr, 0));
+            TRY(allreduce(h, A + h->off_gram_y, (size_t)h->m * h->m));
         }
         for (int trip = 0; trip < max_iter; ++trip) {
             if (trip >= 1 + LOOK) {
@@ -1240,7 +1254,11 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 }
                 {
                     ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                    CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, trip, st));
+                    if (gram_stop)
+                        CK(launch_normalize_q_stop(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec,
+                                                   A + h->off_gram_y, h->q_prev, h->ctrl, trip, tol, st));
+                    else
+                        CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, trip, st));
                     h->stats.kernel_launches++;
                 }
                 RowPassArgs r{};
@@ -1250,12 +1268,14 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 r.t_out = Ua;
                 r.epi = 0;
                 r.div = 1.0;
-                r.d2part = h->d2part;
+                r.d2part = gram_stop ? nullptr : h->d2part;
                 r.ctrl = h->ctrl;
                 r.trip = trip;
                 TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
                 const int nd2 = d2_grid(h->gy_row);
-                if (fused_xchg) {
+                if (gram_stop) {
+                    // the stop test already ran inside normalize_q_stop
+                } else if (fused_xchg) {
                     // partial sums of ||u_old - u_new||^2 -> global sum -> stop test, one kernel
                     XchgArgs xa{};
                     xa.n_sets = 1;

@@ -64,6 +64,36 @@ cudaError_t launch_normalize_q(const double* qraw, int m, int pitch, double* qco
     return cudaGetLastError();
 }
 
+__global__ void normalize_q_stop_kernel(const double* qraw, int m, int pitch, double* qcol, double* qvec,
+                                        const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol) {
+    if (trip_is_dead(ctrl, trip)) return;
+    if (threadIdx.x != 0) return;
+    double q[8], dq[8];
+    double nrm = 0.0;
+    for (int i = 0; i < m; ++i) nrm = fma(qraw[i], qraw[i], nrm);
+    nrm = sqrt(nrm);
+    for (int i = 0; i < m; ++i) {
+        q[i] = qraw[i] / nrm;
+        dq[i] = q_prev[i] - q[i];
+        qcol[i] = q[i];
+        q_prev[i] = q[i];
+    }
+    for (int i = 0; i < pitch; ++i) qvec[i] = i < m ? q[i] : 0.0;
+    double d2 = 0.0;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) d2 = fma(dq[i] * gram[i * m + j], dq[j], d2);
+    ctrl->trips_taken = trip + 1;
+    ctrl->last_d2 = d2;
+    // trip 0 compares against +inf in the reference (tpls.py:77) and can never stop
+    if (trip >= 1 && sqrt(fabs(d2)) < tol) ctrl->done_trip = trip;
+}
+
+cudaError_t launch_normalize_q_stop(const double* qraw, int m, int pitch, double* qcol, double* qvec, const double* gram,
+                                    double* q_prev, Ctrl* ctrl, int trip, double tol, cudaStream_t s) {
+    normalize_q_stop_kernel<<<1, 32, 0, s>>>(qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) sum_small_kernel(const double* parts, int n, double* out, const Ctrl* ctrl,
                                                         int trip) {
     if (trip_is_dead(ctrl, trip)) return;

@@ -19,6 +19,11 @@ cudaError_t launch_gather_col(const double* src, long long n, int pitch, int col
 cudaError_t launch_normalize_q(const double* qraw, int m, int pitch, double* qcol, double* qvec, const Ctrl* ctrl,
                                int trip, cudaStream_t s);
 
+// The same normalisation plus the stop test of tpls.py:103 without a pass over the samples: u = Y q, so
+// ||u_old - u_new||^2 = dq^T (Y'Y) dq with dq = q_prev - q (gram = all-reduced Y'Y, m <= 8); q_prev <- q.
+cudaError_t launch_normalize_q_stop(const double* qraw, int m, int pitch, double* qcol, double* qvec, const double* gram,
+                                    double* q_prev, Ctrl* ctrl, int trip, double tol, cudaStream_t s);
+
 // out[0] = sum parts[0..n)
 cudaError_t launch_sum_small(const double* parts, int n, double* out, const Ctrl* ctrl, int trip, cudaStream_t s);
 

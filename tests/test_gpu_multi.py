@@ -47,7 +47,7 @@ def test_sharded_fit_matches_golden(tmp_path, case):
     assert p["trips"].tolist() == g["trips"].tolist()
     for k, e in aligned_errors(whole, g).items():
         assert e < 1e-8, (case, k, e)
-    assert int(p["collectives"]) >= 3 * int(p["trips"].sum())
+    assert int(p["collectives"]) >= 2 * int(p["trips"].sum())   # Z and q every trip; the stop test rides on q
 
 
 @pytest.mark.parametrize("case,tol", [("synthetic_f64", 1e-8), ("synthetic_f32", 1e-4), ("synthetic_miss_f64", 1e-8)])
