@@ -304,6 +304,26 @@ def run_ours(args):
     except Exception as exc:  # noqa: BLE001
         cov = {"error": repr(exc)[:200]}
 
+    # ---- transform of the resident shard through the fitted model: complete data is read
+    #      in place, R projection passes + the score recurrence; the (n, R) scores come back to the host ----
+    xform = None
+    try:
+        est.transform(Xs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            est.transform(Xs)
+        barrier()
+        dt = (time.perf_counter() - t0) / 2
+        tt2 = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
+        moved = 2 * 4.0 * n_total * 4096 * R
+        xform = {"s_per_call": tt2.item(), "rows_per_s": n_total / tt2.item(), "gbs_on_bytes_moved": moved / tt2.item() / 1e9,
+                 "passes": R, "includes": "D2H of the scores, host clock"}
+    except Exception as exc:  # noqa: BLE001
+        xform = {"error": repr(exc)[:200]}
+
     # ---- end to end through the estimator API with pinned host arrays ----
     e2e = None
     n_iter_resident = est.n_iter_.tolist()
@@ -394,7 +414,7 @@ def run_ours(args):
                    "l2": "every pass streams 2 x %.1f GB per GPU, far larger than the 126 MB L2 (no flush needed)"
                          % (4.0 * n_loc * 4096 / 1e9),
                    "fraction_of_hbm_peak": value / (world * peak), "fit_ms_device_last": fit_ms_device,
-                   "covariance_mode": cov},
+                   "covariance_mode": cov, "transform": xform},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if cpu is not None:

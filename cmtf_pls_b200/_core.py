@@ -193,7 +193,15 @@ def run_transform(Xs, means, loadings_per_tensor, R, device=None):
     eng = get_engine(dev)
     wk = [kron_rows(ws, R) for ws in loadings_per_tensor]
     mm = [np.ascontiguousarray(np.asarray(mu, dtype=np_dtype_of(X)).reshape(-1)) for mu, X in zip(means, Xs)]
-    return eng.transform(Xs, mm, wk)
+    # constants of the read-only path (complete data): the deflation recurrence on the scores alone needs
+    # <mean_l, kron_l[a]> and <kron_l[b], kron_l[a]>, averaged over the coupled tensors like the scores
+    c = np.mean([w @ m.astype(np.float64) for w, m in zip(wk, mm)], axis=0)
+    G = np.mean([w @ w.T for w in wk], axis=0)
+    if not (np.all(np.isfinite(c)) and np.all(np.isfinite(G))):  # e.g. a training column that was all NaN
+        c = G = None
+    else:
+        c, G = np.ascontiguousarray(c), np.ascontiguousarray(G)
+    return eng.transform(Xs, mm, wk, c, G)
 
 
 def y_scores(Y, Y_mean, Y_shape, X_scores, coef, Q):

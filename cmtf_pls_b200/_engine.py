@@ -41,6 +41,7 @@ class Stats(C.Structure):
         ("collectives", C.c_int64),
         ("h2d_bytes", C.c_double),
         ("covariance_mode", C.c_int64),
+        ("last_transform_path", C.c_int64),
     ]
 
 
@@ -81,7 +82,7 @@ SIGNATURES = {
     "tpls_release_data": (C.c_int, [_H]),
     "tpls_trim": (C.c_int, [_H]),
     "tpls_transform": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(C.c_int), C.c_int64,
-                                 C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P]),
+                                 C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "tpls_op_contract": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P, C.POINTER(C.c_float), C.c_int]),
     "tpls_op_project": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P, C.POINTER(C.c_float), C.c_int]),
     "tpls_op_deflate_contract": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, C.c_int, _P, _P,
@@ -257,8 +258,9 @@ class Engine:
     def release_data(self):
         self._ck(self.lib.tpls_release_data(self.h))
 
-    def transform(self, xs, means, wkrons):
-        """xs[l]: (n_new, ...) array/tensor; means[l]: numpy, X's dtype; wkrons[l]: (R, P) float64 numpy."""
+    def transform(self, xs, means, wkrons, proj_offset=None, proj_gram=None):
+        """xs[l]: (n_new, ...) array/tensor; means[l]: numpy, X's dtype; wkrons[l]: (R, P) float64 numpy;
+        proj_offset (R,), proj_gram (R, R): constants of the read-only path for complete data (or None)."""
         L = len(xs)
         n_new = int(xs[0].shape[0])
         R = int(wkrons[0].shape[0])
@@ -268,5 +270,7 @@ class Engine:
         mp = (_P * L)(*[_ptr(m) for m in means])
         wp = (_P * L)(*[_ptr(w) for w in wkrons])
         out = np.empty((n_new, R), dtype=np.float64)
-        self._ck(self.lib.tpls_transform(self.h, L, R, xp, dt, n_new, ps, mp, wp, out.ctypes.data))
+        po = None if proj_offset is None else proj_offset.ctypes.data
+        pgm = None if proj_gram is None else proj_gram.ctypes.data
+        self._ck(self.lib.tpls_transform(self.h, L, R, xp, dt, n_new, ps, mp, wp, po, pgm, out.ctypes.data))
         return out

@@ -300,6 +300,35 @@ cudaError_t launch_count_rescale(double* z, const double* cnt, double n_total, i
     return cudaGetLastError();
 }
 
+__global__ void rows_complete_kernel(const double* rowcnt, long long n, double p, int* flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= !(rowcnt[i] == p);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+cudaError_t launch_rows_complete(const double* rowcnt, long long n, double p, int* flag, cudaStream_t s) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(592, (n + 255) / 256));
+    rows_complete_kernel<<<blocks, 256, 0, s>>>(rowcnt, n, p, flag);
+    return cudaGetLastError();
+}
+
+__global__ void score_recurrence_kernel(double* S, long long n, int R, const double* c, const double* G) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        for (int a = 0; a < R; ++a) {
+            double t = S[(size_t)a * n + i] - c[a];
+            for (int b = 0; b < a; ++b) t = fma(-S[(size_t)b * n + i], G[b * R + a], t);
+            S[(size_t)a * n + i] = t;
+        }
+    }
+}
+
+cudaError_t launch_score_recurrence(double* S, long long n, int R, const double* c, const double* G, cudaStream_t s) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
+    score_recurrence_kernel<<<blocks, 256, 0, s>>>(S, n, R, c, G);
+    return cudaGetLastError();
+}
+
 template <typename XT>
 __global__ void widen_kernel(const XT* src, double* dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

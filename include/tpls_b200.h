@@ -125,6 +125,7 @@ typedef struct tpls_stats {
     int64_t collectives;        /* NCCL all-reduces issued by the last fit */
     double h2d_bytes;           /* bytes staged host->device by tpls_set_x / tpls_set_y since the last fit */
     int64_t covariance_mode;    /* 1 when the last fit ran the cross-covariance loop */
+    int64_t last_transform_path; /* last tpls_transform: 1 = read-only path (complete data), 2 = sequential path */
 } tpls_stats;
 int tpls_get_stats(tpls_handle h, tpls_stats* out);
 
@@ -147,11 +148,15 @@ int tpls_trim(tpls_handle h);
  * Stateless with respect to tpls_fit: the model is passed in, so it also serves an
  * estimator that was pickled or fitted elsewhere.  xs[l]: (n_new, ps[l]) in dtypes[l];
  * means[l]: ps[l] values in dtypes[l]; wkrons[l]: (R, ps[l]) float64, row a = kron of the
- * component-a loading vectors.  Rows with NaNs use the masked projection
- * (missingvals.py:23-38). */
+ * component-a loading vectors.
+ * proj_offset (R) and proj_gram (R x R), optional: c_a = mean_l <mean_l, wkron_l[a]> and
+ * G_ba = mean_l <wkron_l[b], wkron_l[a]>.  With them, data WITHOUT NaNs is never copied or
+ * deflated: R read-only projection passes over the rows where they lie, then the deflation
+ * recurrence t_a = r_a - c_a - sum_{b<a} t_b G_ba on the scores.  Rows with NaNs (or NULL
+ * constants) take the sequential path with the masked projection (missingvals.py:23-38). */
 int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* const* xs, const int* dtypes,
                    int64_t n_new, const int64_t* ps, const void* const* means, const double* const* wkrons,
-                   double* scores_out);
+                   const double* proj_offset, const double* proj_gram, double* scores_out);
 
 /* ---- single operators (used by the parity tests and by bench.py's per-kernel roofline) ----
  * All pointers here are DEVICE pointers; x is (n, p) C-ordered with p*elem a multiple of 16. */

@@ -223,3 +223,32 @@ def test_covariance_mode_streams_far_fewer_bytes():
     assert b.stats_["streamed_bytes"] < 0.25 * a.stats_["streamed_bytes"]
     for k, e in aligned_errors(_state(b, False), _state(a, False) | {"R2X": [a.R2X]}).items():
         assert e < 1e-7, (k, e)
+
+
+def test_transform_paths_agree_and_complete_data_is_read_in_place():
+    """Complete new data takes the read-only path (R projections + the score recurrence); the same data with a
+    single NaN takes the sequential masked path; both must agree with each other and with the oracle."""
+    import torch
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import ctPLS, _core
+    Xs, Y, _ = orc.synthetic((300, 16, 8), 3, 4, error=0.4, seed=12, extra_dims=[(300, 20)])
+    est = ctPLS(4)
+    est.fit(Xs, Y)
+    ref = orc.fit([x.copy() for x in Xs], Y.copy(), 4, r2_mode="residual")
+    Xn, _, _ = orc.synthetic((50, 16, 8), 3, 4, error=0.4, seed=13, extra_dims=[(50, 20)])
+    want = orc.transform(ref, [x.copy() for x in Xn])
+    Xd = [torch.from_numpy(x).cuda() for x in Xn]
+    got = est.transform(Xd)
+    eng = _core.get_engine(0)
+    assert eng.stats()["last_transform_path"] == 1
+    for a, b in zip(Xd, Xn):
+        assert torch.equal(a.cpu(), torch.from_numpy(b))          # never written
+    assert col_err(got, want) < FP64_TOL
+    Xm = [x.copy() for x in Xn]
+    Xm[0][3, 2, 1] = np.nan
+    got_m = est.transform(Xm)
+    assert eng.stats()["last_transform_path"] == 2
+    want_m = orc.transform(ref, [x.copy() for x in Xm])
+    assert col_err(got_m, want_m) < FP64_TOL
+    keep = np.arange(50) != 3
+    assert col_err(got_m[keep], got[keep]) < FP64_TOL
