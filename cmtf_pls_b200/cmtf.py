@@ -46,6 +46,17 @@ class ctPLS(Mapping):
     def copy(self):
         return copy(self)
 
+    def __getstate__(self):
+        """Pickle the fitted model, not the references to the training arrays or to a process group."""
+        state = dict(self.__dict__)
+        for k in ("_Xs_ref", "_Y_ref", "process_group"):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.__dict__.setdefault("process_group", None)
+
     # ---- fit (cmtf.py:44-140) ----
     def fit(self, Xs, Y, tol=1e-8, max_iter=100, verbose=0, overwrite_x=False, profile=False):
         assert isinstance(Xs, list)
@@ -75,6 +86,8 @@ class ctPLS(Mapping):
         self._Xs_ref = Xs
         self._Y_ref = Y
         self.n_iter_ = st["trips"]
+        # the reference is silent when max_iter is exhausted (tpls.py:79-107); here it can be asked
+        self.converged_ = st["trips"] < max_iter
         self.stats_ = st["stats"]
         self.profile_ = st["profile"]
         self._device = st["device"]

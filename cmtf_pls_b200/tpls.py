@@ -53,6 +53,17 @@ class tPLS(Mapping):
     def copy(self):
         return copy(self)
 
+    def __getstate__(self):
+        """Pickle the fitted model, not the references to the training arrays or to a process group."""
+        state = dict(self.__dict__)
+        for k in ("_X_ref", "_Y_ref", "process_group"):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.__dict__.setdefault("process_group", None)
+
     # ---- fit (tpls.py:44-120) ----
     def fit(self, X, Y, tol=1e-8, max_iter=100, verbose=0, overwrite_x=False, profile=False):
         assert X.shape[0] == Y.shape[0]
@@ -76,6 +87,8 @@ class tPLS(Mapping):
         self.Y_mean = st["Y_mean"]
         self.coef_ = st["coef"]
         self.n_iter_ = st["trips"]
+        # the reference is silent when max_iter is exhausted (tpls.py:79-107); here it can be asked
+        self.converged_ = st["trips"] < max_iter
         self.stats_ = st["stats"]
         self.profile_ = st["profile"]
         self._device = st["device"]

@@ -252,3 +252,36 @@ def test_transform_paths_agree_and_complete_data_is_read_in_place():
     assert col_err(got_m, want_m) < FP64_TOL
     keep = np.arange(50) != 3
     assert col_err(got_m[keep], got[keep]) < FP64_TOL
+
+
+def test_pickle_roundtrip_and_convergence_flags():
+    import pickle
+    g = load_golden("t4_maxiter_20x6x5x4_m5_r2")
+    from cmtf_pls_b200 import tPLS
+    est = tPLS(2)
+    est.fit(g["Xs"][0].copy(), g["Y"].copy(), max_iter=4)
+    assert est.n_iter_.tolist() == [4, 4] and not est.converged_.any()      # silent in the reference (tpls.py:79-107)
+    est.fit(g["Xs"][0].copy(), g["Y"].copy())
+    assert est.converged_.all()
+    clone = pickle.loads(pickle.dumps(est))
+    assert not hasattr(clone, "_X_ref")
+    Xn = g["Xs"][0][:5].copy()
+    assert np.array_equal(clone.predict(Xn), est.predict(Xn))
+
+
+def test_all_missing_row_gives_nan_score_like_the_reference():
+    """missingvals.py:37 divides by the number of observed entries of the row: 0/0 -> NaN, unguarded."""
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import tPLS
+    X, Y, _ = orc.synthetic((40, 6, 5), 2, 3, error=0.3, seed=2)
+    est = tPLS(2)
+    est.fit(X, Y)
+    Xn = X[:6].copy()
+    Xn[2] = np.nan
+    Xn[4, 1, 1] = np.nan
+    s = est.transform(Xn)
+    assert np.isnan(s[2]).all() and np.isfinite(np.delete(s, 2, axis=0)).all()
+    ref = orc.fit([X.copy()], Y.copy(), 2, r2_mode="residual")
+    want = orc.transform(ref, [Xn.copy()])
+    keep = np.arange(6) != 2
+    assert col_err(s[keep], want[keep]) < FP64_TOL
