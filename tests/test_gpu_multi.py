@@ -35,7 +35,8 @@ def _whole(path, n_tensors, n_modes):
                 W=[[p[f"W{l}_{k}"] for k in range(n_modes[l])] for l in range(n_tensors)]), p
 
 
-@pytest.mark.parametrize("case", ["ct_90x32x16_90x24_m4_r5", "t3_miss_70x12x8_m4_r4", "t4_60x8x6x4_m3_r4"])
+@pytest.mark.parametrize("case", ["ct_90x32x16_90x24_m4_r5", "t3_miss_70x12x8_m4_r4", "t4_60x8x6x4_m3_r4",
+                                  "t2_same_xy_40x30_r4"])   # the last one has 30 responses: explicit ||du||^2 exchange
 def test_sharded_fit_matches_golden(tmp_path, case):
     world = min(_ngpu(), 4)
     if world < 2:
