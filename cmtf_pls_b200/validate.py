@@ -39,33 +39,72 @@ def _to_device(X, device):
     return torch.from_numpy(np.ascontiguousarray(X)).to(dev)
 
 
+def _device_fold_fit(Xd, Yd, R, tol, max_iter, device, algorithm):
+    """The product's fold fit: one R-component device fit with the fold as 0/1 row weights."""
+    def fit_fold(w):
+        return _core.run_fit(Xd, Yd, R, tol, max_iter, device=device, row_weights=w, algorithm=algorithm)
+    return fit_fold
+
+
+def _sum_over_ranks(arrays, group, device):
+    """In-place sum of small host arrays over the ranks of ``group`` (True = default group)."""
+    import torch
+    import torch.distributed as dist
+    pg = None if group is True else group
+    on_gpu = dist.get_backend(pg) == "nccl"
+    for a in arrays:
+        t = torch.from_numpy(a)
+        if on_gpu:
+            d = t.to(torch.device("cuda", device if device is not None else torch.cuda.current_device()))
+            dist.all_reduce(d, group=pg)
+            t.copy_(d)
+        else:
+            dist.all_reduce(t, group=pg)
+
+
 def q2y_sweep(X, Y, n_components, n_splits=5, seed=0, device=None, tol=1e-8, max_iter=100, folds=None,
-              return_scores=False):
+              return_scores=False, algorithm="stream", fold_group=None, _fit_fold=None):
     """Q2Y for 1, 2, ..., ``n_components`` components by K-fold cross-validation.
 
     ``X`` is one tensor (tPLS) or a list of coupled tensors (ctPLS); ``folds``
     optionally gives the held-out row indices of every fold explicitly.
     Returns an array of ``n_components`` values (and, with ``return_scores``,
     the cross-validated scores of every sample, shape (N, n_components)).
+
+    ``fold_group`` (a torch.distributed process group, or True for the default
+    one) runs the sweep FOLD-PARALLEL (folds are independent
+    units): every rank holds the complete X and Y, fits folds rank, rank +
+    world, ... on its own GPU with no data-path collective, and only the R
+    PRESS sums (and the cross-validated scores when asked for) are summed over
+    the ranks at the end.  Every rank returns the same result.
     """
     Xs = list(X) if isinstance(X, (list, tuple)) else [X]
     Yn = Y.detach().cpu().numpy() if _core._is_torch(Y) else np.asarray(Y)
     Y2 = np.asarray(Yn, dtype=np.float64).reshape(Yn.shape[0], -1)
     n, R = Y2.shape[0], int(n_components)
-    Xd = [_to_device(x, device) for x in Xs]
-    Yd = _to_device(Y2, device)
     folds = _folds(n, n_splits, seed) if folds is None else [np.asarray(f) for f in folds]
+    rank, world = 0, 1
+    if fold_group is not None and fold_group is not False:
+        import torch.distributed as dist
+        pg = None if fold_group is True else fold_group
+        rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+    if _fit_fold is None:                      # tests inject a CPU fit to exercise the fold plumbing without a GPU
+        Xd = [_to_device(x, device) for x in Xs]
+        Yd = _to_device(Y2, device)
+        _fit_fold = _device_fold_fit(Xd, Yd, R, tol, max_iter, device, algorithm)
     press = np.zeros(R)
     cv_scores = np.zeros((n, R))
-    for held in folds:
+    for held in folds[rank::world]:
         w = np.ones(n)
         w[held] = 0.0
-        st = _core.run_fit(Xd, Yd, R, tol, max_iter, device=device, row_weights=w)
+        st = _fit_fold(w)
         T = st["T"][held]
         cv_scores[held] = T
         for k in range(1, R + 1):
             pred = T[:, :k] @ st["coef"][:k, :k] @ st["Q"][:, :k].T + st["Y_mean"]
             press[k - 1] += float(np.sum((pred - Y2[held]) ** 2))
+    if world > 1:
+        _sum_over_ranks([press, cv_scores] if return_scores else [press], fold_group, device)
     q2 = 1.0 - press / float(np.sum(Y2 ** 2))
     return (q2, cv_scores) if return_scores else q2
 

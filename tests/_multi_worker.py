@@ -21,6 +21,17 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     from cmtf_pls_b200 import ctPLS
     from cmtf_pls_b200.sharding import shard_rows, row_block
+    if case == "cvfold":
+        # fold-parallel sweep: every rank holds all rows and fits its own folds, no data-path collective
+        from oracle import tpls_oracle as orc
+        from cmtf_pls_b200 import q2y_sweep
+        from cmtf_pls_b200.validate import _folds
+        X, Y, _ = orc.synthetic((90, 12, 8), 3, 4, error=0.4, seed=9)
+        q, cv = q2y_sweep(X, Y, 4, folds=_folds(90, 5, 3), return_scores=True, device=local, fold_group=True)
+        if rank == 0:
+            np.savez(out, q=q, cv=cv)
+        dist.destroy_process_group()
+        return
     if case.startswith("synthetic"):
         from oracle import tpls_oracle as orc
         dt = np.float32 if case.endswith("f32") else np.float64

@@ -70,3 +70,21 @@ def test_sharded_fit_matches_oracle_c4_rows(tmp_path, case, tol):
     assert p["trips"].tolist() == ref["trips"].tolist()
     for k, e in aligned_errors(whole, ref).items():
         assert e < tol, (case, k, e)
+
+
+def test_fold_parallel_cv_sweep_matches_oracle_refits(tmp_path):
+    """the folds of the cross-validation sweep are independent units -- one fold per GPU,
+    only the PRESS sums cross devices."""
+    world = min(_ngpu(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200.validate import _folds
+    X, Y, _ = orc.synthetic((90, 12, 8), 3, 4, error=0.4, seed=9)
+    q_ref, cv_ref = orc.q2y_kfold(X, Y, 4, _folds(90, 5, 3))
+    out = str(tmp_path / "cv.npz")
+    _run("cvfold", world, out)
+    p = np.load(out)
+    assert np.max(np.abs(p["q"] - q_ref)) < 1e-8
+    s = np.sign(np.sum(p["cv"] * cv_ref, axis=0))
+    assert np.max(np.abs(p["cv"] * s - cv_ref)) / np.max(np.abs(cv_ref)) < 1e-8

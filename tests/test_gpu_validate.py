@@ -19,12 +19,13 @@ def test_q2y_sweep_matches_oracle_refits(shape, coupled, miss):
         X[rng.random(X.shape) < 0.1] = np.nan
     folds = _folds(shape[0], 5, 3)
     q_ref, cv_ref = orc.q2y_kfold(X, Y, 4, folds)
-    q, cv = q2y_sweep(X, Y, 4, n_splits=5, seed=3, return_scores=True)
-    assert np.max(np.abs(q - q_ref)) < 1e-8
-    # held-out rows' scores are transform() of the held-out data under each fold's model
-    s = np.sign(np.sum(cv * cv_ref, axis=0))
-    assert np.max(np.abs(cv * s - cv_ref)) / np.max(np.abs(cv_ref)) < 1e-8
-    assert q[-1] > 0.5 and np.all(np.diff(q[:3]) > -1e-3)
+    for alg in ("stream", "covariance"):
+        q, cv = q2y_sweep(X, Y, 4, n_splits=5, seed=3, return_scores=True, algorithm=alg)
+        assert np.max(np.abs(q - q_ref)) < 1e-8, alg
+        # held-out rows' scores are transform() of the held-out data under each fold's model
+        s = np.sign(np.sum(cv * cv_ref, axis=0))
+        assert np.max(np.abs(cv * s - cv_ref)) / np.max(np.abs(cv_ref)) < 1e-8, alg
+        assert q[-1] > 0.5 and np.all(np.diff(q[:3]) > -1e-3)
 
 
 def test_get_q2y_leave_one_out_like_reference():

@@ -83,3 +83,41 @@ def test_row_block_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         row_block(10, 3, 3)
+
+
+# --------------------------------------------------------------------------
+# fold-parallel cross-validation sweep (folds are independent units)
+# --------------------------------------------------------------------------
+def _fold_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cmtf_pls_b200.validate import q2y_sweep, _folds
+    from oracle import tpls_oracle as orc
+    X, Y, _ = orc.synthetic((40, 8, 6), 3, 3, error=0.4, seed=9)
+    fitted = []
+
+    def fit_fold(w):            # CPU stand-in for the device fit: refit on the kept rows, project every row
+        keep = w > 0
+        st = orc.fit([X[keep]], Y[keep], 3, r2_mode="residual")
+        fitted.append(int(np.flatnonzero(~keep)[0]))
+        return dict(T=orc.transform(st, [X]), coef=st["coef"], Q=st["Q"], Y_mean=st["Y_mean"])
+
+    folds = _folds(40, 5, 3)
+    q, cv = q2y_sweep(X, Y, 3, folds=folds, return_scores=True, fold_group=True, _fit_fold=fit_fold)
+    np.savez(os.path.join(out_dir, f"f{rank}.npz"), q=q, cv=cv, n_fits=np.array(len(fitted)))
+    dist.destroy_process_group()
+
+
+def test_fold_parallel_sweep_over_gloo(tmp_path):
+    from cmtf_pls_b200.validate import _folds
+    from oracle import tpls_oracle as orc
+    world = 2
+    mp.spawn(_fold_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    X, Y, _ = orc.synthetic((40, 8, 6), 3, 3, error=0.4, seed=9)
+    q_ref, cv_ref = orc.q2y_kfold(X, Y, 3, _folds(40, 5, 3))
+    parts = [np.load(tmp_path / f"f{r}.npz") for r in range(world)]
+    assert [int(p["n_fits"]) for p in parts] == [3, 2]          # folds 0, 2, 4 on rank 0; 1, 3 on rank 1
+    for p in parts:                                             # every rank returns the complete result
+        assert np.max(np.abs(p["q"] - q_ref)) < 1e-10
+        assert np.max(np.abs(p["cv"] - cv_ref)) < 1e-9 * np.max(np.abs(cv_ref))
