@@ -56,7 +56,7 @@ struct Tensor {
     int* miss_flag = nullptr;
     int* sweeps = nullptr;
     size_t r1_ws = 0;
-    int r1_nmax = 1, r1_zs = 0, r1_mt = 0;
+    int r1_nmax = 1, r1_zs = 0, r1_mt = 0, r1_tab = 0;
     // arena offsets (doubles)
     size_t off_colsum = 0, off_colcnt = 0, off_z = 0, off_ss = 0;
 };
@@ -561,6 +561,8 @@ int tpls_set_x(tpls_handle h, int index, const void* x, int dtype, int ndim, con
     long long p = 1;
     for (int k = 0; k < ndim; ++k) {
         if (shape[k] <= 0) return fail(h, "tpls_set_x: empty mode %d", k);
+        if (k && ndim > 3 && shape[k] > 65535)  // the rank-1 kernel keeps per-mode indices of a >= 3-way Z in 16 bits
+            return fail(h, "tpls_set_x: mode %d of a %d-way X has %lld entries, at most 65535 are supported", k, ndim, (long long)shape[k]);
         t.shape[k] = shape[k];
         if (k) p *= shape[k];
     }
@@ -748,7 +750,7 @@ static int layout_fit(tpls_handle h, int L, int R) {
         TRY(dev_alloc(h, (void**)&t.sweeps, sizeof(int) * 4, tr));
         int dims[kMaxZModes];
         for (int k = 1; k < t.ndim; ++k) dims[k - 1] = (int)t.shape[k];
-        t.r1_ws = rank1_workspace_doubles(t.ndim - 1, dims, &t.r1_nmax, &t.r1_zs, &t.r1_mt);
+        t.r1_ws = rank1_workspace_doubles(t.ndim - 1, dims, &t.r1_nmax, &t.r1_zs, &t.r1_mt, &t.r1_tab);
         TRY(dev_alloc(h, (void**)&t.r1_scratch, sizeof(double) * t.r1_ws, tr));
     }
     return 0;
@@ -771,6 +773,7 @@ static void fill_rank1_task(tpls_handle h, Tensor& t, int a, Rank1Task& k, bool 
     k.nmax = t.r1_nmax;
     k.zs_len = t.r1_zs;
     k.mt_len = t.r1_mt;
+    k.tab_cols = t.r1_tab;
     k.sweeps = t.sweeps;
 }
 
@@ -1878,11 +1881,12 @@ int tpls_op_rank1(tpls_handle h, const double* z, int nmodes, const int* dims, d
     k.pitch = (int)p;
     k.nmodes = nmodes;
     k.wkron = wkron_out;
-    int nmax = 1, zs_len = 0, mt_len = 0;
-    const size_t ws = rank1_workspace_doubles(nmodes, dims, &nmax, &zs_len, &mt_len);
+    int nmax = 1, zs_len = 0, mt_len = 0, tab_cols = 0;
+    const size_t ws = rank1_workspace_doubles(nmodes, dims, &nmax, &zs_len, &mt_len, &tab_cols);
     k.nmax = nmax;
     k.zs_len = zs_len;
     k.mt_len = mt_len;
+    k.tab_cols = tab_cols;
     double* scratch = nullptr;
     int* sweeps = nullptr;
     CK(cudaMalloc((void**)&scratch, sizeof(double) * ws));
@@ -1892,8 +1896,8 @@ int tpls_op_rank1(tpls_handle h, const double* z, int nmodes, const int* dims, d
     long long* stamps = nullptr;
     const bool want_stamps = getenv("TPLS_RANK1_STAMPS") != nullptr;
     if (want_stamps) {
-        CK(cudaMalloc((void**)&stamps, sizeof(long long) * 8));
-        CK(cudaMemset(stamps, 0, sizeof(long long) * 8));
+        CK(cudaMalloc((void**)&stamps, sizeof(long long) * 16));
+        CK(cudaMemset(stamps, 0, sizeof(long long) * 16));
         k.stamps = stamps;
     }
     size_t smem = ws * sizeof(double);
@@ -1907,10 +1911,12 @@ int tpls_op_rank1(tpls_handle h, const double* z, int nmodes, const int* dims, d
     cudaStreamSynchronize(h->stream);
     if (!rc && sweeps_out) cudaMemcpy(sweeps_out, sweeps, sizeof(int), cudaMemcpyDeviceToHost);
     if (want_stamps) {
-        long long hs[8];
+        long long hs[16];
         cudaMemcpy(hs, stamps, sizeof hs, cudaMemcpyDeviceToHost);
         fprintf(stderr, "rank1 stamps (cycles): load->gram %lld  eig %lld  init-rest %lld  als %lld  publish %lld\n", hs[1] - hs[0],
                 hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4]);
+        fprintf(stderr, "   last run: als rows %lld  als sums %lld  als renorm %lld | squarings %lld  in %lld  eig tail %lld\n", hs[8],
+                hs[9], hs[10], hs[12], hs[13], hs[14]);
         cudaFree(stamps);
     }
     cudaFree(scratch);

@@ -12,9 +12,11 @@
 // rank one, so "1 - trace < 1e-7" means the iterate just formed has a
 // second-to-first eigenvalue ratio below ~1e-14: logarithmic in the spectral
 // gap, one tiny reduction per step, then two polish steps against the original
-// Gram matrix.  Everything is fp64.  Matrices are stored with leading dimension
-// rounded up to 4 and zero pads so that the 4x4 register tiles need no bounds
-// checks and load 16 bytes at a time.
+// Gram matrix.  Everything is fp64.  Matrices are stored with their order rounded
+// up to 4 (zero pads, so the 4x4 register tiles need no bounds checks and load 16
+// bytes at a time) and a leading dimension of that + 2, so that consecutive rows
+// start 16 bytes apart modulo 128: the lanes that split a contraction index
+// between them read conflict-free.
 #include "rank1.cuh"
 
 #include <algorithm>
@@ -27,52 +29,81 @@ constexpr int NTH = kRank1Threads;
 constexpr int NWARP = NTH / 32;
 
 __host__ __device__ inline int up4(int v) { return (v + 3) & ~3; }
+__host__ __device__ inline int ldp(int v) { return up4(v) + 2; }  // leading dimension of a padded matrix of order v
 
-// block-wide sums with ONE barrier each: warp partials go to one of two alternating
-// buffers, every thread then folds the 16 partials itself
-struct Blk {
+// Workspace of the HOSVD start of one mode of a >= 3-way Z (doubles): the unfolding copy, the Gram matrix and
+// the two squaring buffers, two vectors.  Every mode has its own area because the modes are worked on
+// concurrently by different thread groups.
+struct ModeWs {
+    int n;       // order of the Gram matrix: min(dk, mk)
+    int ld;      // its leading dimension
+    int mt;      // doubles of the unfolding copy
+    int gram;    // doubles of ONE n4 x ld matrix
+    int vec;     // doubles of one work vector
+    int total;
+};
+__host__ __device__ inline ModeWs mode_ws(int dk, int mk) {
+    ModeWs w;
+    w.n = dk <= mk ? dk : mk;
+    w.ld = ldp(w.n);
+    w.mt = up4((dk <= mk ? mk : dk) * w.ld);
+    w.gram = up4(w.n) * w.ld;
+    w.vec = up4(dk);
+    w.total = w.mt + 3 * w.gram + 2 * w.vec;
+    return w;
+}
+
+// A group of warps of the CTA that synchronises on its own named barrier: the whole CTA (barrier 0, i.e.
+// __syncthreads) or one slice of it per mode during the HOSVD start.  Block-wide sums take ONE barrier: warp
+// partials go to one of two alternating buffers, every thread then folds the partials itself.
+struct Grp {
+    int tid, nth, bar;
     double* red;  // [2][2*NWARP]
     int* ired;    // [2][NWARP]
     int flip;
+    long long* dbg;  // optional diagnostics (clock64 accumulators), nullptr in normal use
+    __device__ __forceinline__ void sync() const { named_bar_sync(bar, nth); }
+    __device__ __forceinline__ void tick(int slot, long long t0) const {
+        if (dbg != nullptr && tid == 0) dbg[slot] += clock64() - t0;
+    }
 };
 
-__device__ __forceinline__ double bsum(double v, Blk& b) {
+__device__ __forceinline__ double bsum(double v, Grp& g) {
     v = warp_sum(v);
-    double* r = b.red + b.flip * 2 * NWARP;
-    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
-    __syncthreads();
+    double* r = g.red + g.flip * 2 * NWARP;
+    if ((g.tid & 31) == 0) r[g.tid >> 5] = v;
+    g.sync();
     double t = 0.0;
-#pragma unroll
-    for (int q = 0; q < NWARP; ++q) t += r[q];
-    b.flip ^= 1;
+    const int nw = g.nth >> 5;
+    for (int q = 0; q < nw; ++q) t += r[q];
+    g.flip ^= 1;
     return t;
 }
 
-__device__ __forceinline__ void bsum2(double& v1, double& v2, Blk& b) {
-    v1 = warp_sum(v1);
-    v2 = warp_sum(v2);
-    double* r = b.red + b.flip * 2 * NWARP;
-    if ((threadIdx.x & 31) == 0) {
-        r[threadIdx.x >> 5] = v1;
-        r[NWARP + (threadIdx.x >> 5)] = v2;
+// the same for two values that only lane 0 of every warp holds (no warp-level fold needed)
+__device__ __forceinline__ void bsum2_lane0(double& v1, double& v2, Grp& g) {
+    double* r = g.red + g.flip * 2 * NWARP;
+    if ((g.tid & 31) == 0) {
+        r[g.tid >> 5] = v1;
+        r[NWARP + (g.tid >> 5)] = v2;
     }
-    __syncthreads();
+    g.sync();
     double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-    for (int q = 0; q < NWARP; ++q) {
+    const int nw = g.nth >> 5;
+    for (int q = 0; q < nw; ++q) {
         t1 += r[q];
         t2 += r[NWARP + q];
     }
-    b.flip ^= 1;
+    g.flip ^= 1;
     v1 = t1;
     v2 = t2;
 }
 
 // index of the first entry with the largest |a[i]|
-__device__ __forceinline__ int argmax_abs(const double* a, int n, Blk& b) {
+__device__ __forceinline__ int argmax_abs(const double* a, int n, Grp& g) {
     double bv = -1.0;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += NTH) {
+    for (int i = g.tid; i < n; i += g.nth) {
         const double v = fabs(a[i]);
         if (v > bv) {
             bv = v;
@@ -87,17 +118,17 @@ __device__ __forceinline__ int argmax_abs(const double* a, int n, Blk& b) {
             bi = oi;
         }
     }
-    double* r = b.red + b.flip * 2 * NWARP;
-    int* ir = b.ired + b.flip * NWARP;
-    if ((threadIdx.x & 31) == 0) {
-        r[threadIdx.x >> 5] = bv;
-        ir[threadIdx.x >> 5] = bi;
+    double* r = g.red + g.flip * 2 * NWARP;
+    int* ir = g.ired + g.flip * NWARP;
+    if ((g.tid & 31) == 0) {
+        r[g.tid >> 5] = bv;
+        ir[g.tid >> 5] = bi;
     }
-    __syncthreads();
+    g.sync();
     bv = r[0];
     bi = ir[0];
-#pragma unroll
-    for (int q = 1; q < NWARP; ++q) {
+    const int nw = g.nth >> 5;
+    for (int q = 1; q < nw; ++q) {
         const double ov = r[q];
         const int oi = ir[q];
         if (ov > bv || (ov == bv && oi < bi)) {
@@ -105,49 +136,99 @@ __device__ __forceinline__ int argmax_abs(const double* a, int n, Blk& b) {
             bi = oi;
         }
     }
-    b.flip ^= 1;
+    g.flip ^= 1;
     return bi;
 }
 
-// C[i*n4 + j] = scale * sum_k Mt[k*n4 + i] * Mt[k*n4 + j]   (n4 % 4 == 0, pads of Mt are zero)
-__device__ __forceinline__ void syrk_fast(double* __restrict__ C, const double* __restrict__ Mt, int krows, int n4, double scale) {
-    // a thread owns rows i0..i0+3 (contiguous: two broadcast 16-byte loads) and columns tj, tj+nt, tj+2nt,
-    // tj+3nt (strided: the 16 lanes of a tile row read 16 consecutive doubles -- conflict-free)
+// C = scale * Mt^T Mt on the leading n4 x n4 block (n4 % 4 == 0; Mt is krows x n4 with leading dimension
+// ldm, C has leading dimension ldc, pads of Mt are zero).  C is symmetric: only the 4x4 tiles on or above
+// the diagonal are computed, then mirrored.  The active tiles are packed into consecutive threads (an fp64
+// instruction costs the same pipe time for a warp with one active lane) and the contraction index is split
+// over S lanes of a warp that meet in a shuffle tree, so that small matrices with a long contraction (the
+// Gram matrix of a wide unfolding) and the squarings of small matrices still use the whole group.  Fixed
+// association order => bit-reproducible.
+// TRACE: returns trace(C) through one group reduction whose barrier also publishes C.
+template <bool TRACE>
+__device__ __forceinline__ double syrk_tri(double* __restrict__ C, int ldc, const double* __restrict__ Mt, int ldm, int krows,
+                                           int n4, double scale, Grp& g) {
     const int nt = n4 >> 2;
-    for (int t = threadIdx.x; t < nt * nt; t += NTH) {
-        const int i0 = (t / nt) << 2, tj = t % nt;
+    const int ntri = (nt * (nt + 1)) >> 1;
+    int S = 1;
+    while (S < 32 && ntri * (S * 2) <= g.nth && S * 2 <= krows) S <<= 1;
+    const int ks = g.tid & (S - 1);
+    const int slot = g.tid / S;
+    const int per_round = g.nth / S;
+    double tr = 0.0;
+    for (int base = 0; base < ntri; base += per_round) {  // warp-uniform trip count: the shuffles below stay converged
+        const int t = base + slot;
+        const bool active = t < ntri;
+        int ti = 0, tj = 0;
+        if (active) {
+            int rem = t, len = nt;
+            while (rem >= len) {
+                rem -= len;
+                --len;
+                ++ti;
+            }
+            tj = ti + rem;
+        }
         double acc[4][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[q][r] = 0.0;
-        const double* pa = Mt + i0;
-        const double* pb = Mt + tj;
-#pragma unroll 4
-        for (int k = 0; k < krows; ++k) {
-            const double2 a01 = *reinterpret_cast<const double2*>(pa + (size_t)k * n4);
-            const double2 a23 = *reinterpret_cast<const double2*>(pa + (size_t)k * n4 + 2);
-            const double ai[4] = {a01.x, a01.y, a23.x, a23.y};
-            double bj[4];
+        if (active) {
+            const double* pa = Mt + 4 * ti;
+            const double* pb = Mt + 4 * tj;
+#pragma unroll 2
+            for (int k = ks; k < krows; k += S) {
+                const double2 a01 = *reinterpret_cast<const double2*>(pa + (size_t)k * ldm);
+                const double2 a23 = *reinterpret_cast<const double2*>(pa + (size_t)k * ldm + 2);
+                const double2 b01 = *reinterpret_cast<const double2*>(pb + (size_t)k * ldm);
+                const double2 b23 = *reinterpret_cast<const double2*>(pb + (size_t)k * ldm + 2);
+                const double ai[4] = {a01.x, a01.y, a23.x, a23.y};
+                const double bj[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-            for (int r = 0; r < 4; ++r) bj[r] = pb[(size_t)k * n4 + r * nt];
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[q][r] = fma(ai[q], bj[r], acc[q][r]);
+            }
+        }
+        __syncwarp();
+        for (int m = S >> 1; m >= 1; m >>= 1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) acc[q][r] = fma(ai[q], bj[r], acc[q][r]);
+                for (int r = 0; r < 4; ++r) acc[q][r] += shfl_xor_d(acc[q][r], m);
         }
+        if (active && ks == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 4; ++q) {
+                double* row = C + (size_t)(4 * ti + q) * ldc + 4 * tj;
+                *reinterpret_cast<double2*>(row) = make_double2(acc[q][0] * scale, acc[q][1] * scale);
+                *reinterpret_cast<double2*>(row + 2) = make_double2(acc[q][2] * scale, acc[q][3] * scale);
+            }
+            if (ti != tj) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) C[(size_t)(i0 + q) * n4 + tj + r * nt] = acc[q][r] * scale;
+                for (int r = 0; r < 4; ++r) {
+                    double* row = C + (size_t)(4 * tj + r) * ldc + 4 * ti;
+                    *reinterpret_cast<double2*>(row) = make_double2(acc[0][r] * scale, acc[1][r] * scale);
+                    *reinterpret_cast<double2*>(row + 2) = make_double2(acc[2][r] * scale, acc[3][r] * scale);
+                }
+            } else if (TRACE) {
+                tr += ((acc[0][0] + acc[1][1]) + (acc[2][2] + acc[3][3])) * scale;
+            }
+        }
     }
-    __syncthreads();
+    if (TRACE) return bsum(tr, g);
+    g.sync();
+    return 0.0;
 }
 
 // y[i] = sum_{j < cols} M[i*ld + j] * x[j], i < rows: 8 lanes per row
-__device__ __forceinline__ void matvec8(double* y, const double* M, int ld, const double* x, int rows, int cols) {
-    const int part = threadIdx.x & 7, r0 = threadIdx.x >> 3;
-    for (int rb = 0; rb < rows; rb += NTH / 8) {
+__device__ __forceinline__ void matvec8(double* y, const double* M, int ld, const double* x, int rows, int cols, const Grp& g) {
+    const int part = g.tid & 7, r0 = g.tid >> 3;
+    for (int rb = 0; rb < rows; rb += g.nth / 8) {
         const int i = rb + r0;
         double s = 0.0;
         if (i < rows)
@@ -157,51 +238,48 @@ __device__ __forceinline__ void matvec8(double* y, const double* M, int ld, cons
         s += shfl_xor_d(s, 1);
         if (i < rows && part == 0) y[i] = s;
     }
-    __syncthreads();
+    g.sync();
 }
 
-__device__ __forceinline__ double vec_dot(const double* a, const double* b, int n, Blk& blk) {
+__device__ __forceinline__ double vec_dot(const double* a, const double* b, int n, Grp& g) {
     double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += NTH) s = fma(a[i], b[i], s);
-    return bsum(s, blk);
+    for (int i = g.tid; i < n; i += g.nth) s = fma(a[i], b[i], s);
+    return bsum(s, g);
 }
 
-__device__ __forceinline__ void vec_div(double* a, double d, int n) {
-    for (int i = threadIdx.x; i < n; i += NTH) a[i] /= d;
-    __syncthreads();
-}
-
-// dst = src / ||src||
-__device__ __forceinline__ void normalize_into(double* dst, const double* src, int n, Blk& blk) {
+// dst = src / ||src||; returns ||src||
+__device__ __forceinline__ double normalize_into(double* dst, const double* src, int n, Grp& g) {
     double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += NTH) s = fma(src[i], src[i], s);
-    const double nv = sqrt(bsum(s, blk));
-    for (int i = threadIdx.x; i < n; i += NTH) dst[i] = src[i] / nv;
-    __syncthreads();
+    for (int i = g.tid; i < n; i += g.nth) s = fma(src[i], src[i], s);
+    const double nv = sqrt(bsum(s, g));
+    for (int i = g.tid; i < n; i += g.nth) dst[i] = src[i] / nv;
+    g.sync();
+    return nv;
 }
 
-// Leading eigenpair of the symmetric PSD matrix G (n x n stored n4 x n4 with zero pads).
-// A, B: n4*n4 work buffers.  v (n) receives the unit eigenvector; returns the eigenvalue.
-__device__ __forceinline__ double lead_eig(const double* G, double* A, double* B, double* v, double* tmp, int n, Blk& blk, int polish,
-                                           bool want_lambda) {
+// Leading eigenpair of the symmetric PSD matrix G (order n, stored up4(n) x up4(n) with zero pads, leading
+// dimension ld).  A, B: work buffers of the same shape.  v (n) receives the unit eigenvector; returns the
+// eigenvalue when asked for it.
+__device__ __forceinline__ double lead_eig(const double* G, double* A, double* B, double* v, double* tmp, int n, int ld, Grp& g,
+                                           int polish, bool want_lambda) {
     const int n4 = up4(n);
     double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += NTH) s += G[(size_t)i * n4 + i];
-    const double tr = bsum(s, blk);
+    for (int i = g.tid; i < n; i += g.nth) s += G[(size_t)i * ld + i];
+    const double tr = bsum(s, g);
     if (!(tr > 0.0)) {
-        for (int i = threadIdx.x; i < n; i += NTH) v[i] = 0.0;
-        __syncthreads();
+        for (int i = g.tid; i < n; i += g.nth) v[i] = 0.0;
+        g.sync();
         return 0.0;
     }
     const double* src = G;
     double* dst = A;
     double* oth = B;
     double scale = (1.0 / tr) * (1.0 / tr);
+    const long long c0 = g.dbg != nullptr ? clock64() : 0;
     for (int it = 0; it < 64; ++it) {
-        syrk_fast(dst, src, n4, n4, scale);  // dst = (src / tr(src))^2
-        s = 0.0;
-        for (int i = threadIdx.x; i < n; i += NTH) s += dst[(size_t)i * n4 + i];
-        const double tau = bsum(s, blk);  // sum of squared normalised eigenvalues, -> 1 at rank one
+        // dst = (src / tr(src))^2; tau = its trace = sum of squared normalised eigenvalues, -> 1 at rank one
+        const double tau = syrk_tri<true>(dst, ld, src, ld, n4, n4, scale, g);
+        if (g.dbg != nullptr && g.tid == 0) g.dbg[12] += 1;
         src = dst;
         double* sw = dst;
         dst = oth;
@@ -209,33 +287,35 @@ __device__ __forceinline__ double lead_eig(const double* G, double* A, double* B
         if (1.0 - tau < 1e-7) break;
         scale = (1.0 / tau) * (1.0 / tau);
     }
+    g.tick(13, c0);
+    const long long c1 = g.dbg != nullptr ? clock64() : 0;
     // src ~ v v^T: take the column with the largest diagonal entry
-    for (int i = threadIdx.x; i < n; i += NTH) tmp[i] = src[(size_t)i * n4 + i];
-    __syncthreads();
-    const int bi = argmax_abs(tmp, n, blk);
-    for (int i = threadIdx.x; i < n; i += NTH) v[i] = src[(size_t)i * n4 + bi];
-    __syncthreads();
-    double nv = sqrt(vec_dot(v, v, n, blk));
-    vec_div(v, nv, n);
+    for (int i = g.tid; i < n; i += g.nth) tmp[i] = src[(size_t)i * ld + i];
+    g.sync();
+    const int bi = argmax_abs(tmp, n, g);
+    for (int i = g.tid; i < n; i += g.nth) tmp[i] = src[(size_t)i * ld + bi];
+    g.sync();
+    normalize_into(v, tmp, n, g);
     // polish against the original matrix
+    double nv = 0.0;
     for (int q = 0; q < polish; ++q) {
-        matvec8(tmp, G, n4, v, n, n);
-        nv = sqrt(vec_dot(tmp, tmp, n, blk));
-        for (int i = threadIdx.x; i < n; i += NTH) v[i] = tmp[i] / nv;
-        __syncthreads();
+        matvec8(tmp, G, ld, v, n, n, g);
+        nv = normalize_into(v, tmp, n, g);
     }
+    g.tick(14, c1);
     if (!want_lambda) return 0.0;
-    matvec8(tmp, G, n4, v, n, n);
-    return vec_dot(tmp, v, n, blk);
+    if (polish > 0) return nv;  // ||G v|| of the last step: the eigenvalue to the accuracy of v (quadratic in its error)
+    matvec8(tmp, G, ld, v, n, n, g);
+    return vec_dot(tmp, v, n, g);
 }
 
-__device__ __forceinline__ void flip_to_positive_peak(double* f, int n, Blk& blk) {
-    const int i = argmax_abs(f, n, blk);
+__device__ __forceinline__ void flip_to_positive_peak(double* f, int n, Grp& g) {
+    const int i = argmax_abs(f, n, g);
     const bool neg = f[i] < 0.0;
-    __syncthreads();
+    g.sync();
     if (neg)
-        for (int q = threadIdx.x; q < n; q += NTH) f[q] = -f[q];
-    __syncthreads();
+        for (int q = g.tid; q < n; q += g.nth) f[q] = -f[q];
+    g.sync();
 }
 
 // the factor vectors live back to back in the workspace; offsets stay in registers so that the compiler
@@ -267,71 +347,220 @@ __device__ __forceinline__ int unf_index(const Geo& g, int a, int j) {
 }
 
 // f[a] = sum_j Zk(a, j) * x[j]   (general mode, strided)
-__device__ __forceinline__ void unf_matvec(double* f, const double* zs, const Geo& g, const double* x) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int a = w; a < g.dk; a += NWARP) {
+__device__ __forceinline__ void unf_matvec(double* f, const double* zs, const Geo& geo, const double* x, const Grp& g) {
+    const int lane = g.tid & 31, w = g.tid >> 5, nw = g.nth >> 5;
+    for (int a = w; a < geo.dk; a += nw) {
         double s = 0.0;
-        for (int j = lane; j < g.mk; j += 32) s = fma(zs[unf_index(g, a, j)], x[j], s);
+        for (int j = lane; j < geo.mk; j += 32) s = fma(zs[unf_index(geo, a, j)], x[j], s);
         s = warp_sum(s);
         if (lane == 0) f[a] = s;
     }
-    __syncthreads();
+    g.sync();
 }
 
-// kr[j] = prod_{m != k} f_m[i_m(j)], j enumerating the other modes in C order
-__device__ __forceinline__ void other_modes_product(double* kr, const Rank1Task& T, int k, const Facs& f, int mk) {
-    for (int j = threadIdx.x; j < mk; j += NTH) {
-        int rem = j;
-        double pr = 1.0;
-        for (int m = T.nmodes - 1; m >= 0; --m) {
-            if (m == k) continue;
-            const int d = T.dims[m];
-            const int i = rem % d;
-            rem /= d;
-            pr *= f[m][i];
+// HOSVD start of ONE mode (tensorly initialize_cp, init="svd"): the leading left singular vector of the mode-k
+// unfolding, sign fixed so that its largest-|entry| is positive.  Runs on the thread group g with the group's
+// own workspace w; returns the singular value (wanted for mode 0 only, which carries sigma into the weights).
+__device__ __forceinline__ double hosvd_mode(const double* zs, const Geo& geo, double* fk, double* w, Grp& g, bool want_sigma) {
+    const ModeWs m = mode_ws(geo.dk, geo.mk);
+    double* mt = w;
+    double* G = mt + m.mt;
+    double* A = G + m.gram;
+    double* B = A + m.gram;
+    double* tmp = B + m.gram;
+    double* tmp2 = tmp + m.vec;
+    const int n4 = up4(m.n), ld = m.ld;
+    double sigma = 0.0;
+    if (geo.dk <= geo.mk) {
+        // Mt[j][a] = Zk(a, j): rows are the columns of the unfolding
+        for (int i = g.tid; i < geo.mk * n4; i += g.nth) {
+            const int j = i / n4, a = i - j * n4;
+            mt[(size_t)j * ld + a] = a < geo.dk ? zs[unf_index(geo, a, j)] : 0.0;
         }
-        kr[j] = pr;
+        g.sync();
+        syrk_tri<false>(G, ld, mt, ld, geo.mk, n4, 1.0, g);
+        const double lam = lead_eig(G, A, B, fk, tmp, geo.dk, ld, g, 2, want_sigma);
+        sigma = sqrt(lam);
+    } else {
+        // tall unfolding: eigenvector of the small side, then one multiplication by the unfolding
+        for (int i = g.tid; i < geo.dk * n4; i += g.nth) {
+            const int a = i / n4, j = i - a * n4;
+            mt[(size_t)a * ld + j] = j < geo.mk ? zs[unf_index(geo, a, j)] : 0.0;
+        }
+        g.sync();
+        syrk_tri<false>(G, ld, mt, ld, geo.dk, n4, 1.0, g);
+        lead_eig(G, A, B, tmp2, tmp, geo.mk, ld, g, 2, false);
+        unf_matvec(tmp, zs, geo, tmp2, g);
+        sigma = normalize_into(fk, tmp, geo.dk, g);
     }
-    __syncthreads();
+    flip_to_positive_peak(fk, geo.dk, g);
+    return sigma;
+}
+
+struct AlsIn {
+    const double* zs;
+    const int* off_tab;
+    const unsigned short* dig_tab;
+    double weight, normz2, normz, tol;
+    int normalize_on_break;
+    double* mode_out;  // [2][kMaxZModes] shared scratch of the renormalisation
+};
+
+// Rank-1 ALS sweeps of tensorly's parafac for an NM-way Z (NM >= 3), starting from the factors in f (norms^2 in
+// nrm2_in, weight in in.weight).  One barrier per mode update and one per renormalisation:
+//   * a warp per row a of the mode-k unfolding: factor[a] = weight * <Zk(a, :), prod of the other factors> / gram,
+//     columns striding over the lanes, offsets and other-mode indices from the tables;
+//   * lane 0 of the warp finishes the row and keeps ||factor||^2 and <mttkrp, factor> partials, which meet in
+//     one block-wide sum;
+//   * cp_normalize: warp m rescales factor m and takes its new squared norm.
+// NM and the mode being updated are compile-time constants, so every per-mode quantity is a register.
+// Returns the number of sweeps.
+template <int NM>
+__device__ __forceinline__ int als_sweeps(const Rank1Task& T, const Facs& f, const double* nrm2_in, const AlsIn& in, Grp& cta) {
+    constexpr int DG = 4 * ((NM - 1 + 3) / 4);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* fp[NM];
+    int dims[NM], ik[NM], mk[NM], tb[NM];
+    double nrm2[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        fp[m] = f[m];
+        dims[m] = T.dims[m];
+        nrm2[m] = nrm2_in[m];
+    }
+    ik[NM - 1] = 1;
+#pragma unroll
+    for (int m = NM - 2; m >= 0; --m) ik[m] = ik[m + 1] * dims[m + 1];
+    tb[0] = 0;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        mk[m] = T.p / dims[m];
+        if (m + 1 < NM) tb[m + 1] = tb[m] + mk[m];
+    }
+    double weight = in.weight;
+    double err_prev = 0.0;
+    int sweeps = 0;
+    for (int it = 0; it < 100; ++it) {
+        ++sweeps;
+        double iprod = 0.0;
+#pragma unroll
+        for (int k = 0; k < NM; ++k) {
+            double gram = weight * weight;
+#pragma unroll
+            for (int m = 0; m < NM; ++m)
+                if (m != k) gram *= nrm2[m];
+            double s1 = 0.0, s2 = 0.0;
+            const long long c0 = cta.dbg != nullptr ? clock64() : 0;
+            const int* offk = in.off_tab + tb[k];
+            const unsigned short* digk = in.dig_tab + (size_t)tb[k] * DG;
+            for (int a = wid; a < dims[k]; a += NWARP) {
+                const double* zrow = in.zs + a * ik[k];
+                double acc = 0.0;
+#pragma unroll 4
+                for (int j = lane; j < mk[k]; j += 32) {
+                    unsigned short dg[DG];
+                    if (DG == 4) {
+                        const uint2 w = *reinterpret_cast<const uint2*>(digk + (size_t)j * DG);
+                        dg[0] = (unsigned short)(w.x & 0xffffu);
+                        dg[1] = (unsigned short)(w.x >> 16);
+                        dg[2] = (unsigned short)(w.y & 0xffffu);
+                        dg[3] = (unsigned short)(w.y >> 16);
+                    } else {
+                        const uint4 w = *reinterpret_cast<const uint4*>(digk + (size_t)j * DG);
+                        const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            dg[2 * q] = (unsigned short)(ww[q] & 0xffffu);
+                            dg[2 * q + 1] = (unsigned short)(ww[q] >> 16);
+                        }
+                    }
+                    double pr = 1.0;
+#pragma unroll
+                    for (int m = 0; m < NM; ++m) {
+                        if (m == k) continue;
+                        const int slot = m < k ? m : m - 1;
+                        pr *= fp[m][dg[slot]];
+                    }
+                    acc = fma(zrow[offk[j]], pr, acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    const double mt_i = acc * weight;
+                    const double fi = mt_i / gram;
+                    fp[k][a] = fi;
+                    s1 = fma(fi, fi, s1);
+                    s2 = fma(mt_i, fi, s2);  // <mttkrp, factor>, wanted for the last mode only
+                }
+            }
+            cta.tick(8, c0);
+            const long long c1 = cta.dbg != nullptr ? clock64() : 0;
+            bsum2_lane0(s1, s2, cta);
+            cta.tick(9, c1);
+            nrm2[k] = s1;
+            if (k == NM - 1) iprod = s2;
+        }
+        const long long c2 = cta.dbg != nullptr ? clock64() : 0;
+        double fn2 = weight * weight;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) fn2 *= nrm2[m];
+        const double err = sqrt(fabs(in.normz2 + fn2 - 2.0 * iprod)) / in.normz;
+        const bool stop = it >= 1 && fabs(err_prev - err) < in.tol;
+        err_prev = err;
+        if (stop && !in.normalize_on_break) break;
+        // cp_normalize: weights into factor 0, then every column norm back into the weights
+        const double w_in = weight;
+        double sc[NM];
+        weight = 1.0;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            sc[m] = sqrt(nrm2[m]) * (m == 0 ? fabs(w_in) : 1.0);
+            weight *= sc[m];
+        }
+        double* mo = in.mode_out + (it & 1) * kMaxZModes;  // two alternating buffers: one barrier per renormalisation
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            if (wid == m) {
+                const double dv = sc[m] == 0.0 ? 1.0 : sc[m];
+                double q = 0.0;
+                for (int i = lane; i < dims[m]; i += 32) {
+                    const double v = (m == 0 ? fp[m][i] * w_in : fp[m][i]) / dv;
+                    fp[m][i] = v;
+                    q = fma(v, v, q);
+                }
+                q = warp_sum(q);
+                if (lane == 0) mo[m] = q;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < NM; ++m) nrm2[m] = mo[m];
+        cta.tick(10, c2);
+        if (stop) break;
+    }
+    return sweeps;
 }
 
 __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int normalize_on_break, double* ws) {
-    __shared__ double red[4 * NWARP];
-    __shared__ int ired[2 * NWARP];
-    Blk blk{red, ired, 0};
+    __shared__ double red[(kMaxZModes + 1) * 4 * NWARP];
+    __shared__ int ired[(kMaxZModes + 1) * 2 * NWARP];
+    __shared__ double mode_out[2 * kMaxZModes];  // per mode: ||f||^2 of the start, sigma
+    Grp cta{(int)threadIdx.x, NTH, 0, red, ired, 0, T.stamps};
+    if (T.stamps != nullptr && threadIdx.x == 0)
+        for (int i = 8; i < 16; ++i) T.stamps[i] = 0;
     const int p = T.p;
     const int nm = T.nmodes;
 #define TPLS_STAMP(i) \
     if (T.stamps != nullptr && threadIdx.x == 0) T.stamps[i] = clock64()
 
-    // workspace carve-up (doubles); see rank1_workspace_doubles
     int sumd = 0, maxd = 0;
     for (int m = 0; m < nm; ++m) {
         sumd += T.dims[m];
         maxd = max(maxd, T.dims[m]);
     }
-    const int n4max = up4(T.nmax);
-    const size_t n2 = (size_t)n4max * n4max;
-    double* zs = ws;             // Z (nm == 2: row-padded d0 x up4(d1))
-    double* mt = zs + T.zs_len;  // unfolding copy / Z^T padded / Khatri-Rao vector
-    double* G = mt + T.mt_len;
-    double* A = G + n2;
-    double* B = A + n2;
-    double* fac = B + n2;
-    double* tmp = fac + up4(sumd);
-    double* tmp2 = tmp + up4(max(maxd, T.nmax));
-    Facs f;
-    f.base = fac;
-    {
-        int off = 0;
-        for (int m = 0; m < kMaxZModes; ++m) {
-            f.off[m] = off;
-            if (m < nm) off += T.dims[m];
-        }
-    }
 
     TPLS_STAMP(0);
     if (nm == 1) {
+        double* zs = ws;
         double s = 0.0;
         for (int i = threadIdx.x; i < p; i += NTH) {
             double z = T.z[i];
@@ -342,7 +571,7 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
             zs[i] = z;
             s = fma(z, z, s);
         }
-        const double normz = sqrt(bsum(s, blk));
+        const double normz = sqrt(bsum(s, cta));
         for (int i = threadIdx.x; i < T.pitch; i += NTH) {
             const double w = i < p ? zs[i] / normz : 0.0;
             if (i < p) T.w[0][i] = w;
@@ -352,17 +581,32 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         return;
     }
 
+    // workspace carve-up (doubles); see rank1_workspace_doubles
+    double* zs = ws;                 // Z (nm == 2: row-padded d0 x ldp(d1))
+    double* fac = zs + T.zs_len;     // the factor vectors, back to back
+    double* rest = fac + up4(sumd);  // nm == 2: Z^T, Gram, squaring buffers, vector; nm >= 3: per-mode areas, tables
+    Facs f;
+    f.base = fac;
+    {
+        int off = 0;
+        for (int m = 0; m < kMaxZModes; ++m) {
+            f.off[m] = off;
+            if (m < nm) off += T.dims[m];
+        }
+    }
+
     // ---- load Z (with the observed-count rescaling of missingvals.py:18 when masked) ----
     const int d0 = T.dims[0], d1 = nm == 2 ? T.dims[1] : 0;
-    const int ld0 = up4(d0), ld1 = up4(d1);
+    const int ld0 = ldp(d0), ld1 = ldp(d1);
+    double* mt2 = rest;  // nm == 2: padded Z^T
     double s = 0.0;
     if (nm == 2) {
-        // padded row-major Z in zs and padded Z^T in mt
-        if (ld1 != d1)
+        // padded row-major Z in zs and padded Z^T in mt2 (the pads up to a multiple of four are read as zeros)
+        if (up4(d1) != d1)
             for (int i = threadIdx.x; i < d0 * ld1; i += NTH) zs[i] = 0.0;
-        if (ld0 != d0)
-            for (int i = threadIdx.x; i < d1 * ld0; i += NTH) mt[i] = 0.0;
-        if (ld1 != d1 || ld0 != d0) __syncthreads();
+        if (up4(d0) != d0)
+            for (int i = threadIdx.x; i < d1 * ld0; i += NTH) mt2[i] = 0.0;
+        if (up4(d1) != d1 || up4(d0) != d0) __syncthreads();
     }
     for (int i = threadIdx.x; i < p; i += NTH) {
         double z = T.z[i];  // plain load: the covariance loop rewrites Z between calls
@@ -374,16 +618,17 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         if (nm == 2) {
             const int a = i / d1, j = i - a * d1;
             zs[(size_t)a * ld1 + j] = z;
-            mt[(size_t)j * ld0 + a] = z;
+            mt2[(size_t)j * ld0 + a] = z;
         } else {
             zs[i] = z;
         }
     }
-    const double normz2 = bsum(s, blk);
+    const double normz2 = bsum(s, cta);
     const double normz = sqrt(normz2);
 
     TPLS_STAMP(1);
     int sweeps = 0;
+    const unsigned short* dig0 = nullptr;  // nm >= 3: per column of the mode-0 unfolding, the indices of modes 1..
     if (nm == 2) {
         // ---- matrix Z: the rank-1 CP is the leading singular pair ----
         // tensorly starts ALS from the exact SVD, which is already the fixed point: its two sweeps leave
@@ -392,108 +637,91 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         // side, the sign rule on f1, then one power step each way (= one ALS sweep) as a polish.
         const int ks = d0 <= d1 ? 0 : 1;
         const int n = T.dims[ks], no = T.dims[1 - ks];
+        const int ldg = ldp(n);
+        const size_t n2 = (size_t)up4(n) * ldg;
+        double* G = mt2 + T.mt_len;
+        double* A = G + n2;
+        double* B = A + n2;
+        double* tmp = B + n2;
         // rows of Mt are the columns of the mode-ks unfolding: Z^T for ks == 0, Z for ks == 1
-        const double* Mt = ks == 0 ? mt : zs;
-        syrk_fast(G, Mt, no, up4(n), 1.0);
-        lead_eig(G, A, B, f[ks], tmp, n, blk, /*polish=*/1, /*want_lambda=*/false);
+        const double* Mt = ks == 0 ? mt2 : zs;
+        syrk_tri<false>(G, ldg, Mt, ks == 0 ? ld0 : ld1, no, up4(n), 1.0, cta);
+        lead_eig(G, A, B, f[ks], tmp, n, ldg, cta, /*polish=*/1, /*want_lambda=*/false);
         TPLS_STAMP(2);
         if (ks == 0) {
-            matvec8(tmp, mt, ld0, f[0], d1, d0);
-            normalize_into(f[1], tmp, d1, blk);
+            matvec8(tmp, mt2, ld0, f[0], d1, d0, cta);
+            normalize_into(f[1], tmp, d1, cta);
         }
-        flip_to_positive_peak(f[1], d1, blk);
-        matvec8(tmp, zs, ld1, f[1], d0, d1);
-        normalize_into(f[0], tmp, d0, blk);
-        matvec8(tmp, mt, ld0, f[0], d1, d0);
-        normalize_into(f[1], tmp, d1, blk);
+        flip_to_positive_peak(f[1], d1, cta);
+        matvec8(tmp, zs, ld1, f[1], d0, d1, cta);
+        normalize_into(f[0], tmp, d0, cta);
+        matvec8(tmp, mt2, ld0, f[0], d1, d0, cta);
+        normalize_into(f[1], tmp, d1, cta);
         sweeps = 2;
         TPLS_STAMP(3);
     } else {
-        // ---- HOSVD start ----
-        double weight = 1.0;
-        for (int k = 0; k < nm; ++k) {
-            const Geo g = mode_geo(T, k);
-            double lam;
-            if (g.dk <= g.mk) {
-                const int n4 = up4(g.dk);
-                for (int i = threadIdx.x; i < g.mk * n4; i += NTH) {
-                    const int j = i / n4, a = i - j * n4;
-                    mt[i] = a < g.dk ? zs[unf_index(g, a, j)] : 0.0;
+        // ---- HOSVD start: the modes are independent, one slice of the CTA each, concurrently ----
+        const int gsz = max(32, (NTH / nm) & ~31);
+        const int my_mode = threadIdx.x / gsz;
+        {
+            int woff = 0;
+            for (int k = 0; k < nm; ++k) {
+                const Geo geo = mode_geo(T, k);
+                if (k == my_mode) {
+                    Grp g{(int)threadIdx.x - k * gsz, gsz, 1 + k, red + (1 + k) * 4 * NWARP, ired + (1 + k) * 2 * NWARP, 0,
+                          k == 0 ? T.stamps : nullptr};
+                    const double sigma = hosvd_mode(zs, geo, f[k], rest + woff, g, k == 0);
+                    const double n2k = vec_dot(f[k], f[k], geo.dk, g);
+                    if (g.tid == 0) {
+                        mode_out[2 * k] = n2k;
+                        mode_out[2 * k + 1] = sigma;
+                    }
                 }
-                __syncthreads();
-                syrk_fast(G, mt, g.mk, n4, 1.0);
-                lam = lead_eig(G, A, B, f[k], tmp, g.dk, blk, 2, true);
-                if (k == 0) weight = sqrt(lam);
-            } else {
-                const int n4 = up4(g.mk);
-                for (int i = threadIdx.x; i < g.dk * n4; i += NTH) {
-                    const int a = i / n4, j = i - a * n4;
-                    mt[i] = j < g.mk ? zs[unf_index(g, a, j)] : 0.0;
-                }
-                __syncthreads();
-                syrk_fast(G, mt, g.dk, n4, 1.0);
-                lead_eig(G, A, B, tmp2, tmp, g.mk, blk, 2, false);
-                unf_matvec(f[k], zs, g, tmp2);
-                const double sigma = sqrt(vec_dot(f[k], f[k], g.dk, blk));
-                vec_div(f[k], sigma, g.dk);
-                if (k == 0) weight = sigma;
+                woff += mode_ws(geo.dk, geo.mk).total;
             }
-            flip_to_positive_peak(f[k], g.dk, blk);
         }
+        __syncthreads();
         TPLS_STAMP(2);
+        double weight = mode_out[1];
+        double nrm2[kMaxZModes];
+        for (int m = 0; m < kMaxZModes; ++m) nrm2[m] = m < nm ? mode_out[2 * m] : 1.0;
+
+        // ---- index tables for the sweeps (the per-mode areas are free again): for every mode k and every
+        //      column j of its unfolding, the flat offset of Zk(0, j) and the indices of the other modes
+        //      (16 bits each, padded to 4 or 8 per column so that one 64/128-bit load fetches them) ----
+        int* off_tab = reinterpret_cast<int*>(rest);
+        unsigned short* dig_tab = reinterpret_cast<unsigned short*>(off_tab + up4(T.tab_cols));
+        const int DG = 4 * ((nm - 1 + 3) / 4);
+        dig0 = dig_tab;
+        {
+            int tbase = 0;
+            for (int k = 0; k < nm; ++k) {
+                const Geo geo = mode_geo(T, k);
+                for (int j = threadIdx.x; j < geo.mk; j += NTH) {
+                    off_tab[tbase + j] = unf_index(geo, 0, j);
+                    int rem = j, slot = nm - 2;
+                    for (int m = nm - 1; m >= 0; --m) {
+                        if (m == k) continue;
+                        const int d = T.dims[m];
+                        dig_tab[(size_t)(tbase + j) * DG + slot] = (unsigned short)(rem % d);
+                        rem /= d;
+                        --slot;
+                    }
+                }
+                tbase += geo.mk;
+            }
+        }
+        __syncthreads();
         TPLS_STAMP(3);
 
-        // ---- ALS sweeps (tensorly parafac, rank 1) ----
-        double nrm2[kMaxZModes];
-        for (int m = 0; m < nm; ++m) nrm2[m] = vec_dot(f[m], f[m], T.dims[m], blk);
-        double err_prev = 0.0;
-        double* kr = mt;
-        for (int it = 0; it < 100; ++it) {
-            ++sweeps;
-            double iprod = 0.0;
-            for (int k = 0; k < nm; ++k) {
-                const int dk = T.dims[k];
-                const Geo g = mode_geo(T, k);
-                other_modes_product(kr, T, k, f, g.mk);
-                unf_matvec(tmp, zs, g, kr);
-                double gram = weight * weight;
-                for (int m = 0; m < nm; ++m)
-                    if (m != k) gram *= nrm2[m];
-                // factor = (weight * Z x_others f) / gram; iprod = <mttkrp, factor> (last mode only)
-                double s1 = 0.0, s2 = 0.0;
-                for (int i = threadIdx.x; i < dk; i += NTH) {
-                    const double mt_i = tmp[i] * weight;
-                    const double fi = mt_i / gram;
-                    f[k][i] = fi;
-                    s1 = fma(fi, fi, s1);
-                    s2 = fma(mt_i, fi, s2);
-                }
-                bsum2(s1, s2, blk);
-                nrm2[k] = s1;
-                if (k == nm - 1) iprod = s2;
-            }
-            double fn2 = weight * weight;
-            for (int m = 0; m < nm; ++m) fn2 *= nrm2[m];
-            const double err = sqrt(fabs(normz2 + fn2 - 2.0 * iprod)) / normz;
-            const bool stop = it >= 1 && fabs(err_prev - err) < tol;
-            err_prev = err;
-            if (stop && !normalize_on_break) break;
-            // cp_normalize: weights into factor 0, then every column norm back into the weights
-            const double w_in = weight;
-            weight = 1.0;
-            for (int m = 0; m < nm; ++m) {
-                const double sc = sqrt(nrm2[m]) * (m == 0 ? fabs(w_in) : 1.0);
-                const double dv = sc == 0.0 ? 1.0 : sc;
-                double s1 = 0.0;
-                for (int i = threadIdx.x; i < T.dims[m]; i += NTH) {
-                    const double v = (m == 0 ? f[m][i] * w_in : f[m][i]) / dv;
-                    f[m][i] = v;
-                    s1 = fma(v, v, s1);
-                }
-                weight *= sc;
-                nrm2[m] = bsum(s1, blk);
-            }
-            if (stop) break;
+        // ---- ALS sweeps (tensorly parafac, rank 1), mode count known at compile time ----
+        AlsIn in{zs, off_tab, dig_tab, weight, normz2, normz, tol, normalize_on_break, mode_out};
+        switch (nm) {
+            case 3: sweeps = als_sweeps<3>(T, f, nrm2, in, cta); break;
+            case 4: sweeps = als_sweeps<4>(T, f, nrm2, in, cta); break;
+            case 5: sweeps = als_sweeps<5>(T, f, nrm2, in, cta); break;
+            case 6: sweeps = als_sweeps<6>(T, f, nrm2, in, cta); break;
+            default: sweeps = als_sweeps<7>(T, f, nrm2, in, cta); break;
         }
     }
 
@@ -501,21 +729,19 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
     // ---- publish ----
     for (int m = 0; m < nm; ++m)
         for (int i = threadIdx.x; i < T.dims[m]; i += NTH) T.w[m][i] = f[m][i];
+    const int mk0 = p / d0;
     for (int i = threadIdx.x; i < T.pitch; i += NTH) {
         double pr = 0.0;
-        if (i < p && nm == 2) {
-            const int a = i / d1;
-            pr = f[0][a] * f[1][i - a * d1];
-        } else if (i < p) {
-            int rem = i;
+        if (i < p) {
             // kron(w_0, w_1, ...) built the way numpy.kron nests it: ((w0 * w1) * w2) ...
-            int idx[kMaxZModes];
-            for (int m = nm - 1; m >= 0; --m) {
-                idx[m] = rem % T.dims[m];
-                rem /= T.dims[m];
+            const int a = i / mk0, j = i - a * mk0;
+            pr = f[0][a];
+            if (nm == 2) {
+                pr *= f[1][j];
+            } else {
+                const unsigned short* dg = dig0 + (size_t)j * (4 * ((nm - 1 + 3) / 4));
+                for (int m = 1; m < nm; ++m) pr *= f[m][dg[m - 1]];
             }
-            pr = f[0][idx[0]];
-            for (int m = 1; m < nm; ++m) pr *= f[m][idx[m]];
         }
         T.wkron[i] = pr;
     }
@@ -541,7 +767,7 @@ __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid
     extern __shared__ __align__(16) double dyn[];
     __shared__ double q_last[8], q_new[8], r_acc[8], lred[4 * NWARP];
     __shared__ int lired[2 * NWARP];
-    Blk blk{lred, lired, 0};
+    Grp blk{(int)threadIdx.x, NTH, 0, lred, lired, 0, nullptr};
     const int M = a.m, L = a.n_tasks;
     if (threadIdx.x < 8) q_last[threadIdx.x] = threadIdx.x == 0 ? 1.0 : 0.0;  // u_0 = Y[:, 0] = Y e_0 (tpls.py:78)
     __syncthreads();
@@ -622,7 +848,8 @@ cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_sm
     return cudaGetLastError();
 }
 
-size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out) {
+size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out,
+                               int* tab_cols_out) {
     long long p = 1;
     int sumd = 0, maxd = 0;
     for (int m = 0; m < nmodes; ++m) {
@@ -630,27 +857,33 @@ size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* 
         sumd += dims[m];
         maxd = std::max(maxd, dims[m]);
     }
-    long long nmax = 1, zs_len = p, mt_len = p;
+    long long nmax = 1, zs_len = (p + 3) & ~3ll, mt_len = 0, rest = 0, tab_cols = 0;
     if (nmodes == 2) {
+        // [Z padded | factors | Z^T padded | Gram, two squaring buffers | vector]
         nmax = std::min(dims[0], dims[1]);
-        zs_len = (long long)dims[0] * up4(dims[1]);
-        mt_len = (long long)dims[1] * up4(dims[0]);
+        zs_len = ((long long)dims[0] * ldp(dims[1]) + 3) & ~3ll;
+        mt_len = ((long long)dims[1] * ldp(dims[0]) + 3) & ~3ll;
+        rest = mt_len + 3ll * up4((int)nmax) * ldp((int)nmax) + up4(maxd);
     } else if (nmodes >= 3) {
-        mt_len = 0;
+        // [Z | factors | per-mode HOSVD areas, reused afterwards for the index tables]
+        long long areas = 0;
         for (int m = 0; m < nmodes; ++m) {
             const long long dk = dims[m], mk = p / dims[m];
             nmax = std::max(nmax, std::min(dk, mk));
-            mt_len = std::max(mt_len, dk <= mk ? mk * up4((int)dk) : dk * up4((int)mk));
+            areas += mode_ws((int)dk, (int)mk).total;
+            tab_cols += mk;
         }
-        mt_len = std::max(mt_len, p);
+        const long long tc4 = (tab_cols + 3) & ~3ll;
+        // ints of the offset table + shorts of the digit table, rounded up to whole doubles
+        const long long tables = (tc4 * 4 + tc4 * 4 * ((nmodes - 1 + 3) / 4) * 2 + 7) / 8;
+        rest = std::max(areas, tables);
+        mt_len = rest;
     }
-    zs_len = (zs_len + 3) & ~3ll;
-    mt_len = (mt_len + 3) & ~3ll;
     if (nmax_out) *nmax_out = (int)nmax;
     if (zs_len_out) *zs_len_out = (int)zs_len;
     if (mt_len_out) *mt_len_out = (int)mt_len;
-    const long long n4 = up4((int)nmax);
-    return (size_t)(zs_len + mt_len + 3 * n4 * n4 + up4(sumd) + 2 * up4((int)std::max<long long>(maxd, nmax)) + 16);
+    if (tab_cols_out) *tab_cols_out = (int)tab_cols;
+    return (size_t)(zs_len + up4(sumd) + rest + 16);
 }
 
 cudaError_t launch_rank1(const Rank1Args& a, size_t smem_bytes, cudaStream_t s) {

@@ -28,8 +28,9 @@ struct Rank1Task {
     int use_smem;
     int nmax;               // largest Gram order needed
     int zs_len, mt_len;     // workspace segment lengths (doubles), from rank1_workspace_doubles
+    int tab_cols;           // >= 3 modes: sum over the modes of the unfolding widths (index-table length)
     int* sweeps;            // out (optional): ALS sweeps taken
-    long long* stamps;      // out (optional, diagnostics): clock64 at phase boundaries [8]
+    long long* stamps;      // out (optional, diagnostics): clock64 at phase boundaries [0..7], cycle accumulators [8..15]
 };
 
 struct Rank1Args {
@@ -63,7 +64,8 @@ struct CovLoopArgs {
 cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_smem, cudaStream_t s);
 
 // doubles of workspace a task needs, and the Gram order it implies
-size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out);
+size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out,
+                               int* tab_cols_out);
 cudaError_t launch_rank1(const Rank1Args& a, size_t smem_bytes, cudaStream_t s);
 
 }  // namespace tpls

@@ -16,8 +16,11 @@ def main():
     eng = get_engine(0)
     lib = eng.lib
     out = []
-    for n, p, dt in [(250_000, 4096, torch.float32), (125_000, 4096, torch.float64), (1_000_000, 512, torch.float32),
-                     (2_000_000, 24, torch.float64), (400_000, 2048, torch.float32)]:
+    shapes = [(250_000, 4096, torch.float32), (125_000, 4096, torch.float64), (1_000_000, 512, torch.float32),
+              (2_000_000, 24, torch.float64), (400_000, 2048, torch.float32)]
+    if "--only-rank1" in sys.argv:
+        shapes = []
+    for n, p, dt in shapes:
         code = 0 if dt == torch.float32 else 1
         X = torch.randn(n, p, dtype=dt, device="cuda")
         u = torch.randn(n, dtype=torch.float64, device="cuda")
@@ -51,20 +54,28 @@ def main():
             out.append(dict(op=name, n=n, p=p, dtype=str(dt), ms=m, gbs=mult * gb / m * 1e3))
         del X, Y
         torch.cuda.empty_cache()
-    for dims in [(64, 64), (32, 16, 8), (64, 32), (24,), (38, 65)]:
+    torch.manual_seed(0)
+    for dims, kind in [((64, 64), "easy"), ((32, 16, 8), "easy"), ((64, 32), "easy"), ((24,), "easy"), ((38, 65), "easy"),
+                       ((64, 64), "hard"), ((32, 16, 8), "hard"), ((64, 32), "hard"), ((16, 8, 6, 4), "hard")]:
         Z = torch.randn(*dims, dtype=torch.float64, device="cuda")
-        v = [torch.randn(d, dtype=torch.float64, device="cuda") for d in dims]
-        if len(dims) == 2:
-            Z += 4 * torch.outer(v[0], v[1])
-        if len(dims) == 3:
-            Z += 4 * torch.einsum("i,j,k->ijk", *v)
+        if kind == "easy":      # one dominant rank-1 term: large spectral gap, few squarings
+            v = [torch.randn(d, dtype=torch.float64, device="cuda") for d in dims]
+            if len(dims) == 2:
+                Z += 4 * torch.outer(v[0], v[1])
+            if len(dims) == 3:
+                Z += 4 * torch.einsum("i,j,k->ijk", *v)
+        else:                   # twelve comparable rank-1 terms like the covariance of a rank-12 CP data set
+            letters = "ijkl"[:len(dims)]
+            for r in range(12):
+                v = [torch.randn(d, dtype=torch.float64, device="cuda") for d in dims]
+                Z += (3.0 - 0.1 * r) * torch.einsum(",".join(letters) + "->" + letters, *v)
         w = torch.zeros(sum(dims), dtype=torch.float64, device="cuda")
         wk = torch.zeros(int(np.prod(dims)), dtype=torch.float64, device="cuda")
         sw = C.c_int(0)
         ms = C.c_float(0)
         eng._ck(lib.tpls_op_rank1(eng.h, Z.data_ptr(), len(dims), (C.c_int * len(dims))(*dims), 1e-8, 0, w.data_ptr(),
                                   wk.data_ptr(), C.byref(sw), C.byref(ms), 20))
-        out.append(dict(op="rank1", dims=dims, sweeps=sw.value, us=ms.value * 1e3))
+        out.append(dict(op="rank1", dims=dims, kind=kind, sweeps=sw.value, us=ms.value * 1e3))
     for r in out:
         print(json.dumps(r))
 
