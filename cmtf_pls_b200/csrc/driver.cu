@@ -1244,18 +1244,38 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
                 c.ctrl = h->ctrl;
                 c.trip = trip;
                 TRY(col_pass(h, TPLS_F64, false, PF_CONTRACT, c, TPLS_K_YSIDE));
+                // with the Y'Y stop test the normalisation of q and the stop decision ride on the kernel that
+                // finishes the q reduction (the exchange kernel, or the second reduction stage on one GPU)
+                const bool q_fused = gram_stop && h->pitch_y <= 32 && (fused_xchg || h->world == 1);
                 if (fused_xchg) {
                     XchgArgs xa{};
                     xa.n_sets = 1;
                     xa.sets[0] = XchgSet{h->zpart_y, h->gy.grid_x, h->pitch_y, h->pitch_y, 0};
                     xa.out = A + h->off_q;
                     xa.count = h->pitch_y;
+                    if (q_fused) {
+                        xa.do_qstop = 1;
+                        xa.q_m = h->m;
+                        xa.q_pitch = h->pitch_y;
+                        xa.qcol = h->Q + (size_t)a * h->m;
+                        xa.qvec = h->qvec;
+                        xa.gram = A + h->off_gram_y;
+                        xa.q_prev = h->q_prev;
+                        xa.ctrl = h->ctrl;
+                        xa.trip = trip;
+                        xa.tol = tol;
+                    }
                     TRY(xchg_launch(h, xa));
+                } else if (q_fused) {
+                    ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+                    CK(launch_reduce_q_stop(h->zpart_y, h->gy.grid_x, h->pitch_y, A + h->off_q, h->m, h->pitch_y,
+                                            h->Q + (size_t)a * h->m, h->qvec, A + h->off_gram_y, h->q_prev, h->ctrl, trip, tol, st));
+                    h->stats.kernel_launches++;
                 } else {
                     TRY(reduce_cols(h, h->zpart_y, A + h->off_q, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
                     TRY(allreduce(h, A + h->off_q, h->pitch_y));
                 }
-                {
+                if (!q_fused) {
                     ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
                     if (gram_stop)
                         CK(launch_normalize_q_stop(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec,

@@ -68,24 +68,46 @@ __global__ void normalize_q_stop_kernel(const double* qraw, int m, int pitch, do
                                         const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol) {
     if (trip_is_dead(ctrl, trip)) return;
     if (threadIdx.x != 0) return;
-    double q[8], dq[8];
-    double nrm = 0.0;
-    for (int i = 0; i < m; ++i) nrm = fma(qraw[i], qraw[i], nrm);
-    nrm = sqrt(nrm);
-    for (int i = 0; i < m; ++i) {
-        q[i] = qraw[i] / nrm;
-        dq[i] = q_prev[i] - q[i];
-        qcol[i] = q[i];
-        q_prev[i] = q[i];
+    normalize_q_stop_body(qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
+}
+
+// 32 columns x 8 part-groups, the fold of reduce_cols_kernel (passes.cu) for one 32-column chunk
+__global__ void __launch_bounds__(256) reduce_q_stop_kernel(const double* part, int n_parts, int stride, double* qraw, int m,
+                                                            int pitch, double* qcol, double* qvec, const double* gram,
+                                                            double* q_prev, Ctrl* ctrl, int trip, double tol) {
+    if (trip_is_dead(ctrl, trip)) return;
+    __shared__ double fold[8][33];
+    const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    if (c < pitch) {
+        int b = q;
+        for (; b + 24 < n_parts; b += 32) {
+            t0 += part[(size_t)(b + 0) * stride + c];
+            t1 += part[(size_t)(b + 8) * stride + c];
+            t2 += part[(size_t)(b + 16) * stride + c];
+            t3 += part[(size_t)(b + 24) * stride + c];
+        }
+        for (; b < n_parts; b += 8) t0 += part[(size_t)b * stride + c];
     }
-    for (int i = 0; i < pitch; ++i) qvec[i] = i < m ? q[i] : 0.0;
-    double d2 = 0.0;
-    for (int i = 0; i < m; ++i)
-        for (int j = 0; j < m; ++j) d2 = fma(dq[i] * gram[i * m + j], dq[j], d2);
-    ctrl->trips_taken = trip + 1;
-    ctrl->last_d2 = d2;
-    // trip 0 compares against +inf in the reference (tpls.py:77) and can never stop
-    if (trip >= 1 && sqrt(fabs(d2)) < tol) ctrl->done_trip = trip;
+    fold[q][c] = (t0 + t1) + (t2 + t3);
+    __syncthreads();
+    if (q == 0 && c < pitch) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += fold[k][c];
+        fold[0][c] = t;
+        qraw[c] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) normalize_q_stop_body(fold[0], m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
+}
+
+cudaError_t launch_reduce_q_stop(const double* part, int n_parts, int stride, double* qraw, int m, int pitch, double* qcol,
+                                 double* qvec, const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol,
+                                 cudaStream_t s) {
+    if (pitch > 32 || m > 8) return cudaErrorInvalidValue;
+    reduce_q_stop_kernel<<<1, 256, 0, s>>>(part, n_parts, stride, qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_normalize_q_stop(const double* qraw, int m, int pitch, double* qcol, double* qvec, const double* gram,

@@ -24,6 +24,36 @@ cudaError_t launch_normalize_q(const double* qraw, int m, int pitch, double* qco
 cudaError_t launch_normalize_q_stop(const double* qraw, int m, int pitch, double* qcol, double* qvec, const double* gram,
                                     double* q_prev, Ctrl* ctrl, int trip, double tol, cudaStream_t s);
 
+// The q normalisation + stop test above as one device routine (thread 0 of a CTA), shared with the kernels that
+// fold it into the reduction that produces qraw (reduce_q_stop below, xchg_kernel).
+__device__ __forceinline__ void normalize_q_stop_body(const double* qraw, int m, int pitch, double* qcol, double* qvec,
+                                                      const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol) {
+    double q[8], dq[8];
+    double nrm = 0.0;
+    for (int i = 0; i < m; ++i) nrm = fma(qraw[i], qraw[i], nrm);
+    nrm = sqrt(nrm);
+    for (int i = 0; i < m; ++i) {
+        q[i] = qraw[i] / nrm;
+        dq[i] = q_prev[i] - q[i];
+        qcol[i] = q[i];
+        q_prev[i] = q[i];
+    }
+    for (int i = 0; i < pitch; ++i) qvec[i] = i < m ? q[i] : 0.0;
+    double d2 = 0.0;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) d2 = fma(dq[i] * gram[i * m + j], dq[j], d2);
+    ctrl->trips_taken = trip + 1;
+    ctrl->last_d2 = d2;
+    // trip 0 compares against +inf in the reference (tpls.py:77) and can never stop
+    if (trip >= 1 && sqrt(fabs(d2)) < tol) ctrl->done_trip = trip;
+}
+
+// Single GPU: second stage of the q = Y't reduction (same association order as reduce_cols), the normalisation
+// and the stop test in ONE launch: qraw[c] = sum_b part[b*stride + c], c < pitch (<= 32).
+cudaError_t launch_reduce_q_stop(const double* part, int n_parts, int stride, double* qraw, int m, int pitch, double* qcol,
+                                 double* qvec, const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol,
+                                 cudaStream_t s);
+
 // out[0] = sum parts[0..n)
 cudaError_t launch_sum_small(const double* parts, int n, double* out, const Ctrl* ctrl, int trip, cudaStream_t s);
 

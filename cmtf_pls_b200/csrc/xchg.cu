@@ -1,5 +1,6 @@
 // One-shot peer-memory all-reduce fused with the local second-stage reduction -- see xchg.cuh.
 #include "xchg.cuh"
+#include "small.cuh"
 
 #include <algorithm>
 
@@ -106,10 +107,16 @@ __global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgA
             }
         }
     }
+    if (a.do_qstop) {  // count <= 32: this is the only CTA and a.out is complete after the barrier
+        __syncthreads();
+        if (threadIdx.x == 0 && !trip_is_dead(a.ctrl, a.trip))
+            normalize_q_stop_body(a.out, a.q_m, a.q_pitch, a.qcol, a.qvec, a.gram, a.q_prev, a.ctrl, a.trip, a.tol);
+    }
 }
 
 cudaError_t launch_xchg(const XchgArgs& a, cudaStream_t s) {
     const int n_chunks = (a.count + 31) / 32;
+    if (a.do_qstop && (a.count > 32 || a.q_m > 8)) return cudaErrorInvalidValue;
     const int blocks = std::max(1, std::min(444, n_chunks));  // all CTAs must be co-resident: 3 per SM is safe
     xchg_kernel<<<blocks, 256, 0, s>>>(a);
     return cudaGetLastError();

@@ -49,6 +49,14 @@ struct XchgArgs {
     int trip;
     double tol;
     int do_stop;
+    // optional (count <= 32, one CTA): `out` is the raw q = Y't -- normalise it and run the stop test through
+    // dq^T (Y'Y) dq in this kernel (small.cuh normalize_q_stop_body); uses ctrl / trip / tol above
+    int do_qstop;
+    int q_m, q_pitch;
+    double* qcol;
+    double* qvec;
+    const double* gram;
+    double* q_prev;
 };
 
 cudaError_t launch_xchg(const XchgArgs& a, cudaStream_t s);
