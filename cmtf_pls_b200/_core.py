@@ -137,6 +137,8 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
     Returns a dict with T, W (list per tensor of loading matrices), U, Q, coef,
     R2X (list), R2Y, X_mean (list), Y_mean, has_miss (list), trips, stats.
     """
+    import time
+    t_host = [time.perf_counter()]
     Xs = [as_input(X, "X") for X in Xs]
     Y2 = y_as_f64_2d(Y)
     dev = _device_of(Xs + [Y2], device)
@@ -159,7 +161,9 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
     if profile:
         flags |= _engine.FIT_PROFILE
     try:
+        t_host.append(time.perf_counter())
         eng.fit(len(Xs), R, tol, max_iter, flags)
+        t_host.append(time.perf_counter())
         out = dict(
             T=eng.x_factor(0, 0, n, R),
             W=[[eng.x_factor(i, k, int(X.shape[k]), R) for k in range(1, X.ndim)] for i, X in enumerate(Xs)],
@@ -173,12 +177,33 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
             has_miss=[eng.has_missing(i) for i in range(len(Xs))],
             trips=eng.trips(R),
             stats=eng.stats(),
-            profile=eng.profile() if profile else None,
+            profile=LazyProfile(eng) if profile else None,
             device=dev,
         )
+        # host-side wall clock of the three stages of this call (ms): staging the inputs, the device fit
+        # (returns when the GPU is done), fetching the fitted state
+        t_host.append(time.perf_counter())
+        out["stats"]["host_ms"] = dict(stage=1e3 * (t_host[1] - t_host[0]), fit=1e3 * (t_host[2] - t_host[1]),
+                                       fetch=1e3 * (t_host[3] - t_host[2]))
     finally:
         eng.release_data()
     return out
+
+
+class LazyProfile:
+    """Per-class CUDA-event profile of the profiled fits since the last read (`tpls_get_profile`).  The event
+    queries (a few microseconds for each of the ~2000 launches of a fit) are made when it is read, not inside
+    ``fit``; reading it after several profiled fits on the same device gives their sums."""
+
+    def __init__(self, eng):
+        self._eng = eng
+        self._value = None
+
+    def get(self):
+        if self._value is None:
+            self._value = self._eng.profile()
+            self._eng = None
+        return self._value
 
 
 def kron_rows(loadings, R):

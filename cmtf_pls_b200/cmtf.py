@@ -49,7 +49,7 @@ class ctPLS(Mapping):
     def __getstate__(self):
         """Pickle the fitted model, not the references to the training arrays or to a process group."""
         state = dict(self.__dict__)
-        for k in ("_Xs_ref", "_Y_ref", "process_group"):
+        for k in ("_Xs_ref", "_Y_ref", "process_group", "_profile"):
             state.pop(k, None)
         return state
 
@@ -89,7 +89,7 @@ class ctPLS(Mapping):
         # the reference is silent when max_iter is exhausted (tpls.py:79-107); here it can be asked
         self.converged_ = st["trips"] < max_iter
         self.stats_ = st["stats"]
-        self.profile_ = st["profile"]
+        self._profile = st["profile"]
         self._device = st["device"]
         if verbose:
             for a, k in enumerate(self.n_iter_):
@@ -100,6 +100,13 @@ class ctPLS(Mapping):
     def Xs_miss(self):
         """Positions of missing values of the training tensors (cmtf.py:80-82), computed on demand."""
         return [X.isnan().cpu().numpy() if _core._is_torch(X) else np.isnan(X) for X in self._Xs_ref]
+
+    @property
+    def profile_(self):
+        """Per-kernel-class timings of the profiled fits (``fit(..., profile=True)``) since the last read; None
+        when the last fit was not profiled."""
+        p = getattr(self, "_profile", None)
+        return None if p is None else p.get()
 
     # ---- new data (cmtf.py:142-231) ----
     def _scores(self, Xs):

@@ -282,6 +282,8 @@ struct ProfScope {
     }
 };
 
+// Sums the launch records of every profiled fit since the last collection (event queries cost a few
+// microseconds each, so they are made when the profile is asked for, not inside the fit).
 void prof_collect(tpls_handle h) {
     h->prof_sum = tpls_profile{};
     for (auto& r : h->prof) {
@@ -473,6 +475,10 @@ int tpls_destroy(tpls_handle h) {
     cudaEventDestroy(h->ev_stop);
     for (auto& e : h->ev_trip) cudaEventDestroy(e);
     for (auto& e : h->ev_pool) cudaEventDestroy(e);
+    for (auto& r : h->prof) {  // launch records of profiled fits that were never collected
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -1010,7 +1016,6 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     h->stats.h2d_bytes = h2d;
     h->h2d_bytes = 0;
     h->profile = (flags & TPLS_FIT_PROFILE) != 0;
-    h->prof.clear();
     h->cov_alloc = (flags & TPLS_FIT_COVARIANCE) != 0 && h->m <= 8;
     TRY(alloc_fit(h, L, R));
     CK(cudaEventRecord(h->ev_start, st));
@@ -1375,7 +1380,6 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
     h->stats.fit_ms = ms;
-    prof_collect(h);
     if (h->xchg_ready) {
         int xerr = 0;
         CK(cudaMemcpy(&xerr, static_cast<char*>(h->xchg_buf) + 520, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1496,6 +1500,11 @@ int tpls_get_trips(tpls_handle h, int* out) {
 }
 
 int tpls_get_profile(tpls_handle h, tpls_profile* out) {
+    if (h && !h->prof.empty()) {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        prof_collect(h);
+    }
     if (!h) return fail(nullptr, "NULL handle");
     *out = h->prof_sum;
     return 0;

@@ -56,7 +56,7 @@ class tPLS(Mapping):
     def __getstate__(self):
         """Pickle the fitted model, not the references to the training arrays or to a process group."""
         state = dict(self.__dict__)
-        for k in ("_X_ref", "_Y_ref", "process_group"):
+        for k in ("_X_ref", "_Y_ref", "process_group", "_profile"):
             state.pop(k, None)
         return state
 
@@ -90,7 +90,7 @@ class tPLS(Mapping):
         # the reference is silent when max_iter is exhausted (tpls.py:79-107); here it can be asked
         self.converged_ = st["trips"] < max_iter
         self.stats_ = st["stats"]
-        self.profile_ = st["profile"]
+        self._profile = st["profile"]
         self._device = st["device"]
         if verbose:
             for a, k in enumerate(self.n_iter_):
@@ -104,6 +104,13 @@ class tPLS(Mapping):
         if _core._is_torch(X):
             return X.isnan().cpu().numpy()
         return np.isnan(X)
+
+    @property
+    def profile_(self):
+        """Per-kernel-class timings of the profiled fits (``fit(..., profile=True)``) since the last read; None
+        when the last fit was not profiled."""
+        p = getattr(self, "_profile", None)
+        return None if p is None else p.get()
 
     # ---- new data (tpls.py:122-186) ----
     def _scores(self, X):

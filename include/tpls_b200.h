@@ -130,7 +130,7 @@ typedef struct tpls_stats {
 int tpls_get_stats(tpls_handle h, tpls_stats* out);
 
 typedef struct tpls_profile {
-    double ms[TPLS_N_KERNEL_CLASSES];        /* summed launch durations of the last profiled fit */
+    double ms[TPLS_N_KERNEL_CLASSES];        /* summed launch durations of the profiled fits since the last call */
     int64_t launches[TPLS_N_KERNEL_CLASSES];
     double bytes[TPLS_N_KERNEL_CLASSES];     /* algorithmic bytes of X moved by those launches */
 } tpls_profile;
