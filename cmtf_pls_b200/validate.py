@@ -63,13 +63,19 @@ def _sum_over_ranks(arrays, group, device):
 
 
 def q2y_sweep(X, Y, n_components, n_splits=5, seed=0, device=None, tol=1e-8, max_iter=100, folds=None,
-              return_scores=False, algorithm="stream", fold_group=None, _fit_fold=None):
+              return_scores=False, algorithm="covariance", fold_group=None, _fit_fold=None):
     """Q2Y for 1, 2, ..., ``n_components`` components by K-fold cross-validation.
 
     ``X`` is one tensor (tPLS) or a list of coupled tensors (ctPLS); ``folds``
     optionally gives the held-out row indices of every fold explicitly.
     Returns an array of ``n_components`` values (and, with ``return_scores``,
     the cross-validated scores of every sample, shape (N, n_components)).
+
+    ``algorithm``: inner loop of the fold fits.  The default is the covariance
+    loop (one cross-covariance pass per component; same results as the
+    streaming loop to rounding, several times faster), which the library
+    replaces by the streaming loop on its own when there are more than 8
+    responses (4 with missing values); ``"stream"`` forces the latter.
 
     ``fold_group`` (a torch.distributed process group, or True for the default
     one) runs the sweep FOLD-PARALLEL (folds are independent

@@ -129,12 +129,13 @@ def main():
         if c.get("cv"):
             arg = Xs if len(Xs) > 1 else Xs[0]
             q2y_sweep(arg, Y, 2, n_splits=2)                    # warm-up
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            q2 = q2y_sweep(arg, Y, c["R"], n_splits=c["cv"], seed=0)
-            torch.cuda.synchronize()
-            line["cv_sweep"] = {"folds": c["cv"], "s_wall": time.perf_counter() - t0, "q2y": [float(v) for v in q2],
-                                "note": "one R-component fit per fold (nested components), folds as 0/1 row weights"}
+            line["cv_sweep"] = {"folds": c["cv"], "note": "one R-component fit per fold (nested components), folds as 0/1 row weights"}
+            for alg in ("stream", "covariance"):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                q2 = q2y_sweep(arg, Y, c["R"], n_splits=c["cv"], seed=0, algorithm=alg)
+                torch.cuda.synchronize()
+                line["cv_sweep"][alg] = {"s_wall": time.perf_counter() - t0, "q2y": [float(v) for v in q2]}
         if not args.no_cpu and c["cpu_rows"]:
             # the oracle port (numpy restatement of the reference's fit, incl. its dense R2 re-evaluation) on the
             # first cpu_rows rows of the same data
