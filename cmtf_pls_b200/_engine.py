@@ -197,18 +197,22 @@ class Engine:
         self._keep.clear()
 
     # ---- results ----
-    @staticmethod
-    def _host_out(rows, cols):
+    def _host_out(self, rows, cols):
         """Host array for a device result.  Large ones (the N x R score matrices) are backed by pinned memory
-        from torch's caching host allocator: the device-to-host copy then runs at DMA speed instead of through
-        the driver's bounce buffers (160 MB of scores: ~4 ms instead of ~45 ms).  The ndarray keeps the tensor
-        alive; the block returns to the cache when the array is garbage-collected."""
-        if rows * cols * 8 >= (1 << 22) and os.environ.get("TPLS_PAGEABLE_OUT", "") == "":
-            try:
-                import torch
-                return torch.empty((rows, cols), dtype=torch.float64, pin_memory=True).numpy()
-            except Exception:  # noqa: BLE001 -- no torch / pinning refused: pageable memory works too
-                pass
+        from torch's caching host allocator once this engine is seen to fit REPEATEDLY (cross-validation sweeps,
+        bootstraps, benchmarks): the device-to-host copy then runs at DMA speed instead of through the driver's
+        bounce buffers (160 MB of scores: ~4 ms instead of ~45 ms).  Pinning fresh memory costs more than that,
+        so the first fit of a process stays on pageable memory and never pays for it.  The ndarray keeps the
+        pinned tensor alive; its block returns to torch's cache when the array is garbage-collected.
+        TPLS_PAGEABLE_OUT=1 turns this off."""
+        if rows * cols * 8 >= (1 << 22):
+            self._big_fetches = getattr(self, "_big_fetches", 0) + 1
+            if self._big_fetches > 2 and os.environ.get("TPLS_PAGEABLE_OUT", "") == "":
+                try:
+                    import torch
+                    return torch.empty((rows, cols), dtype=torch.float64, pin_memory=True).numpy()
+                except Exception:  # noqa: BLE001 -- no torch / pinning refused: pageable memory works too
+                    pass
         return np.empty((rows, cols), dtype=np.float64)
 
     def x_factor(self, index, mode, rows, R):

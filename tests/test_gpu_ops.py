@@ -90,7 +90,8 @@ def test_deflate_contract(eng, n, p, dtype, masked):
 
 
 @pytest.mark.parametrize("dims", [(24,), (64, 64), (38, 65), (65, 38), (32, 16), (8, 6, 4), (32, 16, 8), (5, 4, 3, 3),
-                                  (100, 4, 3), (2, 2), (1, 7), (120, 90)])
+                                  (100, 4, 3), (2, 2), (1, 7), (120, 90), (4, 3, 3, 2, 2), (3, 3, 2, 2, 2, 2), (3, 2, 2, 2, 2, 2, 2),
+                                  (16, 8, 6, 4), (40, 33, 5)])
 def test_rank1_matches_restated_parafac(eng, dims):
     import torch
     from oracle import tpls_oracle as orc

@@ -101,6 +101,8 @@ def test_fit_leaves_inputs_untouched_and_api_surface():
     ((257, 7, 3), 2, 2, np.float32),        # row bytes not a multiple of 16 -> pitched staging
     ((130, 9, 7), 3, 2, np.float64),        # odd P in fp64 -> pitched staging
     ((64, 130, 40), 3, 2, np.float32),      # P = 5200 > one slab
+    ((60, 4, 3, 3, 2, 2), 3, 2, np.float64),    # 6-way X: 5-way covariance tensor (rank-1 ALS with 5 modes)
+    ((50, 3, 3, 2, 2, 2, 2), 2, 2, np.float64),  # 7-way X: 6-way covariance tensor (wide index records)
 ])
 def test_fit_matches_oracle_seeded(shape, M, R, dtype):
     from oracle import tpls_oracle as orc
