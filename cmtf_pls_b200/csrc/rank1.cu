@@ -318,14 +318,6 @@ __device__ __forceinline__ void flip_to_positive_peak(double* f, int n, Grp& g) 
     g.sync();
 }
 
-// the factor vectors live back to back in the workspace; offsets stay in registers so that the compiler
-// keeps seeing workspace-derived (shared-memory) addresses
-struct Facs {
-    double* base;
-    int off[kMaxZModes];
-    __device__ __forceinline__ double* operator[](int m) const { return base + off[m]; }
-};
-
 struct Geo {  // mode-k unfolding geometry
     int dk, mk, ik;
 };
@@ -416,18 +408,23 @@ struct AlsIn {
 // NM and the mode being updated are compile-time constants, so every per-mode quantity is a register.
 // Returns the number of sweeps.
 template <int NM>
-__device__ __forceinline__ int als_sweeps(const Rank1Task& T, const Facs& f, const double* nrm2_in, const AlsIn& in, Grp& cta) {
+__device__ __forceinline__ int als_sweeps(const Rank1Task& T, double* const fb, const double* nrm2_in, const AlsIn& in, Grp& cta) {
     constexpr int DG = 4 * ((NM - 1 + 3) / 4);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double* fp[NM];
+    // factor m lives at fb[fo[m] ...]: ONE base pointer derived from the workspace plus integer offsets, so that
+    // the compiler keeps seeing a shared-memory address (pointers kept in an array or a struct turn every factor
+    // access into a generic load)
+    int fo[NM];
     int dims[NM], ik[NM], mk[NM], tb[NM];
     double nrm2[NM];
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
-        fp[m] = f[m];
         dims[m] = T.dims[m];
         nrm2[m] = nrm2_in[m];
     }
+    fo[0] = 0;
+#pragma unroll
+    for (int m = 1; m < NM; ++m) fo[m] = fo[m - 1] + dims[m - 1];
     ik[NM - 1] = 1;
 #pragma unroll
     for (int m = NM - 2; m >= 0; --m) ik[m] = ik[m + 1] * dims[m + 1];
@@ -479,7 +476,7 @@ __device__ __forceinline__ int als_sweeps(const Rank1Task& T, const Facs& f, con
                     for (int m = 0; m < NM; ++m) {
                         if (m == k) continue;
                         const int slot = m < k ? m : m - 1;
-                        pr *= fp[m][dg[slot]];
+                        pr *= fb[fo[m] + dg[slot]];
                     }
                     acc = fma(zrow[offk[j]], pr, acc);
                 }
@@ -487,7 +484,7 @@ __device__ __forceinline__ int als_sweeps(const Rank1Task& T, const Facs& f, con
                 if (lane == 0) {
                     const double mt_i = acc * weight;
                     const double fi = mt_i / gram;
-                    fp[k][a] = fi;
+                    fb[fo[k] + a] = fi;
                     s1 = fma(fi, fi, s1);
                     s2 = fma(mt_i, fi, s2);  // <mttkrp, factor>, wanted for the last mode only
                 }
@@ -523,8 +520,8 @@ __device__ __forceinline__ int als_sweeps(const Rank1Task& T, const Facs& f, con
                 const double dv = sc[m] == 0.0 ? 1.0 : sc[m];
                 double q = 0.0;
                 for (int i = lane; i < dims[m]; i += 32) {
-                    const double v = (m == 0 ? fp[m][i] * w_in : fp[m][i]) / dv;
-                    fp[m][i] = v;
+                    const double v = (m == 0 ? fb[fo[m] + i] * w_in : fb[fo[m] + i]) / dv;
+                    fb[fo[m] + i] = v;
                     q = fma(v, v, q);
                 }
                 q = warp_sum(q);
@@ -585,16 +582,6 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
     double* zs = ws;                 // Z (nm == 2: row-padded d0 x ldp(d1))
     double* fac = zs + T.zs_len;     // the factor vectors, back to back
     double* rest = fac + up4(sumd);  // nm == 2: Z^T, Gram, squaring buffers, vector; nm >= 3: per-mode areas, tables
-    Facs f;
-    f.base = fac;
-    {
-        int off = 0;
-        for (int m = 0; m < kMaxZModes; ++m) {
-            f.off[m] = off;
-            if (m < nm) off += T.dims[m];
-        }
-    }
-
     // ---- load Z (with the observed-count rescaling of missingvals.py:18 when masked) ----
     const int d0 = T.dims[0], d1 = nm == 2 ? T.dims[1] : 0;
     const int ld0 = ldp(d0), ld1 = ldp(d1);
@@ -646,17 +633,19 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         // rows of Mt are the columns of the mode-ks unfolding: Z^T for ks == 0, Z for ks == 1
         const double* Mt = ks == 0 ? mt2 : zs;
         syrk_tri<false>(G, ldg, Mt, ks == 0 ? ld0 : ld1, no, up4(n), 1.0, cta);
-        lead_eig(G, A, B, f[ks], tmp, n, ldg, cta, /*polish=*/1, /*want_lambda=*/false);
+        double* const f0 = fac;        // the two factor vectors, back to back
+        double* const f1 = fac + d0;
+        lead_eig(G, A, B, ks == 0 ? f0 : f1, tmp, n, ldg, cta, /*polish=*/1, /*want_lambda=*/false);
         TPLS_STAMP(2);
         if (ks == 0) {
-            matvec8(tmp, mt2, ld0, f[0], d1, d0, cta);
-            normalize_into(f[1], tmp, d1, cta);
+            matvec8(tmp, mt2, ld0, f0, d1, d0, cta);
+            normalize_into(f1, tmp, d1, cta);
         }
-        flip_to_positive_peak(f[1], d1, cta);
-        matvec8(tmp, zs, ld1, f[1], d0, d1, cta);
-        normalize_into(f[0], tmp, d0, cta);
-        matvec8(tmp, mt2, ld0, f[0], d1, d0, cta);
-        normalize_into(f[1], tmp, d1, cta);
+        flip_to_positive_peak(f1, d1, cta);
+        matvec8(tmp, zs, ld1, f1, d0, d1, cta);
+        normalize_into(f0, tmp, d0, cta);
+        matvec8(tmp, mt2, ld0, f0, d1, d0, cta);
+        normalize_into(f1, tmp, d1, cta);
         sweeps = 2;
         TPLS_STAMP(3);
     } else {
@@ -664,20 +653,22 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         const int gsz = max(32, (NTH / nm) & ~31);
         const int my_mode = threadIdx.x / gsz;
         {
-            int woff = 0;
+            int woff = 0, foff = 0;
             for (int k = 0; k < nm; ++k) {
                 const Geo geo = mode_geo(T, k);
+                double* const fk = fac + foff;
                 if (k == my_mode) {
                     Grp g{(int)threadIdx.x - k * gsz, gsz, 1 + k, red + (1 + k) * 4 * NWARP, ired + (1 + k) * 2 * NWARP, 0,
                           k == 0 ? T.stamps : nullptr};
-                    const double sigma = hosvd_mode(zs, geo, f[k], rest + woff, g, k == 0);
-                    const double n2k = vec_dot(f[k], f[k], geo.dk, g);
+                    const double sigma = hosvd_mode(zs, geo, fk, rest + woff, g, k == 0);
+                    const double n2k = vec_dot(fk, fk, geo.dk, g);
                     if (g.tid == 0) {
                         mode_out[2 * k] = n2k;
                         mode_out[2 * k + 1] = sigma;
                     }
                 }
                 woff += mode_ws(geo.dk, geo.mk).total;
+                foff += geo.dk;
             }
         }
         __syncthreads();
@@ -717,30 +708,39 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         // ---- ALS sweeps (tensorly parafac, rank 1), mode count known at compile time ----
         AlsIn in{zs, off_tab, dig_tab, weight, normz2, normz, tol, normalize_on_break, mode_out};
         switch (nm) {
-            case 3: sweeps = als_sweeps<3>(T, f, nrm2, in, cta); break;
-            case 4: sweeps = als_sweeps<4>(T, f, nrm2, in, cta); break;
-            case 5: sweeps = als_sweeps<5>(T, f, nrm2, in, cta); break;
-            case 6: sweeps = als_sweeps<6>(T, f, nrm2, in, cta); break;
-            default: sweeps = als_sweeps<7>(T, f, nrm2, in, cta); break;
+            case 3: sweeps = als_sweeps<3>(T, fac, nrm2, in, cta); break;
+            case 4: sweeps = als_sweeps<4>(T, fac, nrm2, in, cta); break;
+            case 5: sweeps = als_sweeps<5>(T, fac, nrm2, in, cta); break;
+            case 6: sweeps = als_sweeps<6>(T, fac, nrm2, in, cta); break;
+            default: sweeps = als_sweeps<7>(T, fac, nrm2, in, cta); break;
         }
     }
 
     TPLS_STAMP(4);
     // ---- publish ----
-    for (int m = 0; m < nm; ++m)
-        for (int i = threadIdx.x; i < T.dims[m]; i += NTH) T.w[m][i] = f[m][i];
+    {
+        int fo = 0;
+        for (int m = 0; m < nm; ++m) {
+            for (int i = threadIdx.x; i < T.dims[m]; i += NTH) T.w[m][i] = fac[fo + i];
+            fo += T.dims[m];
+        }
+    }
     const int mk0 = p / d0;
     for (int i = threadIdx.x; i < T.pitch; i += NTH) {
         double pr = 0.0;
         if (i < p) {
             // kron(w_0, w_1, ...) built the way numpy.kron nests it: ((w0 * w1) * w2) ...
             const int a = i / mk0, j = i - a * mk0;
-            pr = f[0][a];
+            pr = fac[a];
             if (nm == 2) {
-                pr *= f[1][j];
+                pr *= fac[d0 + j];
             } else {
                 const unsigned short* dg = dig0 + (size_t)j * (4 * ((nm - 1 + 3) / 4));
-                for (int m = 1; m < nm; ++m) pr *= f[m][dg[m - 1]];
+                int fo = d0;
+                for (int m = 1; m < nm; ++m) {
+                    pr *= fac[fo + dg[m - 1]];
+                    fo += T.dims[m];
+                }
             }
         }
         T.wkron[i] = pr;
