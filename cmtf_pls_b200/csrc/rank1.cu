@@ -391,7 +391,7 @@ __device__ __forceinline__ double hosvd_mode(const double* zs, const Geo& geo, d
 
 struct AlsIn {
     const double* zs;
-    const int* off_tab;
+    const double* zc;  // row-major copies of the unfoldings of modes 1.. (mode 0 is Z itself), up4(p) doubles each
     const unsigned short* dig_tab;
     double weight, normz2, normz, tol;
     int normalize_on_break;
@@ -401,7 +401,8 @@ struct AlsIn {
 // Rank-1 ALS sweeps of tensorly's parafac for an NM-way Z (NM >= 3), starting from the factors in f (norms^2 in
 // nrm2_in, weight in in.weight).  One barrier per mode update and one per renormalisation:
 //   * a warp per row a of the mode-k unfolding: factor[a] = weight * <Zk(a, :), prod of the other factors> / gram,
-//     columns striding over the lanes, offsets and other-mode indices from the tables;
+//     columns striding over the lanes (every unfolding is kept row-major, so the reads are conflict-free), the
+//     other-mode indices of a column from a table;
 //   * lane 0 of the warp finishes the row and keeps ||factor||^2 and <mttkrp, factor> partials, which meet in
 //     one block-wide sum;
 //   * cp_normalize: warp m rescales factor m and takes its new squared norm.
@@ -415,7 +416,7 @@ __device__ __forceinline__ int als_sweeps(const Rank1Task& T, double* const fb, 
     // the compiler keeps seeing a shared-memory address (pointers kept in an array or a struct turn every factor
     // access into a generic load)
     int fo[NM];
-    int dims[NM], ik[NM], mk[NM], tb[NM];
+    int dims[NM], mk[NM], tb[NM];
     double nrm2[NM];
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
@@ -425,9 +426,6 @@ __device__ __forceinline__ int als_sweeps(const Rank1Task& T, double* const fb, 
     fo[0] = 0;
 #pragma unroll
     for (int m = 1; m < NM; ++m) fo[m] = fo[m - 1] + dims[m - 1];
-    ik[NM - 1] = 1;
-#pragma unroll
-    for (int m = NM - 2; m >= 0; --m) ik[m] = ik[m + 1] * dims[m + 1];
     tb[0] = 0;
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
@@ -448,10 +446,11 @@ __device__ __forceinline__ int als_sweeps(const Rank1Task& T, double* const fb, 
                 if (m != k) gram *= nrm2[m];
             double s1 = 0.0, s2 = 0.0;
             const long long c0 = cta.dbg != nullptr ? clock64() : 0;
-            const int* offk = in.off_tab + tb[k];
+            // rows of the mode-k unfolding are contiguous: consecutive lanes read consecutive doubles
+            const double* zk = k == 0 ? in.zs : in.zc + (size_t)(k - 1) * up4(T.p);
             const unsigned short* digk = in.dig_tab + (size_t)tb[k] * DG;
             for (int a = wid; a < dims[k]; a += NWARP) {
-                const double* zrow = in.zs + a * ik[k];
+                const double* zrow = zk + (size_t)a * mk[k];
                 double acc = 0.0;
 #pragma unroll 4
                 for (int j = lane; j < mk[k]; j += 32) {
@@ -478,7 +477,7 @@ __device__ __forceinline__ int als_sweeps(const Rank1Task& T, double* const fb, 
                         const int slot = m < k ? m : m - 1;
                         pr *= fb[fo[m] + dg[slot]];
                     }
-                    acc = fma(zrow[offk[j]], pr, acc);
+                    acc = fma(zrow[j], pr, acc);
                 }
                 acc = warp_sum(acc);
                 if (lane == 0) {
@@ -677,19 +676,19 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         double nrm2[kMaxZModes];
         for (int m = 0; m < kMaxZModes; ++m) nrm2[m] = m < nm ? mode_out[2 * m] : 1.0;
 
-        // ---- index tables for the sweeps (the per-mode areas are free again): for every mode k and every
-        //      column j of its unfolding, the flat offset of Zk(0, j) and the indices of the other modes
-        //      (16 bits each, padded to 4 or 8 per column so that one 64/128-bit load fetches them) ----
-        int* off_tab = reinterpret_cast<int*>(rest);
-        unsigned short* dig_tab = reinterpret_cast<unsigned short*>(off_tab + up4(T.tab_cols));
+        // ---- for the sweeps (the per-mode areas are free again): per mode k and column j of its unfolding the
+        //      indices of the other modes (16 bits each, padded to 4 or 8 per column so that one 64/128-bit load
+        //      fetches them), and a row-major copy of every unfolding but the first (Z itself) -- read column-wise
+        //      out of Z, the last mode's rows would put all lanes of a warp on two banks ----
         const int DG = 4 * ((nm - 1 + 3) / 4);
+        unsigned short* dig_tab = reinterpret_cast<unsigned short*>(rest);
+        double* zc = rest + up4((int)(((size_t)up4(T.tab_cols) * DG * 2 + 7) / 8));
         dig0 = dig_tab;
         {
             int tbase = 0;
             for (int k = 0; k < nm; ++k) {
                 const Geo geo = mode_geo(T, k);
                 for (int j = threadIdx.x; j < geo.mk; j += NTH) {
-                    off_tab[tbase + j] = unf_index(geo, 0, j);
                     int rem = j, slot = nm - 2;
                     for (int m = nm - 1; m >= 0; --m) {
                         if (m == k) continue;
@@ -699,6 +698,13 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
                         --slot;
                     }
                 }
+                if (k > 0) {
+                    double* zk = zc + (size_t)(k - 1) * up4(p);
+                    for (int i = threadIdx.x; i < p; i += NTH) {
+                        const int a = i / geo.mk, j = i - a * geo.mk;
+                        zk[i] = zs[unf_index(geo, a, j)];
+                    }
+                }
                 tbase += geo.mk;
             }
         }
@@ -706,7 +712,7 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         TPLS_STAMP(3);
 
         // ---- ALS sweeps (tensorly parafac, rank 1), mode count known at compile time ----
-        AlsIn in{zs, off_tab, dig_tab, weight, normz2, normz, tol, normalize_on_break, mode_out};
+        AlsIn in{zs, zc, dig_tab, weight, normz2, normz, tol, normalize_on_break, mode_out};
         switch (nm) {
             case 3: sweeps = als_sweeps<3>(T, fac, nrm2, in, cta); break;
             case 4: sweeps = als_sweeps<4>(T, fac, nrm2, in, cta); break;
@@ -865,7 +871,7 @@ size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* 
         mt_len = ((long long)dims[1] * ldp(dims[0]) + 3) & ~3ll;
         rest = mt_len + 3ll * up4((int)nmax) * ldp((int)nmax) + up4(maxd);
     } else if (nmodes >= 3) {
-        // [Z | factors | per-mode HOSVD areas, reused afterwards for the index tables]
+        // [Z | factors | per-mode HOSVD areas, reused afterwards for the index table and the unfolding copies]
         long long areas = 0;
         for (int m = 0; m < nmodes; ++m) {
             const long long dk = dims[m], mk = p / dims[m];
@@ -874,8 +880,10 @@ size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* 
             tab_cols += mk;
         }
         const long long tc4 = (tab_cols + 3) & ~3ll;
-        // ints of the offset table + shorts of the digit table, rounded up to whole doubles
-        const long long tables = (tc4 * 4 + tc4 * 4 * ((nmodes - 1 + 3) / 4) * 2 + 7) / 8;
+        // after the HOSVD start the areas hold the index table (4 or 8 shorts per column, rounded up to whole
+        // doubles) and the row-major copies of the unfoldings of modes 1..
+        const long long dgd = (tc4 * 4 * ((nmodes - 1 + 3) / 4) * 2 + 7) / 8;
+        const long long tables = ((dgd + 3) & ~3ll) + (long long)(nmodes - 1) * ((p + 3) & ~3ll);
         rest = std::max(areas, tables);
         mt_len = rest;
     }
