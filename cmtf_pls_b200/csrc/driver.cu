@@ -1,141 +1,13 @@
 // Host side of the C ABI (include/tpls_b200.h): device state of one fit, the
 // NIPALS driver that enqueues the passes, and NCCL all-reduces of the small
 // replicated quantities.  No CPU arithmetic on the data path.
-#include "../../include/tpls_b200.h"
+// transform / predict live in transform.cu, the single-operator entry points in ops.cu.
+#include "driver_internal.cuh"
 
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <functional>
-#include <string>
-#include <vector>
-
-#include "nccl_dl.h"
-#include "passes.cuh"
-#include "rank1.cuh"
-#include "small.cuh"
-#include "xchg.cuh"
-
-using namespace tpls;
-
-namespace {
+namespace tpls_drv {
 
 std::string g_error;
 NcclApi g_nccl;
-
-struct Tensor {
-    bool set = false;
-    int dtype = 0, elem = 4, ndim = 0;
-    long long shape[TPLS_MAX_MODES] = {0};
-    long long n = 0;
-    int p = 0, pitch = 0;
-    const void* src = nullptr;  // centred from here ...
-    void* work = nullptr;       // ... into here (may alias src)
-    void* owned = nullptr;      // library-owned staging / work allocation(s)
-    void* owned2 = nullptr;
-    bool masked = false;
-    PassGeom g{};   // column passes
-    PassGeom gr{};      // row passes
-    PassGeom gr_cnt{};  // the one counting row pass of a masked fit (needs twice the slot space)
-    PassGeom gc{};      // cross-covariance passes (covariance mode)
-    double *covpart = nullptr, *zscratch = nullptr, *sspart_cov = nullptr;
-    int cov_mr = 0;     // accumulators per column of the cross-covariance pass
-    size_t off_c = 0;   // arena offset of C [cov_mr][pitch]
-    // per-fit device buffers
-    double *zpart = nullptr, *cntpart = nullptr, *sspart = nullptr;
-    double *mean_d = nullptr, *wkron = nullptr, *tpart = nullptr, *cpart = nullptr, *r1_scratch = nullptr;
-    double* rowcnt = nullptr;   // masked: observed entries per row (filled by the first projection of a fit)
-    bool rowcnt_ready = false;
-    void* mean_native = nullptr;
-    double* W[TPLS_MAX_MODES] = {nullptr};
-    int* miss_flag = nullptr;
-    int* sweeps = nullptr;
-    size_t r1_ws = 0;
-    int r1_nmax = 1, r1_zs = 0, r1_mt = 0, r1_tab = 0;
-    // arena offsets (doubles)
-    size_t off_colsum = 0, off_colcnt = 0, off_z = 0, off_ss = 0;
-};
-
-}  // namespace
-
-struct tpls_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    int sm_count = 148;
-    std::string error;
-    // comm
-    ncclComm_t comm = nullptr;
-    int rank = 0, world = 1;
-    // peer-memory exchange (xchg.cuh): own buffer + the peers' mappings
-    void* xchg_buf = nullptr;
-    void* xchg_peer[kXchgMaxRanks] = {nullptr};
-    int xchg_cap = 0;
-    bool xchg_ready = false;
-    unsigned long long xchg_seq = 0;
-    // data
-    Tensor x[TPLS_MAX_TENSORS];
-    long long n = 0;
-    int m = 0, pitch_y = 0;
-    double *y_src = nullptr, *y_work = nullptr;
-    double* row_w = nullptr;  // optional 0/1 sample weights of the next fit (cross-validation folds)
-    PassGeom gy{}, gy_row{};
-    double h2d_bytes = 0;
-    // fit state
-    int L = 0, R = 0;
-    bool fitted = false;
-    std::vector<void*> fit_allocs;
-    double *T = nullptr, *U = nullptr, *Q = nullptr, *coef = nullptr, *gram = nullptr;
-    double *arena = nullptr, *qvec = nullptr, *svec = nullptr, *ymean_d = nullptr;
-    double *zpart_y = nullptr, *cntpart_y = nullptr, *sspart_y = nullptr, *d2part = nullptr, *dotpart = nullptr;
-    double* scratch_ss = nullptr;
-    int* trips_dev = nullptr;
-    int* ymiss_flag = nullptr;
-    Ctrl* ctrl = nullptr;
-    int* h_done = nullptr;  // pinned
-    // cache of the large X-sized device buffers, reused across fits (cudaMalloc/cudaFree of tens of GB
-    // costs hundreds of ms); tpls_trim() returns them to the driver
-    struct PoolBuf {
-        void* p;
-        size_t bytes;
-        bool used;
-    };
-    std::vector<PoolBuf> pool;
-    // slab of the per-fit buffers (see dev_alloc) and a grow-only bounce buffer for the getters
-    char* slab = nullptr;
-    size_t slab_cap = 0, slab_off = 0, slab_need = 0;
-    bool slab_dry = false;
-    void* tmp_buf = nullptr;
-    size_t tmp_cap = 0;
-    size_t arena_doubles = 0, off_ysum = 0, off_ycnt = 0, off_n = 0, off_stats_end = 0, off_zcat = 0, zcat_len = 0,
-           off_q = 0, off_d2 = 0, off_dots = 0, off_ss = 0, ss_len = 0;
-    std::vector<double> r2x[TPLS_MAX_TENSORS];
-    std::vector<double> r2y;
-    std::vector<int> trips;
-    double n_total = 0;
-    bool cov_alloc = false;  // the last alloc_fit reserved the covariance-mode buffers
-    size_t off_cov = 0, cov_len = 0, off_gram_y = 0;
-    double *grampart = nullptr, *q_prev = nullptr;
-    tpls_stats stats{};
-    // optional per-kernel-class timing (TPLS_FIT_PROFILE): event pairs on the launching stream
-    bool profile = false;
-    struct ProfRec {
-        int cls;
-        cudaEvent_t a, b;
-        double bytes;
-    };
-    std::vector<ProfRec> prof;
-    std::vector<cudaEvent_t> ev_pool;
-    tpls_profile prof_sum{};
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_trip[4] = {nullptr, nullptr, nullptr, nullptr};
-};
-
-namespace {
 
 int fail(tpls_handle h, const char* fmt, ...) {
     char buf[512];
@@ -150,25 +22,6 @@ int fail(tpls_handle h, const char* fmt, ...) {
     return 1;
 }
 
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e__ = (call);                                                                        \
-        if (e__ != cudaSuccess)                                                                          \
-            return fail(h, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));        \
-    } while (0)
-
-#define CKN(call)                                                                                        \
-    do {                                                                                                 \
-        int r__ = (call);                                                                                \
-        if (r__ != 0) return fail(h, "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__)); \
-    } while (0)
-
-#define TRY(call)                  \
-    do {                           \
-        int r__ = (call);          \
-        if (r__ != 0) return r__;  \
-    } while (0)
-
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes at{};
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -178,8 +31,6 @@ bool is_device_ptr(const void* p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-int pool_get(tpls_handle h, void** out, size_t bytes);
-void pool_put(tpls_handle h, void* p);
 
 // Per-fit buffers are carved out of ONE cached slab (cudaMalloc / cudaFree cost milliseconds each once
 // NCCL has enabled peer access; a fit needs ~60 buffers).  `track == &h->fit_allocs` selects the slab:
@@ -263,24 +114,6 @@ cudaEvent_t prof_event(tpls_handle h) {
     return e;
 }
 
-struct ProfScope {
-    tpls_handle h;
-    bool on;
-    tpls_ctx::ProfRec r{};
-    ProfScope(tpls_handle h_, int cls, double bytes) : h(h_), on(h_->profile) {
-        if (!on) return;
-        r.cls = cls;
-        r.bytes = bytes;
-        r.a = prof_event(h);
-        r.b = prof_event(h);
-        cudaEventRecord(r.a, h->stream);
-    }
-    ~ProfScope() {
-        if (!on) return;
-        cudaEventRecord(r.b, h->stream);
-        h->prof.push_back(r);
-    }
-};
 
 // Sums the launch records of every profiled fit since the last collection (event queries cost a few
 // microseconds each, so they are made when the profile is asked for, not inside the fit).
@@ -340,7 +173,7 @@ int allreduce(tpls_handle h, double* buf, size_t count) {
 }
 
 // ---- pass wrappers that keep the launch / byte counters ----
-int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a, int cls = -1) {
+int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a, int cls) {
     const double bytes = (double)a.g.n_rows * a.g.pitch * a.g.elem_size * ((flags & PF_WRITE) ? 2.0 : 1.0);
     if (cls < 0) {
         cls = TPLS_K_OTHER;
@@ -357,7 +190,7 @@ int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a, i
 }
 
 // mode: 0 dense, 1 masked with known row counts (a.rowcnt), 2 masked and counting (fills a.rowcnt)
-int row_pass(tpls_handle h, int dtype, int mode, RowPassArgs& a, int cls = TPLS_K_PROJECT) {
+int row_pass(tpls_handle h, int dtype, int mode, RowPassArgs& a, int cls) {
     const double bytes = (double)a.g.n_rows * a.g.pitch * a.g.elem_size;
     ProfScope ps(h, cls, bytes);
     CK(launch_rowpass(dtype, mode, a, h->stream));
@@ -405,7 +238,29 @@ int reduce_cols(tpls_handle h, const double* part, double* out, int n_cols, int 
 
 int d2_grid(const PassGeom& g) { return g.n_slabs > 1 ? row_finish_grid(g.n_rows) : g.grid_x; }
 
-}  // namespace
+int copy_out_transposed(tpls_handle h, const double* colmajor, long long rows, int cols, double* out) {
+    CK(cudaSetDevice(h->device));
+    if (is_device_ptr(out)) {
+        CK(launch_transpose_out(colmajor, rows, rows, cols, out, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    const size_t need = sizeof(double) * std::max<long long>(1, rows * cols);
+    if (need > h->tmp_cap) {
+        if (h->tmp_buf) pool_put(h, h->tmp_buf);
+        h->tmp_buf = nullptr;
+        h->tmp_cap = 0;
+        TRY(pool_get(h, &h->tmp_buf, need));
+        h->tmp_cap = need;
+    }
+    double* tmp = static_cast<double*>(h->tmp_buf);
+    CK(launch_transpose_out(colmajor, rows, rows, cols, tmp, h->stream));
+    CK(cudaMemcpyAsync(out, tmp, sizeof(double) * rows * cols, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // namespace tpls_drv
 
 // ===========================================================================
 // C ABI
@@ -1408,27 +1263,6 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
 // ---------------------------------------------------------------------------
 // getters
 // ---------------------------------------------------------------------------
-static int copy_out_transposed(tpls_handle h, const double* colmajor, long long rows, int cols, double* out) {
-    CK(cudaSetDevice(h->device));
-    if (is_device_ptr(out)) {
-        CK(launch_transpose_out(colmajor, rows, rows, cols, out, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
-    }
-    const size_t need = sizeof(double) * std::max<long long>(1, rows * cols);
-    if (need > h->tmp_cap) {
-        if (h->tmp_buf) pool_put(h, h->tmp_buf);
-        h->tmp_buf = nullptr;
-        h->tmp_cap = 0;
-        TRY(pool_get(h, &h->tmp_buf, need));
-        h->tmp_cap = need;
-    }
-    double* tmp = static_cast<double*>(h->tmp_buf);
-    CK(launch_transpose_out(colmajor, rows, rows, cols, tmp, h->stream));
-    CK(cudaMemcpyAsync(out, tmp, sizeof(double) * rows * cols, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
-}
 
 #define NEED_FIT()                                     \
     if (!h) return fail(nullptr, "NULL handle");       \
@@ -1557,400 +1391,6 @@ int tpls_trim(tpls_handle h) {
     CK(cudaStreamSynchronize(h->stream));
     pool_trim(h);
     return 0;
-}
-
-int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* const* xs, const int* dtypes,
-                   int64_t n_new, const int64_t* ps, const void* const* means, const double* const* wkrons,
-                   const double* proj_offset, const double* proj_gram, double* scores_out) {
-    if (!h) return fail(nullptr, "NULL handle");
-    const int L = n_tensors, R = n_components;
-    if (L < 1 || L > TPLS_MAX_TENSORS || R < 1 || R > 64 || n_new <= 0) return fail(h, "tpls_transform: bad sizes");
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    std::vector<void*> tmp;
-    double *S = nullptr, *sspart = nullptr, *pc = nullptr, *pg = nullptr;
-    int* flag = nullptr;
-    int rc = 0;
-    std::vector<const void*> src(L, nullptr);  // the new data where it can be read in place, else its staged copy
-    std::vector<void*> xw(L, nullptr);         // writable working copy (only the sequential path needs it)
-    std::vector<PassGeom> gs(L), grs(L), grs_cnt(L);
-    std::vector<double*> tpart(L, nullptr), cpart(L, nullptr), mean_d(L, nullptr), wk(L, nullptr), rowcnt(L, nullptr);
-    std::vector<int> pitch(L), elem(L);
-    auto stage = [&](int l) -> int {  // pitched private copy of tensor l
-        if (xw[l]) return 0;
-        const size_t bytes = (size_t)n_new * pitch[l] * elem[l];
-        TRY(dev_alloc(h, &xw[l], bytes, &tmp));
-        if (pitch[l] != (int)ps[l]) CK(cudaMemsetAsync(xw[l], 0, bytes, st));
-        CK(cudaMemcpy2DAsync(xw[l], (size_t)pitch[l] * elem[l], xs[l], (size_t)ps[l] * elem[l], (size_t)ps[l] * elem[l], n_new,
-                             cudaMemcpyDefault, st));
-        return 0;
-    };
-    do {
-        if ((rc = dev_alloc(h, (void**)&S, sizeof(double) * n_new * R, &tmp))) break;
-        if ((rc = dev_alloc(h, (void**)&sspart, sizeof(double) * 4096, &tmp))) break;
-        if ((rc = dev_alloc(h, (void**)&pc, sizeof(double) * (R + R * R), &tmp))) break;
-        if ((rc = dev_alloc(h, (void**)&flag, sizeof(int) * 4, &tmp))) break;
-        pg = pc + R;
-        for (int l = 0; l < L && !rc; ++l) {
-            if (dtypes[l] != TPLS_F32 && dtypes[l] != TPLS_F64) {
-                rc = fail(h, "tpls_transform: bad dtype for X[%d]", l);
-                break;
-            }
-            elem[l] = dtypes[l] == TPLS_F32 ? 4 : 8;
-            const int vec = 16 / elem[l];
-            const int p = (int)ps[l];
-            pitch[l] = (p + vec - 1) / vec * vec;
-            if ((rc = dev_alloc(h, (void**)&mean_d[l], sizeof(double) * pitch[l], &tmp))) break;
-            if ((rc = dev_alloc(h, (void**)&wk[l], sizeof(double) * pitch[l] * R, &tmp))) break;
-            if ((rc = dev_alloc(h, (void**)&rowcnt[l], sizeof(double) * n_new, &tmp))) break;
-            void* mean_nat = nullptr;
-            if ((rc = dev_alloc(h, &mean_nat, (size_t)elem[l] * pitch[l], &tmp))) break;
-            cudaError_t e = cudaMemsetAsync(wk[l], 0, sizeof(double) * pitch[l] * R, st);
-            if (e == cudaSuccess) e = cudaMemsetAsync(mean_nat, 0, (size_t)elem[l] * pitch[l], st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(mean_nat, means[l], (size_t)elem[l] * p, cudaMemcpyDefault, st);
-            if (e == cudaSuccess)
-                e = cudaMemcpy2DAsync(wk[l], sizeof(double) * pitch[l], wkrons[l], sizeof(double) * p, sizeof(double) * p, R,
-                                      cudaMemcpyDefault, st);
-            if (e == cudaSuccess) e = launch_widen(dtypes[l], mean_nat, mean_d[l], pitch[l], st);
-            if (e != cudaSuccess) {
-                rc = fail(h, "tpls_transform: staging X[%d] -> %s", l, cudaGetErrorString(e));
-                break;
-            }
-            if (is_device_ptr(xs[l]) && pitch[l] == p && ((uintptr_t)xs[l] % 16 == 0)) {
-                src[l] = xs[l];
-            } else {
-                if ((rc = stage(l))) break;
-                src[l] = xw[l];
-            }
-            gs[l] = make_geom(n_new, p, pitch[l], elem[l], h->sm_count);
-            grs[l] = make_row_geom(n_new, p, pitch[l], elem[l], h->sm_count, false);
-            grs_cnt[l] = make_row_geom(n_new, p, pitch[l], elem[l], h->sm_count, true);
-            if (gs[l].n_slabs > 1) {
-                if ((rc = dev_alloc(h, (void**)&tpart[l], sizeof(double) * n_new * gs[l].n_slabs, &tmp))) break;
-                if ((rc = dev_alloc(h, (void**)&cpart[l], sizeof(double) * n_new * gs[l].n_slabs, &tmp))) break;
-            }
-        }
-        if (rc) break;
-
-        // ---- read-only path for complete data: R raw projections of the UNTOUCHED rows, then the
-        //      deflation recurrence on the scores alone.  With x_c = x - mean and no NaN,
-        //        t_a = mean_l (x_c - sum_{b<a} t_b w_lb) . w_la = r_a - c_a - sum_{b<a} t_b G_ba,
-        //      r_a = mean_l x . w_la,  c_a = mean_l mean_l . w_la,  G_ba = mean_l w_lb . w_la  (passed in).
-        bool done = false;
-        if (proj_offset != nullptr && proj_gram != nullptr) {
-            cudaError_t e = cudaMemcpyAsync(pc, proj_offset, sizeof(double) * R, cudaMemcpyDefault, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(pg, proj_gram, sizeof(double) * R * R, cudaMemcpyDefault, st);
-            if (e == cudaSuccess) e = cudaMemsetAsync(flag, 0, sizeof(int) * 4, st);
-            if (e != cudaSuccess) {
-                rc = fail(h, "tpls_transform: %s", cudaGetErrorString(e));
-                break;
-            }
-            // component 0 doubles as the NaN census: a counting masked pass fills the per-row observed counts
-            for (int l = 0; l < L && !rc; ++l) {
-                RowPassArgs r{};
-                r.g = grs_cnt[l];
-                r.x_in = src[l];
-                r.col_w = wk[l];
-                r.t_out = S;
-                r.tpart = tpart[l];
-                r.cpart = cpart[l];
-                r.rowcnt = rowcnt[l];
-                r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
-                r.div = (double)L;
-                rc = row_pass(h, dtypes[l], 2, r);
-                if (!rc) {
-                    cudaError_t e2 = launch_rows_complete(rowcnt[l], n_new, (double)ps[l], flag, st);
-                    if (e2 != cudaSuccess) rc = fail(h, "rows_complete -> %s", cudaGetErrorString(e2));
-                    h->stats.kernel_launches++;
-                }
-            }
-            if (rc) break;
-            int incomplete = 1;
-            cudaError_t e3 = cudaMemcpyAsync(&incomplete, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
-            if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(st);
-            if (e3 != cudaSuccess) {
-                rc = fail(h, "tpls_transform: %s", cudaGetErrorString(e3));
-                break;
-            }
-            if (!incomplete) {
-                for (int a = 1; a < R && !rc; ++a)
-                    for (int l = 0; l < L && !rc; ++l) {
-                        RowPassArgs r{};
-                        r.g = grs[l];
-                        r.x_in = src[l];
-                        r.col_w = wk[l] + (size_t)a * pitch[l];
-                        r.t_out = S + (size_t)a * n_new;
-                        r.tpart = tpart[l];
-                        r.cpart = cpart[l];
-                        r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
-                        r.div = (double)L;
-                        rc = row_pass(h, dtypes[l], 0, r);
-                    }
-                if (rc) break;
-                cudaError_t e4 = launch_score_recurrence(S, n_new, R, pc, pg, st);
-                if (e4 != cudaSuccess) {
-                    rc = fail(h, "score_recurrence -> %s", cudaGetErrorString(e4));
-                    break;
-                }
-                h->stats.kernel_launches++;
-                done = true;
-            }
-        }
-
-        // ---- sequential path (NaNs present, or no projection constants): centre a private copy, then per
-        //      component project (masked) and deflate with the stored loadings (tpls.py:151-165) ----
-        if (!done) {
-            for (int l = 0; l < L && !rc; ++l) {
-                if ((rc = stage(l))) break;
-                ColPassArgs c{};
-                c.g = gs[l];
-                c.x_in = xw[l];
-                c.x_out = xw[l];
-                c.col_w = mean_d[l];
-                c.sspart = sspart;
-                rc = col_pass(h, dtypes[l], true, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c);
-            }
-            for (int a = 0; a < R && !rc; ++a) {
-                double* Sa = S + (size_t)a * n_new;
-                for (int l = 0; l < L && !rc; ++l) {
-                    RowPassArgs r{};
-                    r.g = a == 0 ? grs_cnt[l] : grs[l];
-                    r.x_in = xw[l];
-                    r.col_w = wk[l] + (size_t)a * pitch[l];
-                    r.t_out = Sa;
-                    r.tpart = tpart[l];
-                    r.cpart = cpart[l];
-                    r.rowcnt = rowcnt[l];
-                    r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
-                    r.div = (double)L;
-                    rc = row_pass(h, dtypes[l], a == 0 ? 2 : 1, r);
-                }
-                for (int l = 0; l < L && !rc && a + 1 < R; ++l) {
-                    ColPassArgs c{};
-                    c.g = gs[l];
-                    c.x_in = xw[l];
-                    c.x_out = xw[l];
-                    c.row_a = Sa;
-                    c.col_w = wk[l] + (size_t)a * pitch[l];
-                    c.sspart = sspart;
-                    rc = col_pass(h, dtypes[l], true, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c);
-                }
-            }
-        }
-        if (rc) break;
-        h->stats.last_transform_path = done ? 1 : 2;
-        rc = copy_out_transposed(h, S, n_new, R, scores_out);
-    } while (0);
-    cudaStreamSynchronize(st);
-    for (void* p : tmp) pool_put(h, p);
-    return rc;
-}
-
-// ---------------------------------------------------------------------------
-// single operators
-// ---------------------------------------------------------------------------
-}  // extern "C"
-
-static int time_loop(tpls_handle h, int repeats, float* ms_out, const std::function<int()>& body) {
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    repeats = std::max(1, repeats);
-    int rc = 0;
-    if (repeats > 1) rc = body();  // warm-up
-    CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < repeats && !rc; ++i) rc = body();
-    CK(cudaEventRecord(e1, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    if (ms_out) *ms_out = ms / repeats;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    return rc;
-}
-
-extern "C" {
-
-static int op_check(tpls_handle h, int dtype, int64_t n, int64_t p) {
-    if (!h) return fail(nullptr, "NULL handle");
-    if (dtype != TPLS_F32 && dtype != TPLS_F64) return fail(h, "bad dtype");
-    const int elem = dtype == TPLS_F32 ? 4 : 8;
-    if (n <= 0 || p <= 0 || (p * elem) % 16 != 0) return fail(h, "operator needs p*elem %% 16 == 0 (p=%lld)", (long long)p);
-    return 0;
-}
-
-int tpls_op_contract(tpls_handle h, const void* x, int dtype, int64_t n, int64_t p, const double* u, int masked,
-                     double* z_out, float* ms_out, int repeats) {
-    TRY(op_check(h, dtype, n, p));
-    CK(cudaSetDevice(h->device));
-    const int elem = dtype == TPLS_F32 ? 4 : 8;
-    PassGeom g = make_geom(n, (int)p, (int)p, elem, h->sm_count);
-    double *zpart = nullptr, *cntpart = nullptr, *cnt = nullptr;
-    CK(cudaMalloc((void**)&zpart, sizeof(double) * g.grid_x * p));
-    CK(cudaMalloc((void**)&cntpart, sizeof(double) * g.grid_x * p));
-    CK(cudaMalloc((void**)&cnt, sizeof(double) * p));
-    int rc = 0;
-    if (masked) {
-        ColPassArgs c{};
-        c.g = g;
-        c.x_in = x;
-        c.zpart = zpart;
-        c.cntpart = cntpart;
-        rc = col_pass(h, dtype, true, PF_COLSTAT, c);
-        if (!rc) rc = reduce_cols(h, cntpart, cnt, (int)p, (int)p, g.grid_x, nullptr, nullptr, 0, nullptr, 0);
-    }
-    if (!rc)
-        rc = time_loop(h, repeats, ms_out, [&]() -> int {
-            ColPassArgs c{};
-            c.g = g;
-            c.x_in = x;
-            c.row_u = u;
-            c.zpart = zpart;
-            TRY(col_pass(h, dtype, masked != 0, PF_CONTRACT, c));
-            return reduce_cols(h, zpart, z_out, (int)p, (int)p, g.grid_x, nullptr, nullptr, 0, nullptr, 0);
-        });
-    // during a fit the observed-count rescaling (missingvals.py:18) is applied by the rank-1 kernel
-    if (!rc && masked) {
-        cudaError_t e = launch_count_rescale(z_out, cnt, (double)n, (int)p, h->stream);
-        if (e != cudaSuccess) rc = fail(h, "count_rescale -> %s", cudaGetErrorString(e));
-    }
-    cudaStreamSynchronize(h->stream);
-    cudaFree(zpart);
-    cudaFree(cntpart);
-    cudaFree(cnt);
-    return rc;
-}
-
-int tpls_op_project(tpls_handle h, const void* x, int dtype, int64_t n, int64_t p, const double* w, int masked,
-                    double* t_out, float* ms_out, int repeats) {
-    TRY(op_check(h, dtype, n, p));
-    CK(cudaSetDevice(h->device));
-    const int elem = dtype == TPLS_F32 ? 4 : 8;
-    PassGeom g = make_row_geom(n, (int)p, (int)p, elem, h->sm_count, false);
-    PassGeom g_cnt = make_row_geom(n, (int)p, (int)p, elem, h->sm_count, true);
-    double *tpart = nullptr, *cpart = nullptr, *rowcnt = nullptr;
-    bool counted = false;
-    CK(cudaMalloc((void**)&rowcnt, sizeof(double) * n));
-    if (g.n_slabs > 1) {
-        CK(cudaMalloc((void**)&tpart, sizeof(double) * n * g.n_slabs));
-        CK(cudaMalloc((void**)&cpart, sizeof(double) * n * g.n_slabs));
-    }
-    int rc = time_loop(h, repeats, ms_out, [&]() -> int {
-        RowPassArgs r{};
-        r.g = (masked && !counted) ? g_cnt : g;
-        r.x_in = x;
-        r.col_w = w;
-        r.t_out = t_out;
-        r.tpart = tpart;
-        r.cpart = cpart;
-        r.rowcnt = rowcnt;
-        r.epi = 0;
-        r.div = 1.0;
-        const int mode = !masked ? 0 : (counted ? 1 : 2);
-        counted = true;
-        return row_pass(h, dtype, mode, r);
-    });
-    cudaStreamSynchronize(h->stream);
-    if (tpart) cudaFree(tpart);
-    if (cpart) cudaFree(cpart);
-    cudaFree(rowcnt);
-    return rc;
-}
-
-int tpls_op_deflate_contract(tpls_handle h, void* x, int dtype, int64_t n, int64_t p, const double* t,
-                             const double* w, const double* u, int masked, double* z_out, double* ss_out,
-                             float* ms_out, int repeats) {
-    TRY(op_check(h, dtype, n, p));
-    CK(cudaSetDevice(h->device));
-    const int elem = dtype == TPLS_F32 ? 4 : 8;
-    PassGeom g = make_geom(n, (int)p, (int)p, elem, h->sm_count);
-    double *zpart = nullptr, *sspart = nullptr;
-    CK(cudaMalloc((void**)&zpart, sizeof(double) * g.grid_x * p));
-    CK(cudaMalloc((void**)&sspart, sizeof(double) * g.grid_x * g.n_slabs));
-    int rc = time_loop(h, repeats, ms_out, [&]() -> int {
-        ColPassArgs c{};
-        c.g = g;
-        c.x_in = x;
-        c.x_out = x;
-        c.row_a = t;
-        c.col_w = w;
-        c.row_u = u;
-        c.zpart = zpart;
-        c.sspart = sspart;
-        TRY(col_pass(h, dtype, masked != 0, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ, c));
-        return reduce_cols(h, zpart, z_out, (int)p, (int)p, g.grid_x, sspart, ss_out, g.grid_x * g.n_slabs, nullptr, 0);
-    });
-    cudaStreamSynchronize(h->stream);
-    cudaFree(zpart);
-    cudaFree(sspart);
-    return rc;
-}
-
-int tpls_op_rank1(tpls_handle h, const double* z, int nmodes, const int* dims, double tol, int flags, double* w_out,
-                  double* wkron_out, int* sweeps_out, float* ms_out, int repeats) {
-    if (!h) return fail(nullptr, "NULL handle");
-    if (nmodes < 1 || nmodes > kMaxZModes) return fail(h, "tpls_op_rank1: nmodes must be 1..%d", kMaxZModes);
-    CK(cudaSetDevice(h->device));
-    Rank1Args ra{};
-    ra.n_tasks = 1;
-    ra.tol = tol;
-    ra.normalize_on_break = (flags & TPLS_FIT_NORMALIZE_ON_BREAK) ? 1 : 0;
-    Rank1Task& k = ra.t[0];
-    long long p = 1;
-    size_t off = 0;
-    for (int m = 0; m < nmodes; ++m) {
-        k.dims[m] = dims[m];
-        k.w[m] = w_out + off;
-        off += dims[m];
-        p *= dims[m];
-    }
-    k.z = z;
-    k.p = (int)p;
-    k.pitch = (int)p;
-    k.nmodes = nmodes;
-    k.wkron = wkron_out;
-    int nmax = 1, zs_len = 0, mt_len = 0, tab_cols = 0;
-    const size_t ws = rank1_workspace_doubles(nmodes, dims, &nmax, &zs_len, &mt_len, &tab_cols);
-    k.nmax = nmax;
-    k.zs_len = zs_len;
-    k.mt_len = mt_len;
-    k.tab_cols = tab_cols;
-    double* scratch = nullptr;
-    int* sweeps = nullptr;
-    CK(cudaMalloc((void**)&scratch, sizeof(double) * ws));
-    CK(cudaMalloc((void**)&sweeps, sizeof(int) * 4));
-    k.scratch = scratch;
-    k.sweeps = sweeps;
-    long long* stamps = nullptr;
-    const bool want_stamps = getenv("TPLS_RANK1_STAMPS") != nullptr;
-    if (want_stamps) {
-        CK(cudaMalloc((void**)&stamps, sizeof(long long) * 16));
-        CK(cudaMemset(stamps, 0, sizeof(long long) * 16));
-        k.stamps = stamps;
-    }
-    size_t smem = ws * sizeof(double);
-    k.use_smem = smem <= 200 * 1024;
-    if (!k.use_smem) smem = 0;
-    int rc = time_loop(h, repeats, ms_out, [&]() -> int {
-        CK(launch_rank1(ra, smem, h->stream));
-        h->stats.kernel_launches++;
-        return 0;
-    });
-    cudaStreamSynchronize(h->stream);
-    if (!rc && sweeps_out) cudaMemcpy(sweeps_out, sweeps, sizeof(int), cudaMemcpyDeviceToHost);
-    if (want_stamps) {
-        long long hs[16];
-        cudaMemcpy(hs, stamps, sizeof hs, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "rank1 stamps (cycles): load->gram %lld  eig %lld  init-rest %lld  als %lld  publish %lld\n", hs[1] - hs[0],
-                hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4]);
-        fprintf(stderr, "   last run: als rows %lld  als sums %lld  als renorm %lld | squarings %lld  in %lld  eig tail %lld\n", hs[8],
-                hs[9], hs[10], hs[12], hs[13], hs[14]);
-        cudaFree(stamps);
-    }
-    cudaFree(scratch);
-    cudaFree(sweeps);
-    return rc;
 }
 
 }  // extern "C"
