@@ -26,6 +26,36 @@ __device__ __forceinline__ bool trip_is_dead(const Ctrl* c, int trip) {
 }
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library starts with pdl_prologue(): it lets the
+// NEXT kernel in the stream be scheduled early (its CTAs then sit at their own griddepcontrol.wait instead of
+// paying the launch latency after this grid has drained) and waits until the PREVIOUS grid has completed and
+// flushed its writes.  Both instructions do nothing for a kernel launched without the PDL attribute, which is
+// the default: TPLS_PDL=1 makes launch_k() set it.  Nothing before the prologue may read or write global memory.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+bool pdl_enabled();  // small.cu: TPLS_PDL=1 in the environment (read once)
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the optional PDL attribute
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP / SYNCS)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -61,6 +61,7 @@ size_t covpass_smem(const PassGeom& g, int pitch_y, int mr) {
 
 template <typename XT, bool MASKED, int MR>
 __global__ void __launch_bounds__(kThreads, 2) covpass_kernel(const __grid_constant__ CovPassArgs a) {
+    pdl_prologue();
     constexpr int VEC = VecOf<XT>::N;
     constexpr int MY = MASKED ? MR / 2 : MR;  // response columns actually read
 
@@ -227,7 +228,7 @@ static cudaError_t run_cov(const CovPassArgs& a, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
-    kern<<<grid, kThreads, smem, s>>>(a);
+    launch_k(kern, dim3(grid), dim3(kThreads), smem, s, a);
     return cudaGetLastError();
 }
 

@@ -74,6 +74,7 @@ size_t colpass_smem(const PassGeom& g) {
 // e.g. 4096 fp32 columns): layout constants fold at compile time and the row loop carries no bounds checks.
 template <typename XT, int CPT, bool MASKED, int FLAGS, bool FULL>
 __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_constant__ ColPassArgs a) {
+    pdl_prologue();
     constexpr int VEC = VecOf<XT>::N;
     constexpr bool DEFLATE = (FLAGS & PF_DEFLATE) != 0;
     constexpr bool WRITE = (FLAGS & PF_WRITE) != 0;
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
 // 32 columns x 8 part-groups per CTA: each thread folds every 8th partial of its column (coalesced 256-byte
 // rows, several loads in flight), the 8 groups meet in shared memory.  Fixed order => bit-reproducible.
 __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
+    pdl_prologue();
     if (trip_is_dead(a.ctrl, a.trip)) return;
     __shared__ double fold[8][33];
     __shared__ double red[40];
@@ -276,11 +278,12 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
 
 cudaError_t launch_reduce_cols(const ReduceArgs& a, cudaStream_t s) {
     const int blocks = std::max(1, (a.n_cols + 31) / 32);
-    reduce_cols_kernel<<<blocks, 256, 0, s>>>(a);
+    launch_k(reduce_cols_kernel, dim3(blocks), dim3(256), 0, s, a);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) row_finish_kernel(const RowFinishArgs a) {
+    pdl_prologue();
     if (trip_is_dead(a.ctrl, a.trip)) return;
     __shared__ double red[40];
     double d2 = 0.0;
@@ -321,7 +324,7 @@ int row_finish_grid(long long n_rows) {
 cudaError_t launch_row_finish(const RowFinishArgs& a, int* grid_out, cudaStream_t s) {
     const int blocks = row_finish_grid(a.n_rows);
     if (grid_out) *grid_out = blocks;
-    row_finish_kernel<<<blocks, 256, 0, s>>>(a);
+    launch_k(row_finish_kernel, dim3(blocks), dim3(256), 0, s, a);
     return cudaGetLastError();
 }
 
@@ -335,7 +338,7 @@ static cudaError_t run_colpass_impl(const ColPassArgs& a, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
-    kern<<<grid, kThreads, smem, s>>>(a);
+    launch_k(kern, dim3(grid), dim3(kThreads), smem, s, a);
     return cudaGetLastError();
 }
 

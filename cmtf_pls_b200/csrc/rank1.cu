@@ -759,6 +759,7 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
 // instead of generic loads); false: it is the task's global scratch buffer.
 template <bool SMEM>
 __global__ void __launch_bounds__(kRank1Threads, 1) rank1_kernel(const __grid_constant__ Rank1Args a) {
+    pdl_prologue();
     if (trip_is_dead(a.ctrl, a.trip)) return;
     extern __shared__ __align__(16) double dyn[];
     const Rank1Task& T = a.t[blockIdx.x];
@@ -770,6 +771,7 @@ __global__ void __launch_bounds__(kRank1Threads, 1) rank1_kernel(const __grid_co
 
 template <bool SMEM>
 __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid_constant__ CovLoopArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(16) double dyn[];
     __shared__ double q_last[8], q_new[8], r_acc[8], lred[4 * NWARP];
     __shared__ int lired[2 * NWARP];
@@ -847,9 +849,9 @@ cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_sm
         cudaError_t e =
             cudaFuncSetAttribute(cov_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        cov_loop_kernel<true><<<1, kRank1Threads, smem_bytes, s>>>(a);
+        launch_k(cov_loop_kernel<true>, dim3(1), dim3(kRank1Threads), smem_bytes, s, a);
     } else {
-        cov_loop_kernel<false><<<1, kRank1Threads, 0, s>>>(a);
+        launch_k(cov_loop_kernel<false>, dim3(1), dim3(kRank1Threads), 0, s, a);
     }
     return cudaGetLastError();
 }
@@ -899,9 +901,9 @@ cudaError_t launch_rank1(const Rank1Args& a, size_t smem_bytes, cudaStream_t s) 
         cudaError_t e =
             cudaFuncSetAttribute(rank1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        rank1_kernel<true><<<a.n_tasks, kRank1Threads, smem_bytes, s>>>(a);
+        launch_k(rank1_kernel<true>, dim3(a.n_tasks), dim3(kRank1Threads), smem_bytes, s, a);
     } else {
-        rank1_kernel<false><<<a.n_tasks, kRank1Threads, 0, s>>>(a);
+        launch_k(rank1_kernel<false>, dim3(a.n_tasks), dim3(kRank1Threads), 0, s, a);
     }
     return cudaGetLastError();
 }

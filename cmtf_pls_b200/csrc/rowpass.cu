@@ -99,6 +99,7 @@ __device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long gro
 // FULL: one slab, every consumer thread owns CPT valid column groups of every row (see colpass_kernel).
 template <typename XT, int CPT, int MODE, bool FULL>
 __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_constant__ RowPassArgs a) {
+    pdl_prologue();
     constexpr int VEC = VecOf<XT>::N;
     constexpr bool MASKED = MODE != 0;
     constexpr bool COUNT = MODE == 2;
@@ -364,7 +365,7 @@ static cudaError_t run_rowpass_impl(const RowPassArgs& a, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
-    kern<<<grid, kRowThreads, smem, s>>>(a);
+    launch_k(kern, dim3(grid), dim3(kRowThreads), smem, s, a);
     return cudaGetLastError();
 }
 

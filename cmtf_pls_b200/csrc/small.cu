@@ -1,13 +1,24 @@
 // Small kernels -- see small.cuh.
 #include "small.cuh"
 
+#include <cstdlib>
+
 #include <algorithm>
 
 namespace tpls {
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("TPLS_PDL");
+        return v != nullptr && *v != '\0' && *v != '0';
+    }();
+    return on;
+}
+
 template <typename XT>
 __global__ void finalize_mean_kernel(const double* colsum, const double* colcnt, const double* n_total, int p, int pitch,
                                      double* mean_d, XT* native_out, int* miss_flag) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= pitch) return;
     if (c >= p) {
@@ -25,27 +36,29 @@ cudaError_t launch_finalize_mean(int dtype, const double* colsum, const double* 
                                  int pitch, double* mean_d, void* native_out, int* miss_flag, cudaStream_t s) {
     const int blocks = (pitch + 255) / 256;
     if (dtype == 0)
-        finalize_mean_kernel<float><<<blocks, 256, 0, s>>>(colsum, colcnt, n_total, p, pitch, mean_d,
+        launch_k(finalize_mean_kernel<float>, dim3(blocks), dim3(256), 0, s, colsum, colcnt, n_total, p, pitch, mean_d,
                                                            (float*)native_out, miss_flag);
     else
-        finalize_mean_kernel<double><<<blocks, 256, 0, s>>>(colsum, colcnt, n_total, p, pitch, mean_d,
+        launch_k(finalize_mean_kernel<double>, dim3(blocks), dim3(256), 0, s, colsum, colcnt, n_total, p, pitch, mean_d,
                                                             (double*)native_out, miss_flag);
     return cudaGetLastError();
 }
 
 __global__ void gather_col_kernel(const double* src, long long n, int pitch, int col, double* dst) {
+    pdl_prologue();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] = src[i * pitch + col];
 }
 
 cudaError_t launch_gather_col(const double* src, long long n, int pitch, int col, double* dst, cudaStream_t s) {
     const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
-    gather_col_kernel<<<blocks, 256, 0, s>>>(src, n, pitch, col, dst);
+    launch_k(gather_col_kernel, dim3(blocks), dim3(256), 0, s, src, n, pitch, col, dst);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) normalize_q_kernel(const double* qraw, int m, int pitch, double* qcol,
                                                           double* qvec, const Ctrl* ctrl, int trip) {
+    pdl_prologue();
     if (trip_is_dead(ctrl, trip)) return;
     __shared__ double red[40];
     double s = 0.0;
@@ -60,12 +73,13 @@ __global__ void __launch_bounds__(256) normalize_q_kernel(const double* qraw, in
 
 cudaError_t launch_normalize_q(const double* qraw, int m, int pitch, double* qcol, double* qvec, const Ctrl* ctrl,
                                int trip, cudaStream_t s) {
-    normalize_q_kernel<<<1, 256, 0, s>>>(qraw, m, pitch, qcol, qvec, ctrl, trip);
+    launch_k(normalize_q_kernel, dim3(1), dim3(256), 0, s, qraw, m, pitch, qcol, qvec, ctrl, trip);
     return cudaGetLastError();
 }
 
 __global__ void normalize_q_stop_kernel(const double* qraw, int m, int pitch, double* qcol, double* qvec,
                                         const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol) {
+    pdl_prologue();
     if (trip_is_dead(ctrl, trip)) return;
     if (threadIdx.x != 0) return;
     normalize_q_stop_body(qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
@@ -75,6 +89,7 @@ __global__ void normalize_q_stop_kernel(const double* qraw, int m, int pitch, do
 __global__ void __launch_bounds__(256) reduce_q_stop_kernel(const double* part, int n_parts, int stride, double* qraw, int m,
                                                             int pitch, double* qcol, double* qvec, const double* gram,
                                                             double* q_prev, Ctrl* ctrl, int trip, double tol) {
+    pdl_prologue();
     if (trip_is_dead(ctrl, trip)) return;
     __shared__ double fold[8][33];
     const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
@@ -106,18 +121,19 @@ cudaError_t launch_reduce_q_stop(const double* part, int n_parts, int stride, do
                                  double* qvec, const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol,
                                  cudaStream_t s) {
     if (pitch > 32 || m > 8) return cudaErrorInvalidValue;
-    reduce_q_stop_kernel<<<1, 256, 0, s>>>(part, n_parts, stride, qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
+    launch_k(reduce_q_stop_kernel, dim3(1), dim3(256), 0, s, part, n_parts, stride, qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
     return cudaGetLastError();
 }
 
 cudaError_t launch_normalize_q_stop(const double* qraw, int m, int pitch, double* qcol, double* qvec, const double* gram,
                                     double* q_prev, Ctrl* ctrl, int trip, double tol, cudaStream_t s) {
-    normalize_q_stop_kernel<<<1, 32, 0, s>>>(qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
+    launch_k(normalize_q_stop_kernel, dim3(1), dim3(32), 0, s, qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) sum_small_kernel(const double* parts, int n, double* out, const Ctrl* ctrl,
                                                         int trip) {
+    pdl_prologue();
     if (trip_is_dead(ctrl, trip)) return;
     __shared__ double red[40];
     double s = 0.0;
@@ -127,11 +143,12 @@ __global__ void __launch_bounds__(256) sum_small_kernel(const double* parts, int
 }
 
 cudaError_t launch_sum_small(const double* parts, int n, double* out, const Ctrl* ctrl, int trip, cudaStream_t s) {
-    sum_small_kernel<<<1, 256, 0, s>>>(parts, n, out, ctrl, trip);
+    launch_k(sum_small_kernel, dim3(1), dim3(256), 0, s, parts, n, out, ctrl, trip);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) stop_kernel(Ctrl* ctrl, int trip, const double* parts, int n, double tol) {
+    pdl_prologue();
     if (trip_is_dead(ctrl, trip)) return;
     __shared__ double red[40];
     double s = 0.0;
@@ -146,22 +163,24 @@ __global__ void __launch_bounds__(256) stop_kernel(Ctrl* ctrl, int trip, const d
 }
 
 cudaError_t launch_stop(Ctrl* ctrl, int trip, const double* parts, int n, double tol, cudaStream_t s) {
-    stop_kernel<<<1, 256, 0, s>>>(ctrl, trip, parts, n, tol);
+    launch_k(stop_kernel, dim3(1), dim3(256), 0, s, ctrl, trip, parts, n, tol);
     return cudaGetLastError();
 }
 
 __global__ void reset_ctrl_kernel(Ctrl* ctrl) {
+    pdl_prologue();
     ctrl->done_trip = -1;
     ctrl->trips_taken = 0;
     ctrl->last_d2 = 0.0;
 }
 
 cudaError_t launch_reset_ctrl(Ctrl* ctrl, cudaStream_t s) {
-    reset_ctrl_kernel<<<1, 1, 0, s>>>(ctrl);
+    launch_k(reset_ctrl_kernel, dim3(1), dim3(1), 0, s, ctrl);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) multi_dot_kernel(const __grid_constant__ DotPairs d, double* part) {
+    pdl_prologue();
     __shared__ double red[40];
     const int j = blockIdx.y;
     const double* a = d.a[j];
@@ -176,12 +195,13 @@ __global__ void __launch_bounds__(256) multi_dot_kernel(const __grid_constant__ 
 cudaError_t launch_multi_dot(const DotPairs& d, double* part, int* grid_out, cudaStream_t s) {
     const int gx = (int)std::max<long long>(1, std::min<long long>(148, (d.n + 2047) / 2048));
     if (grid_out) *grid_out = gx;
-    multi_dot_kernel<<<dim3(gx, d.npairs), 256, 0, s>>>(d, part);
+    launch_k(multi_dot_kernel, dim3(gx, d.npairs), dim3(256), 0, s, d, part);
     return cudaGetLastError();
 }
 
 __global__ void solve_coef_kernel(const double* dots, double* gram, double* coef, int R, int a, const Ctrl* ctrl,
                                   int* trips_out) {
+    pdl_prologue();
     if (threadIdx.x != 0) return;
     const int k = a + 1;
     for (int b = 0; b < k; ++b) {
@@ -214,12 +234,13 @@ __global__ void solve_coef_kernel(const double* dots, double* gram, double* coef
 
 cudaError_t launch_solve_coef(const double* dots, double* gram, double* coef, int R, int a, const Ctrl* ctrl,
                               int* trips_out, cudaStream_t s) {
-    solve_coef_kernel<<<1, 32, 0, s>>>(dots, gram, coef, R, a, ctrl, trips_out);
+    launch_k(solve_coef_kernel, dim3(1), dim3(32), 0, s, dots, gram, coef, R, a, ctrl, trips_out);
     return cudaGetLastError();
 }
 
 __global__ void lincomb_kernel(const double* T, long long n, long long ldt, const double* coef, int R, int a,
                                const double* row_w, double* out) {
+    pdl_prologue();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int b = 0; b <= a; ++b) s = fma(T[b * ldt + i], coef[b * R + a], s);
@@ -230,11 +251,12 @@ __global__ void lincomb_kernel(const double* T, long long n, long long ldt, cons
 cudaError_t launch_lincomb(const double* T, long long n, long long ldt, const double* coef, int R, int a,
                            const double* row_w, double* out, cudaStream_t s) {
     const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
-    lincomb_kernel<<<blocks, 256, 0, s>>>(T, n, ldt, coef, R, a, row_w, out);
+    launch_k(lincomb_kernel, dim3(blocks), dim3(256), 0, s, T, n, ldt, coef, R, a, row_w, out);
     return cudaGetLastError();
 }
 
 __global__ void scale_rows_kernel(double* y, long long n, int pitch, const double* w) {
+    pdl_prologue();
     const long long total = n * pitch;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x)
@@ -244,11 +266,12 @@ __global__ void scale_rows_kernel(double* y, long long n, int pitch, const doubl
 cudaError_t launch_scale_rows(double* y, long long n, int pitch, const double* w, cudaStream_t s) {
     const long long total = n * pitch;
     const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (total + 255) / 256));
-    scale_rows_kernel<<<blocks, 256, 0, s>>>(y, n, pitch, w);
+    launch_k(scale_rows_kernel, dim3(blocks), dim3(256), 0, s, y, n, pitch, w);
     return cudaGetLastError();
 }
 
 __global__ void transpose_out_kernel(const double* in, long long n, long long ld, int cols, double* out) {
+    pdl_prologue();
     const long long total = n * cols;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
@@ -261,22 +284,24 @@ __global__ void transpose_out_kernel(const double* in, long long n, long long ld
 cudaError_t launch_transpose_out(const double* in, long long n, long long ld, int cols, double* out, cudaStream_t s) {
     const long long total = n * cols;
     const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (total + 255) / 256));
-    transpose_out_kernel<<<blocks, 256, 0, s>>>(in, n, ld, cols, out);
+    launch_k(transpose_out_kernel, dim3(blocks), dim3(256), 0, s, in, n, ld, cols, out);
     return cudaGetLastError();
 }
 
 __global__ void fill_kernel(double* p, long long n, double v) {
+    pdl_prologue();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         p[i] = v;
 }
 
 cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t s) {
     const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
-    fill_kernel<<<blocks, 256, 0, s>>>(p, n, v);
+    launch_k(fill_kernel, dim3(blocks), dim3(256), 0, s, p, n, v);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) gram_rows_kernel(const double* y, long long n, int pitch, int m, double* part) {
+    pdl_prologue();
     __shared__ double red[40];
     double acc[36];  // upper triangle of an 8 x 8 matrix
 #pragma unroll
@@ -308,21 +333,23 @@ __global__ void __launch_bounds__(256) gram_rows_kernel(const double* y, long lo
 cudaError_t launch_gram_rows(const double* y, long long n, int pitch, int m, double* part, int* grid_out, cudaStream_t s) {
     const int gx = (int)std::max<long long>(1, std::min<long long>(148, (n + 1023) / 1024));
     if (grid_out) *grid_out = gx;
-    gram_rows_kernel<<<gx, 256, 0, s>>>(y, n, pitch, m, part);
+    launch_k(gram_rows_kernel, dim3(gx), dim3(256), 0, s, y, n, pitch, m, part);
     return cudaGetLastError();
 }
 
 __global__ void count_rescale_kernel(double* z, const double* cnt, double n_total, int p) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < p) z[c] = cnt[c] > 0.0 ? z[c] / cnt[c] * n_total : 0.0;
 }
 
 cudaError_t launch_count_rescale(double* z, const double* cnt, double n_total, int p, cudaStream_t s) {
-    count_rescale_kernel<<<(p + 255) / 256, 256, 0, s>>>(z, cnt, n_total, p);
+    launch_k(count_rescale_kernel, dim3((p + 255) / 256), dim3(256), 0, s, z, cnt, n_total, p);
     return cudaGetLastError();
 }
 
 __global__ void rows_complete_kernel(const double* rowcnt, long long n, double p, int* flag) {
+    pdl_prologue();
     bool bad = false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         bad |= !(rowcnt[i] == p);
@@ -331,11 +358,12 @@ __global__ void rows_complete_kernel(const double* rowcnt, long long n, double p
 
 cudaError_t launch_rows_complete(const double* rowcnt, long long n, double p, int* flag, cudaStream_t s) {
     const int blocks = (int)std::max<long long>(1, std::min<long long>(592, (n + 255) / 256));
-    rows_complete_kernel<<<blocks, 256, 0, s>>>(rowcnt, n, p, flag);
+    launch_k(rows_complete_kernel, dim3(blocks), dim3(256), 0, s, rowcnt, n, p, flag);
     return cudaGetLastError();
 }
 
 __global__ void score_recurrence_kernel(double* S, long long n, int R, const double* c, const double* G) {
+    pdl_prologue();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         for (int a = 0; a < R; ++a) {
             double t = S[(size_t)a * n + i] - c[a];
@@ -347,21 +375,22 @@ __global__ void score_recurrence_kernel(double* S, long long n, int R, const dou
 
 cudaError_t launch_score_recurrence(double* S, long long n, int R, const double* c, const double* G, cudaStream_t s) {
     const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
-    score_recurrence_kernel<<<blocks, 256, 0, s>>>(S, n, R, c, G);
+    launch_k(score_recurrence_kernel, dim3(blocks), dim3(256), 0, s, S, n, R, c, G);
     return cudaGetLastError();
 }
 
 template <typename XT>
 __global__ void widen_kernel(const XT* src, double* dst, int n) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (double)src[i];
 }
 
 cudaError_t launch_widen(int dtype, const void* src, double* dst, int n, cudaStream_t s) {
     if (dtype == 0)
-        widen_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)src, dst, n);
+        launch_k(widen_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, s, (const float*)src, dst, n);
     else
-        widen_kernel<double><<<(n + 255) / 256, 256, 0, s>>>((const double*)src, dst, n);
+        launch_k(widen_kernel<double>, dim3((n + 255) / 256), dim3(256), 0, s, (const double*)src, dst, n);
     return cudaGetLastError();
 }
 

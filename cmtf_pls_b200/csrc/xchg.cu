@@ -24,6 +24,7 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
 
 // chunk = 32 consecutive elements of the exchanged vector; 256 threads = 32 columns x 8 groups
 __global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgArgs a) {
+    pdl_prologue();
     __shared__ double fold[8][33];
     const int slot = (int)(a.seq & 1ull);
     const size_t base = (size_t)slot * a.cap;
@@ -118,7 +119,7 @@ cudaError_t launch_xchg(const XchgArgs& a, cudaStream_t s) {
     const int n_chunks = (a.count + 31) / 32;
     if (a.do_qstop && (a.count > 32 || a.q_m > 8)) return cudaErrorInvalidValue;
     const int blocks = std::max(1, std::min(444, n_chunks));  // all CTAs must be co-resident: 3 per SM is safe
-    xchg_kernel<<<blocks, 256, 0, s>>>(a);
+    launch_k(xchg_kernel, dim3(blocks), dim3(256), 0, s, a);
     return cudaGetLastError();
 }
 
