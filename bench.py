@@ -41,7 +41,7 @@ UNIT = "GB/s"
 N_TOTAL = 1_000_000
 DIMS = (64, 64)
 M, LATENT, ERROR, R = 4, 12, 1.0, 10
-CPU_SAMPLE_ROWS = 4096
+CPU_SAMPLE_ROWS = int(os.environ.get("CMTF_BENCH_CPU_ROWS", "4096"))   # rows of the bounded CPU sample (tests shrink it)
 CPU_SAMPLE_R = 3
 
 
