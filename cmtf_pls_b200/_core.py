@@ -17,7 +17,6 @@ import numpy as np
 from . import _engine
 
 _engines: dict = {}
-_comm_ready: set = set()
 
 
 def _is_torch(a) -> bool:
@@ -55,12 +54,15 @@ def _torch_stream_handle(device: int) -> int:
 
 
 def get_engine(device: int) -> _engine.Engine:
+    """ONE engine per device (it caches X-sized working buffers); it follows torch's current stream from call
+    to call instead of being bound to the stream it was created under."""
     stream = _torch_stream_handle(device)
-    key = (device, stream)
-    eng = _engines.get(key)
+    eng = _engines.get(device)
     if eng is None or eng.h is None:
         eng = _engine.Engine(device, stream or None)
-        _engines[key] = eng
+        _engines[device] = eng
+    else:
+        eng.set_stream(stream)
     return eng
 
 
@@ -71,12 +73,19 @@ def _ensure_comm(eng, group):
     pg = None if group is True else group
     world = dist.get_world_size(pg)
     rank = dist.get_rank(pg)
-    key = (eng.device, id(pg) if pg is not None else 0, world)
-    if key in _comm_ready:
+    # readiness lives on the ENGINE (the communicator and the exchange buffers belong to its handle): a recreated
+    # engine, another group or another world size sets the communicator up again
+    key = (id(pg) if pg is not None else 0, rank, world)
+    if eng.comm_key == key and eng.comm_world == world:
+        return rank, world
+    if world <= 1:
+        eng.init_comm(b"\0" * 128, 0, 1)
+        eng.comm_key, eng.comm_world, eng.exchange = key, 1, "none"
         return rank, world
     box = [eng.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=dist.get_global_rank(pg, 0) if pg is not None else 0, group=pg)
     eng.init_comm(box[0], rank, world)
+    eng.exchange = "nccl"
     # one-shot peer-memory exchange for the per-trip all-reduces (NCCL stays the fallback)
     if os.environ.get("TPLS_NO_XCHG", "") == "":
         ok, why = True, ""
@@ -98,8 +107,35 @@ def _ensure_comm(eng, group):
             if rank == 0:
                 import warnings
                 warnings.warn(f"peer-memory exchange unavailable ({why or 'on another rank'}); NCCL is used for every all-reduce")
-    _comm_ready.add(key)
+        else:
+            eng.exchange = "peer"
+    eng.comm_key, eng.comm_world = key, world
     return rank, world
+
+
+def _ensure_single(eng):
+    eng.init_comm(b"\0" * 128, 0, 1)
+    eng.comm_key, eng.comm_world, eng.exchange = None, 1, "none"
+
+
+def weak_ref(a):
+    import weakref
+    try:
+        return weakref.ref(a)
+    except TypeError:   # an object that cannot be weakly referenced (e.g. a list): no reference at all
+        return None
+
+
+def isnan_of(ref, what):
+    """NaN positions of a weakly referenced training array, or a clear error when it is gone."""
+    a = ref() if ref is not None else None
+    if a is None:
+        raise RuntimeError(
+            f"{what}: the training array is no longer alive (the estimator references it weakly and does not "
+            "pickle it); np.isnan of the data you fitted on gives the same mask")
+    if _is_torch(a):
+        return a.isnan().cpu().numpy()
+    return np.isnan(np.asarray(a))
 
 
 def as_input(a, what):
@@ -144,7 +180,11 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
     dev = _device_of(Xs + [Y2], device)
     eng = get_engine(dev)
     if group is not None and group is not False:
-        _ensure_comm(eng, group)
+        _, world = _ensure_comm(eng, group)
+        if eng.comm_world != world:
+            raise _engine.TplsError(f"engine communicator spans {eng.comm_world} ranks, the process group {world}")
+    elif eng.comm_world != 1:
+        _ensure_single(eng)   # a sharded fit came before on this device: back to a single-GPU handle
     n, m = int(Y2.shape[0]), int(Y2.shape[1])
     R = int(n_components)
     for i, X in enumerate(Xs):
@@ -176,6 +216,7 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
             Y_mean=eng.y_mean(m),
             has_miss=[eng.has_missing(i) for i in range(len(Xs))],
             trips=eng.trips(R),
+            converged=eng.converged(R),
             stats=eng.stats(),
             profile=LazyProfile(eng) if profile else None,
             device=dev,
@@ -183,6 +224,7 @@ def run_fit(Xs, Y, n_components, tol, max_iter, device=None, group=None, overwri
         # host-side wall clock of the three stages of this call (ms): staging the inputs, the device fit
         # (returns when the GPU is done), fetching the fitted state
         t_host.append(time.perf_counter())
+        out["stats"]["exchange"] = eng.exchange
         out["stats"]["host_ms"] = dict(stage=1e3 * (t_host[1] - t_host[0]), fit=1e3 * (t_host[2] - t_host[1]),
                                        fetch=1e3 * (t_host[3] - t_host[2]))
     finally:

@@ -42,10 +42,12 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_double),
         ("covariance_mode", C.c_int64),
         ("last_transform_path", C.c_int64),
+        ("graph_launches", C.c_int64),
+        ("launches_per_trip", C.c_int64),
     ]
 
 
-KERNEL_CLASSES = ["colstat", "contract", "project", "deflate_contract", "residual", "rank1", "yside", "other", "nccl", "spare"]
+KERNEL_CLASSES = ["colstat", "contract", "project", "deflate_contract", "residual", "rank1", "yside", "other", "nccl", "xchg"]
 
 
 class Profile(C.Structure):
@@ -60,6 +62,7 @@ SIGNATURES = {
     "tpls_last_error": (C.c_char_p, [_H]),
     "tpls_create": (C.c_int, [C.POINTER(_H), C.c_int, _P]),
     "tpls_destroy": (C.c_int, [_H]),
+    "tpls_set_stream": (C.c_int, [_H, _P]),
     "tpls_comm_unique_id": (C.c_int, [_P]),
     "tpls_comm_init": (C.c_int, [_H, _P, C.c_int, C.c_int]),
     "tpls_comm_xchg_handle": (C.c_int, [_H, _P]),
@@ -77,6 +80,7 @@ SIGNATURES = {
     "tpls_get_y_mean": (C.c_int, [_H, _P]),
     "tpls_get_has_missing": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int)]),
     "tpls_get_trips": (C.c_int, [_H, _P]),
+    "tpls_get_converged": (C.c_int, [_H, _P]),
     "tpls_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
     "tpls_get_profile": (C.c_int, [_H, C.POINTER(Profile)]),
     "tpls_release_data": (C.c_int, [_H]),
@@ -139,6 +143,10 @@ class Engine:
             raise TplsError(self.lib.tpls_last_error(None).decode())
         self.device = device
         self._keep = []
+        self._stream = stream or 0
+        self.comm_key = None      # (id of the process group, rank, world) the handle's communicator belongs to
+        self.comm_world = 1
+        self.exchange = "none"    # "peer" (CUDA IPC exchange kernels), "nccl", or "none" (single GPU)
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
@@ -154,6 +162,12 @@ class Engine:
     def _ck(self, rc):
         if rc != 0:
             raise TplsError(self.lib.tpls_last_error(self.h).decode())
+
+    def set_stream(self, stream: int):
+        """Follow the caller's current CUDA stream (0: the handle's private stream)."""
+        if stream != self._stream:
+            self._ck(self.lib.tpls_set_stream(self.h, C.c_void_p(stream) if stream else None))
+            self._stream = stream
 
     # ---- multi-GPU ----
     def unique_id(self) -> bytes:
@@ -193,8 +207,10 @@ class Engine:
         self._ck(self.lib.tpls_set_row_weights(self.h, _ptr(w), int(w.shape[0])))
 
     def fit(self, n_tensors, n_components, tol, max_iter, flags=0):
-        self._ck(self.lib.tpls_fit(self.h, n_tensors, n_components, float(tol), int(max_iter), flags))
-        self._keep.clear()
+        try:
+            self._ck(self.lib.tpls_fit(self.h, n_tensors, n_components, float(tol), int(max_iter), flags))
+        finally:
+            self._keep.clear()   # the staged inputs are not pinned by a failed fit either
 
     # ---- results ----
     def _host_out(self, rows, cols):
@@ -259,6 +275,11 @@ class Engine:
         out = np.empty(R, dtype=np.int32)
         self._ck(self.lib.tpls_get_trips(self.h, out.ctypes.data))
         return out
+
+    def converged(self, R):
+        out = np.empty(R, dtype=np.int32)
+        self._ck(self.lib.tpls_get_converged(self.h, out.ctypes.data))
+        return out.astype(bool)
 
     def stats(self) -> dict:
         s = Stats()

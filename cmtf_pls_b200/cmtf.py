@@ -83,23 +83,25 @@ class ctPLS(Mapping):
         self.Xs_hasMiss = st["has_miss"]
         if any(self.Xs_hasMiss):
             print("At least one X has missing values")
-        self._Xs_ref = Xs
-        self._Y_ref = Y
+        self._Xs_ref = [_core.weak_ref(X) for X in Xs]   # for Xs_miss / get_q2y only; not kept alive
+        self._Y_ref = _core.weak_ref(Y)
         self.n_iter_ = st["trips"]
         # the reference is silent when max_iter is exhausted (tpls.py:79-107); here it can be asked
-        self.converged_ = st["trips"] < max_iter
+        self.converged_ = st["converged"]
         self.stats_ = st["stats"]
         self._profile = st["profile"]
         self._device = st["device"]
         if verbose:
             for a, k in enumerate(self.n_iter_):
-                if k < max_iter:
+                if self.converged_[a]:
                     print("Comp {}: converged after {} iterations".format(a, k - 1))
 
     @property
     def Xs_miss(self):
         """Positions of missing values of the training tensors (cmtf.py:80-82), computed on demand."""
-        return [X.isnan().cpu().numpy() if _core._is_torch(X) else np.isnan(X) for X in self._Xs_ref]
+        refs = getattr(self, "_Xs_ref", None) or [None] * self.Xs_len
+        return [np.zeros(self.Xs_shape[ti], dtype=bool) if not self.Xs_hasMiss[ti]
+                else _core.isnan_of(refs[ti], f"Xs_miss[{ti}]") for ti in range(self.Xs_len)]
 
     @property
     def profile_(self):

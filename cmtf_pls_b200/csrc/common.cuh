@@ -10,19 +10,23 @@ namespace tpls {
 // Device-resident control block of one NIPALS component (SURVEY.md §7 hard part
 // 2): every kernel of inner trip k returns at once when the component already
 // converged at an earlier trip, so the host may enqueue trips ahead of the
-// convergence test without a sync.
+// convergence test without a sync, and the trailing contraction of the last trip
+// of a device-resident (graph WHILE) loop does no work.
 // ---------------------------------------------------------------------------
 struct Ctrl {
     int done_trip;    // -1 while iterating, else the trip index that met the stop test
     int trips_taken;  // trips that did real work so far
     double last_d2;   // ||u_old - u_new||^2 of the last executed trip (global after allreduce)
-    int pad[2];
+    int trip;         // index of the trip in flight; advanced by the kernel that takes the stop decision
+    int stop;         // 1 once the component converged or ran max_iter trips: every later loop kernel returns at once
 };
 
-__device__ __forceinline__ bool trip_is_dead(const Ctrl* c, int trip) {
+// The inner loop of a component is a fixed sequence of launches (the "trip body") whose arguments do not depend
+// on the trip index, so that it can be the body of a CUDA-graph WHILE node or be enqueued ahead by the host.
+// `trip` is kept in the argument blocks of the single-operator entry points but no longer read.
+__device__ __forceinline__ bool trip_is_dead(const Ctrl* c, int /*trip*/) {
     if (c == nullptr) return false;
-    int d = *reinterpret_cast<const volatile int*>(&c->done_trip);
-    return d >= 0 && d < trip;
+    return *reinterpret_cast<const volatile int*>(&c->stop) != 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -38,6 +42,10 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 bool pdl_enabled();  // small.cu: TPLS_PDL=1 in the environment (read once)
+// The next launch of this thread is a plain one even with PDL on (the first kernel after a graph WHILE node: a
+// conditional node cannot be the source of a programmatic edge).
+void pdl_hold_next();
+bool pdl_take_hold();
 
 // kernel<<<grid, block, smem, stream>>>(args...) with the optional PDL attribute
 template <typename... KArgs, typename... Args>
@@ -51,7 +59,7 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && !pdl_take_hold()) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

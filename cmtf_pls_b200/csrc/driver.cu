@@ -133,6 +133,7 @@ void prof_collect(tpls_handle h) {
 
 int allreduce_nccl(tpls_handle h, double* buf, size_t count) {
     if (h->world <= 1 || count == 0) return 0;
+    if (h->capturing) return fail(h, "internal error: an NCCL all-reduce inside the captured fit");
     ProfScope ps(h, TPLS_K_NCCL, 0.0);
     CKN(g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream));
     h->stats.collectives++;
@@ -141,11 +142,10 @@ int allreduce_nccl(tpls_handle h, double* buf, size_t count) {
 
 // fills the communicator part of an exchange and launches it (never skipped: see xchg.cuh)
 int xchg_launch(tpls_handle h, XchgArgs& a) {
-    ProfScope ps(h, TPLS_K_NCCL, 0.0);
+    ProfScope ps(h, TPLS_K_XCHG, 0.0);
     a.cap = h->xchg_cap;
     a.rank = h->rank;
     a.world = h->world;
-    a.seq = ++h->xchg_seq;
     for (int r = 0; r < h->world; ++r) {
         char* base = static_cast<char*>(h->xchg_peer[r]);
         a.flags[r] = reinterpret_cast<unsigned long long*>(base);
@@ -154,22 +154,55 @@ int xchg_launch(tpls_handle h, XchgArgs& a) {
     char* mine = static_cast<char*>(h->xchg_buf);
     a.done_ctr = reinterpret_cast<unsigned int*>(mine + 512);
     a.err = reinterpret_cast<int*>(mine + 520);
+    a.seq_ctr = reinterpret_cast<unsigned long long*>(mine + 528);
     CK(launch_xchg(a, h->stream));
     h->stats.kernel_launches++;
     h->stats.collectives++;
     return 0;
 }
 
+static bool xchg_fits(tpls_handle h, size_t count) { return h->xchg_ready && count <= (size_t)h->xchg_cap; }
+
 // Sum of a small replicated vector over the ranks: the one-shot peer-memory exchange when it is set up
 // (and the vector fits its slots), NCCL otherwise.
 int allreduce(tpls_handle h, double* buf, size_t count) {
     if (h->world <= 1 || count == 0) return 0;
-    if (!h->xchg_ready || count > (size_t)h->xchg_cap) return allreduce_nccl(h, buf, count);
+    if (!xchg_fits(h, count)) return allreduce_nccl(h, buf, count);
     XchgArgs a{};
     a.in = buf;
     a.out = buf;
     a.count = (int)count;
     return xchg_launch(h, a);
+}
+
+static int fold_sum_tail(tpls_handle h, const SetList& sl, size_t base_off, size_t count, const Ctrl* ctrl, bool local_only,
+                         XchgArgs* tail) {
+    double* base = h->arena + base_off;
+    if (h->world > 1 && !local_only && xchg_fits(h, count)) {
+        XchgArgs xa{};
+        if (tail) xa = *tail;
+        xa.n_sets = sl.n;
+        for (int i = 0; i < sl.n; ++i) xa.sets[i] = sl.s[i];
+        xa.out = base;
+        xa.count = (int)count;
+        return xchg_launch(h, xa);
+    }
+    FoldArgs f{};
+    f.n_sets = sl.n;
+    for (int i = 0; i < sl.n; ++i) f.sets[i] = sl.s[i];
+    f.out = base;
+    f.ctrl = ctrl;
+    {
+        ProfScope ps(h, TPLS_K_OTHER, 0.0);
+        CK(launch_fold_sets(f, h->stream));
+        h->stats.kernel_launches++;
+    }
+    if (h->world > 1 && !local_only) TRY(allreduce_nccl(h, base, count));
+    return 0;
+}
+
+int fold_sum(tpls_handle h, const SetList& sl, size_t base_off, size_t count, const Ctrl* ctrl, bool local_only) {
+    return fold_sum_tail(h, sl, base_off, count, ctrl, local_only, nullptr);
 }
 
 // ---- pass wrappers that keep the launch / byte counters ----
@@ -209,6 +242,9 @@ int row_pass(tpls_handle h, int dtype, int mode, RowPassArgs& a, int cls) {
         f.epi = a.epi;
         f.div = a.div;
         f.d2part = a.d2part;
+        f.y = a.y;
+        f.pitch_y = a.pitch_y;
+        f.qpart = a.qpart;
         f.ctrl = a.ctrl;
         f.trip = a.trip;
         CK(launch_row_finish(f, nullptr, h->stream));
@@ -260,6 +296,14 @@ int copy_out_transposed(tpls_handle h, const double* colmajor, long long rows, i
     return 0;
 }
 
+void drop_graph(tpls_handle h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    h->graph_exec = nullptr;
+    h->graph = nullptr;
+    h->graph_key = 0;
+}
+
 }  // namespace tpls_drv
 
 // ===========================================================================
@@ -293,11 +337,11 @@ int tpls_create(tpls_handle* out, int device, void* cuda_stream) {
     if (cuda_stream) {
         h->stream = (cudaStream_t)cuda_stream;
     } else {
-        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        if (cudaStreamCreateWithFlags(&h->private_stream, cudaStreamNonBlocking) != cudaSuccess) {
             delete h;
             return fail(nullptr, "cudaStreamCreate failed");
         }
-        h->own_stream = true;
+        h->stream = h->private_stream;
     }
     cudaEventCreate(&h->ev_start);
     cudaEventCreate(&h->ev_stop);
@@ -319,9 +363,12 @@ int tpls_destroy(tpls_handle h) {
     if (h->slab) pool_put(h, h->slab);
     if (h->tmp_buf) pool_put(h, h->tmp_buf);
     pool_trim(h);
+    drop_graph(h);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->body_stream) cudaStreamDestroy(h->body_stream);
     if (h->xchg_buf) {
-        for (int r = 0; r < h->world; ++r)
-            if (r != h->rank && h->xchg_peer[r]) cudaIpcCloseMemHandle(h->xchg_peer[r]);
+        for (int r = 0; r < kXchgMaxRanks; ++r)
+            if (h->xchg_peer[r] && h->xchg_peer[r] != h->xchg_buf) cudaIpcCloseMemHandle(h->xchg_peer[r]);
         cudaFree(h->xchg_buf);
     }
     if (h->comm) g_nccl.CommDestroy(h->comm);
@@ -334,8 +381,22 @@ int tpls_destroy(tpls_handle h) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
-    if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->private_stream) cudaStreamDestroy(h->private_stream);
     delete h;
+    return 0;
+}
+
+int tpls_set_stream(tpls_handle h, void* cuda_stream) {
+    if (!h) return fail(nullptr, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t next = (cudaStream_t)cuda_stream;
+    if (next == nullptr) {
+        if (!h->private_stream) CK(cudaStreamCreateWithFlags(&h->private_stream, cudaStreamNonBlocking));
+        next = h->private_stream;
+    }
+    if (next == h->stream) return 0;
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = next;
     return 0;
 }
 
@@ -351,6 +412,14 @@ int tpls_comm_unique_id(void* id128) {
 
 int tpls_comm_init(tpls_handle h, const void* id128, int rank, int world) {
     if (!h) return fail(nullptr, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    drop_graph(h);
+    if (h->comm) {  // re-initialisation: release the previous communicator and exchange set-up
+        g_nccl.CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    h->xchg_ready = false;
     if (world <= 1) {
         h->rank = 0;
         h->world = 1;
@@ -358,7 +427,6 @@ int tpls_comm_init(tpls_handle h, const void* id128, int rank, int world) {
     }
     const char* why = "";
     if (!g_nccl.load(&why)) return fail(h, "tpls_comm_init: %s", why);
-    CK(cudaSetDevice(h->device));
     NcclUniqueId id;
     memcpy(&id, id128, sizeof id);
     CKN(g_nccl.CommInitRank(&h->comm, world, id, rank));
@@ -394,6 +462,15 @@ int tpls_comm_xchg_open(tpls_handle h, const void* handles) {
     }
     if (!h->xchg_buf) return fail(h, "tpls_comm_xchg_open: call tpls_comm_xchg_handle first");
     CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    drop_graph(h);  // a captured fit holds the old peer addresses
+    for (int r = 0; r < kXchgMaxRanks; ++r) {  // mappings of an earlier set-up
+        if (h->xchg_peer[r] && h->xchg_peer[r] != h->xchg_buf) cudaIpcCloseMemHandle(h->xchg_peer[r]);
+        h->xchg_peer[r] = nullptr;
+    }
+    // flags, counters and the sequence number start from zero on every rank (the caller's all-gather of the
+    // "opened" verdicts orders this before any peer's first exchange)
+    CK(cudaMemset(h->xchg_buf, 0, kXchgHeaderBytes));
     for (int r = 0; r < h->world; ++r) {
         if (r == h->rank) {
             h->xchg_peer[r] = h->xchg_buf;
@@ -403,7 +480,6 @@ int tpls_comm_xchg_open(tpls_handle h, const void* handles) {
         memcpy(&hnd, static_cast<const char*>(handles) + 64 * (size_t)r, sizeof hnd);
         CK(cudaIpcOpenMemHandle(&h->xchg_peer[r], hnd, cudaIpcMemLazyEnablePeerAccess));
     }
-    h->xchg_seq = 0;
     h->xchg_ready = true;
     return 0;
 }
@@ -509,11 +585,13 @@ static int layout_fit(tpls_handle h, int L, int R) {
     h->R = R;
     h->gy = make_geom(n, h->m, h->pitch_y, 8, h->sm_count);
     h->gy_row = make_row_geom(n, h->m, h->pitch_y, 8, h->sm_count, false);
+    // up to kMaxFusedResp responses the Y side of a trip rides on the X passes: the contraction stages the rows of Y
+    const int y_row_bytes = h->pitch_y <= kMaxFusedResp ? h->pitch_y * 8 : 0;
     // arena layout
     size_t off = 0;
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
-        t.g = make_geom(n, t.p, t.pitch, t.elem, h->sm_count);
+        t.g = make_geom(n, t.p, t.pitch, t.elem, h->sm_count, y_row_bytes);
         t.off_colsum = off;
         off += t.pitch;
         t.off_colcnt = off;
@@ -525,6 +603,8 @@ static int layout_fit(tpls_handle h, int L, int R) {
     off += h->pitch_y;
     h->off_n = off;
     off += 1;
+    h->off_nmiss = off;
+    off += L;
     h->off_stats_end = off;
     off = (off + 1) / 2 * 2;
     h->off_zcat = off;
@@ -577,6 +657,10 @@ static int layout_fit(tpls_handle h, int L, int R) {
     TRY(dev_alloc(h, (void**)&h->dotpart, sizeof(double) * 148 * 64, tr));
     TRY(dev_alloc(h, (void**)&h->grampart, sizeof(double) * 148 * 64, tr));
     TRY(dev_alloc(h, (void**)&h->q_prev, sizeof(double) * 8, tr));
+    TRY(dev_alloc(h, (void**)&h->qpart, sizeof(double) * 2048 * kMaxFusedResp, tr));
+    TRY(dev_alloc(h, (void**)&h->e0vec, sizeof(double) * kMaxFusedResp, tr));
+    TRY(dev_alloc(h, (void**)&h->nloc, sizeof(double) * 2, tr));
+    TRY(dev_alloc(h, (void**)&h->conv_dev, sizeof(int) * R, tr));
     TRY(dev_alloc(h, (void**)&h->scratch_ss, sizeof(double) * 8, tr));
     TRY(dev_alloc(h, (void**)&h->trips_dev, sizeof(int) * R, tr));
     TRY(dev_alloc(h, (void**)&h->ymiss_flag, sizeof(int) * 4, tr));
@@ -665,11 +749,15 @@ static int component_tail(tpls_handle h, int R, int a, double* ss_y, bool stream
             CK(launch_multi_dot(d, h->dotpart, &gx, st));
             h->stats.kernel_launches++;
         }
-        TRY(reduce_cols(h, h->dotpart, A + h->off_dots, d.npairs, d.npairs, gx, nullptr, nullptr, 0, nullptr, 0));
-        TRY(allreduce(h, A + h->off_dots, d.npairs));
+        {
+            SetList sl;
+            sl.add(h->dotpart, gx, d.npairs, d.npairs, 0);
+            TRY(fold_sum(h, sl, h->off_dots, d.npairs, nullptr));
+        }
         {
             ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-            CK(launch_solve_coef(A + h->off_dots, h->gram, h->coef, R, a, h->ctrl, stream_mode ? h->trips_dev : nullptr, st));
+            CK(launch_solve_coef(A + h->off_dots, h->gram, h->coef, R, a, h->ctrl, stream_mode ? h->trips_dev : nullptr,
+                                 stream_mode ? h->conv_dev : nullptr, st));
             h->stats.kernel_launches++;
         }
     }
@@ -689,7 +777,12 @@ static int component_tail(tpls_handle h, int R, int a, double* ss_y, bool stream
         c.sspart = h->sspart_y;
         c.row_sw = h->row_w;
         TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c, TPLS_K_YSIDE));
-        TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y + a + 1, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
+        // the residual norm of Y is folded together with the norms of the X pass that follows (see fit_streaming)
+        if (!stream_mode) {
+            SetList sl;
+            sl.add(h->sspart_y, h->gy.grid_x * h->gy.n_slabs, 1, 1, 0);
+            TRY(fold_sum(h, sl, (size_t)(ss_y + a + 1 - A), 1, nullptr, true));
+        }
     }
     return 0;
 }
@@ -712,6 +805,47 @@ static bool cov_supported(tpls_handle h, int L) {
     return true;
 }
 
+static void r1_config(tpls_handle h, int L, size_t* r1_smem, bool* r1_use_smem) {
+    *r1_smem = 0;
+    *r1_use_smem = true;
+    for (int l = 0; l < L; ++l) *r1_smem = std::max(*r1_smem, h->x[l].r1_ws * sizeof(double));
+    if (*r1_smem > 200 * 1024) {
+        *r1_use_smem = false;
+        *r1_smem = 0;
+    }
+}
+
+// observed entries per row of a masked tensor (constant during the fit): one counting row pass with zero weights
+static int count_rows(tpls_handle h, Tensor& t) {
+    RowPassArgs r{};
+    r.g = t.gr_cnt;
+    r.x_in = t.src;
+    r.col_w = t.wkron;  // still all zero
+    r.t_out = h->svec;
+    r.tpart = t.tpart;
+    r.cpart = t.cpart;
+    r.rowcnt = t.rowcnt;
+    r.epi = 0;
+    r.div = 1.0;
+    TRY(row_pass(h, t.dtype, 2, r));
+    t.rowcnt_ready = true;
+    return 0;
+}
+
+// Y'Y of the current (deflated) Y, summed over the ranks: the stop test then needs no pass over the samples and no
+// collective of its own (||u_old - u_new||^2 = dq^T Y'Y dq, u = Y q)
+static int gram_y(tpls_handle h) {
+    int gx = 1;
+    {
+        ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+        CK(launch_gram_rows(h->y_work, h->n, h->pitch_y, h->m, h->grampart, &gx, h->stream));
+        h->stats.kernel_launches++;
+    }
+    SetList sl;
+    sl.add(h->grampart, gx, h->m * h->m, h->m * h->m, 0);
+    return fold_sum(h, sl, h->off_gram_y, (size_t)h->m * h->m, nullptr);
+}
+
 static int fit_covariance(tpls_handle h, int L, int R, double tol, int max_iter, int flags, double* ss_y) {
     cudaStream_t st = h->stream;
     const long long n = h->n;
@@ -720,35 +854,18 @@ static int fit_covariance(tpls_handle h, int L, int R, double tol, int max_iter,
 
     size_t r1_smem = 0;
     bool r1_use_smem = true;
-    for (int l = 0; l < L; ++l) r1_smem = std::max(r1_smem, h->x[l].r1_ws * sizeof(double));
-    if (r1_smem > 200 * 1024) {
-        r1_use_smem = false;
-        r1_smem = 0;
-    }
+    r1_config(h, L, &r1_smem, &r1_use_smem);
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
         t.cov_mr = t.masked ? pow2_at_least(2 * M) : pow2_at_least(M);
-        if (t.masked) {
-            // observed entries per row (constant during the fit): one counting row pass with zero weights
-            RowPassArgs r{};
-            r.g = t.gr_cnt;
-            r.x_in = t.src;
-            r.col_w = t.wkron;  // still all zero
-            r.t_out = h->svec;
-            r.tpart = t.tpart;
-            r.cpart = t.cpart;
-            r.rowcnt = t.rowcnt;
-            r.epi = 0;
-            r.div = 1.0;
-            TRY(row_pass(h, t.dtype, 2, r));
-            t.rowcnt_ready = true;
-        }
+        if (t.masked) TRY(count_rows(h, t));
     }
 
     for (int a = 0; a < R; ++a) {
         double* Ta = h->T + (size_t)a * n;
         double* Ua = h->U + (size_t)a * n;
         // ---- cross-covariance pass: centring (a == 0) or the deflation by component a-1 fused in ----
+        SetList cs, ss;
         for (int l = 0; l < L; ++l) {
             Tensor& t = h->x[l];
             CovPassArgs c{};
@@ -772,18 +889,19 @@ static int fit_covariance(tpls_handle h, int L, int R, double tol, int max_iter,
                 h->stats.kernel_launches++;
                 h->stats.streamed_bytes += bytes;
             }
-            TRY(reduce_cols(h, t.covpart, A + t.off_c, (int)c.c_stride, (int)c.c_stride, t.gc.grid_x, t.sspart_cov,
-                            A + t.off_ss + a, t.gc.grid_x * t.gc.n_slabs, nullptr, 0));
+            cs.add(t.covpart, t.gc.grid_x, (int)c.c_stride, (int)c.c_stride, t.off_c - h->off_cov);
+            ss.add(t.sspart_cov, t.gc.grid_x * t.gc.n_slabs, 1, 1, t.off_ss + a - h->off_ss);
         }
-        // ---- Y'Y of the current Y for the stop test ----
+        // ---- Y'Y of the current Y for the stop test; C of every tensor and Y'Y cross the ranks together ----
+        int gx = 1;
         {
             ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-            int gx = 1;
             CK(launch_gram_rows(h->y_work, n, h->pitch_y, M, h->grampart, &gx, st));
             h->stats.kernel_launches++;
-            TRY(reduce_cols(h, h->grampart, A + h->off_gram_y, M * M, M * M, gx, nullptr, nullptr, 0, nullptr, 0));
         }
-        TRY(allreduce(h, A + h->off_cov, h->cov_len));
+        cs.add(h->grampart, gx, M * M, M * M, h->off_gram_y - h->off_cov);
+        TRY(fold_sum(h, cs, h->off_cov, h->cov_len, nullptr));
+        TRY(fold_sum(h, ss, h->off_ss, h->ss_len, nullptr, true));
         // ---- the whole inner iteration of this component, on the device ----
         {
             CovLoopArgs la{};
@@ -797,6 +915,7 @@ static int fit_covariance(tpls_handle h, int L, int R, double tol, int max_iter,
             la.qvec = h->qvec;
             la.pitch_y = h->pitch_y;
             la.trips_out = h->trips_dev + a;
+            la.conv_out = h->conv_dev + a;
             for (int l = 0; l < L; ++l) {
                 Tensor& t = h->x[l];
                 fill_rank1_task(h, t, a, la.t[l], r1_use_smem);
@@ -836,6 +955,7 @@ static int fit_covariance(tpls_handle h, int L, int R, double tol, int max_iter,
         TRY(component_tail(h, R, a, ss_y, false));
     }
     // ---- residual norm after the last component ----
+    SetList ss;
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
         ColPassArgs c{};
@@ -847,9 +967,371 @@ static int fit_covariance(tpls_handle h, int L, int R, double tol, int max_iter,
         c.sspart = t.sspart;
         c.row_sw = h->row_w;
         TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_SUMSQ, c));
-        TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, t.sspart, A + t.off_ss + R, t.g.grid_x * t.g.n_slabs, nullptr, 0));
+        ss.add(t.sspart, t.g.grid_x * t.g.n_slabs, 1, 1, t.off_ss + R - h->off_ss);
+    }
+    TRY(fold_sum(h, ss, h->off_ss, h->ss_len, nullptr, true));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// streaming component loop (tpls.py:76-120, cmtf.py:88-140)
+//
+// The inner iteration of a component is a FIXED sequence of launches, the trip body, whose arguments do not
+// depend on the trip index (the trip counter and the stop flag live in the control block on the device):
+//
+//     fold / exchange Z -> rank-1 step -> projection of every tensor (the last one also forms the partials of
+//     q = Y't in its epilogue) -> fold / exchange q + normalise + stop test -> contraction of every tensor with
+//     u = Y q formed on the fly from the staged rows of Y (skipped once the stop flag is up)
+//
+// i.e. 3 + 2L launches per trip and no pass over Y.  The body is either captured once per component as the body of
+// a CUDA-graph WHILE node (tpls_fit then is ONE graph launch and the host plays no part in the loop), or enqueued
+// by the host one trip ahead of the last stop flag it has seen (profiling, NCCL collectives).
+// With more than kMaxFusedResp responses the Y side keeps its own passes and the explicit ||u_old - u_new||^2.
+// ---------------------------------------------------------------------------
+struct StreamPlan {
+    int L, R, max_iter, flags;
+    double tol;
+    bool fused;        // Y side fused into the X passes (pitch_y <= kMaxFusedResp)
+    size_t r1_smem;
+    bool r1_use_smem;
+    double* ss_y;
+};
+
+static int contraction(tpls_handle h, const StreamPlan& P, int a, bool in_loop) {
+    (void)in_loop;
+    const long long n = h->n;
+    for (int l = 0; l < P.L; ++l) {
+        Tensor& t = h->x[l];
+        ColPassArgs c{};
+        c.g = t.g;
+        c.x_in = t.work;
+        c.zpart = t.zpart;
+        c.ctrl = h->ctrl;
+        if (P.fused) {
+            c.y = h->y_work;
+            c.q = h->qvec;
+            c.pitch_y = h->pitch_y;
+        } else {
+            c.row_u = h->U + (size_t)a * n;
+        }
+        TRY(col_pass(h, t.dtype, t.masked, PF_CONTRACT, c));
     }
     return 0;
+}
+
+static int trip_body(tpls_handle h, const StreamPlan& P, int a, unsigned long long cond, bool has_cond) {
+    cudaStream_t st = h->stream;
+    const long long n = h->n;
+    const int L = P.L;
+    double* A = h->arena;
+    double* Ta = h->T + (size_t)a * n;
+    double* Ua = h->U + (size_t)a * n;
+    LoopEnd le{};
+    le.tol = P.tol;
+    le.max_iter = P.max_iter;
+    le.has_cond = has_cond ? 1 : 0;
+    le.cond = cond;
+    // ---- Z of every tensor: second reduction stage (+ the sum over the ranks) in one launch ----
+    {
+        SetList sl;
+        for (int l = 0; l < L; ++l) {
+            Tensor& t = h->x[l];
+            sl.add(t.zpart, t.g.grid_x, t.pitch, t.pitch, t.off_z - h->off_zcat);
+        }
+        TRY(fold_sum(h, sl, h->off_zcat, h->zcat_len, h->ctrl));
+    }
+    // ---- K3: rank-1 weight vectors, one CTA per tensor ----
+    {
+        Rank1Args ra{};
+        ra.n_tasks = L;
+        ra.tol = P.tol;
+        ra.normalize_on_break = (P.flags & TPLS_FIT_NORMALIZE_ON_BREAK) ? 1 : 0;
+        ra.ctrl = h->ctrl;
+        for (int l = 0; l < L; ++l) fill_rank1_task(h, h->x[l], a, ra.t[l], P.r1_use_smem);
+        ProfScope ps(h, TPLS_K_RANK1, 0.0);
+        CK(launch_rank1(ra, P.r1_smem, st));
+        h->stats.kernel_launches++;
+    }
+    // ---- K2: t = X x_2 w2 x_3 w3 ..., averaged over the coupled tensors (cmtf.py:120) ----
+    int q_parts = 0;
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        RowPassArgs r{};
+        r.g = t.gr;
+        r.x_in = t.work;
+        r.col_w = t.wkron + (size_t)a * t.pitch;
+        r.t_out = Ta;
+        r.tpart = t.tpart;
+        r.cpart = t.cpart;
+        r.rowcnt = t.rowcnt;
+        r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
+        r.div = (double)L;
+        r.ctrl = h->ctrl;
+        if (P.fused && l == L - 1) {  // K4 fused: partials of q = Y't over the final (averaged) scores
+            r.y = h->y_work;
+            r.pitch_y = h->pitch_y;
+            r.qpart = h->qpart;
+            q_parts = d2_grid(t.gr);
+        }
+        TRY(row_pass(h, t.dtype, t.masked ? 1 : 0, r));
+    }
+    if (P.fused) {
+        // ---- q = Y't / ||.|| and the stop test dq^T (Y'Y) dq (tpls.py:100-107) on the kernel that finishes the
+        //      reduction of q: the exchange kernel across ranks, a single CTA on one GPU ----
+        if (h->world > 1 && xchg_fits(h, h->pitch_y)) {
+            XchgArgs xa{};
+            xa.do_qstop = 1;
+            xa.q_m = h->m;
+            xa.q_pitch = h->pitch_y;
+            xa.qcol = h->Q + (size_t)a * h->m;
+            xa.qvec = h->qvec;
+            xa.gram = A + h->off_gram_y;
+            xa.q_prev = h->q_prev;
+            xa.ctrl = h->ctrl;
+            xa.loop_end = le;
+            SetList sl;
+            sl.add(h->qpart, q_parts, kMaxFusedResp, h->pitch_y, 0);
+            TRY(fold_sum_tail(h, sl, h->off_q, h->pitch_y, h->ctrl, false, &xa));
+        } else {
+            const double* part = h->qpart;
+            int n_parts = q_parts, stride = kMaxFusedResp;
+            if (h->world > 1) {
+                SetList sl;
+                sl.add(h->qpart, q_parts, kMaxFusedResp, h->pitch_y, 0);
+                TRY(fold_sum(h, sl, h->off_q, h->pitch_y, h->ctrl));
+                part = A + h->off_q;
+                n_parts = 1;
+                stride = h->pitch_y;
+            }
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_reduce_q_stop(part, n_parts, stride, A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec,
+                                    A + h->off_gram_y, h->q_prev, h->ctrl, le, st));
+            h->stats.kernel_launches++;
+        }
+    } else {
+        // ---- many responses: q = Y't and u = Y q keep their own passes over Y, explicit ||u_old - u_new||^2 ----
+        {
+            ColPassArgs c{};
+            c.g = h->gy;
+            c.x_in = h->y_work;
+            c.row_u = Ta;
+            c.zpart = h->zpart_y;
+            c.ctrl = h->ctrl;
+            TRY(col_pass(h, TPLS_F64, false, PF_CONTRACT, c, TPLS_K_YSIDE));
+            SetList sl;
+            sl.add(h->zpart_y, h->gy.grid_x, h->pitch_y, h->pitch_y, 0);
+            TRY(fold_sum(h, sl, h->off_q, h->pitch_y, h->ctrl));
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, 0, st));
+            h->stats.kernel_launches++;
+        }
+        RowPassArgs r{};
+        r.g = h->gy_row;
+        r.x_in = h->y_work;
+        r.col_w = h->qvec;
+        r.t_out = Ua;
+        r.epi = 0;
+        r.div = 1.0;
+        r.d2part = h->d2part;
+        r.ctrl = h->ctrl;
+        TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
+        const int nd2 = d2_grid(h->gy_row);
+        if (h->world > 1 && xchg_fits(h, 1)) {
+            XchgArgs xa{};
+            xa.do_stop = 1;
+            xa.ctrl = h->ctrl;
+            xa.loop_end = le;
+            SetList sl;
+            sl.add(h->d2part, nd2, 1, 1, 0);
+            TRY(fold_sum_tail(h, sl, h->off_d2, 1, h->ctrl, false, &xa));
+        } else {
+            const double* parts = h->d2part;
+            int np = nd2;
+            if (h->world > 1) {
+                SetList sl;
+                sl.add(h->d2part, nd2, 1, 1, 0);
+                TRY(fold_sum(h, sl, h->off_d2, 1, h->ctrl));
+                parts = A + h->off_d2;
+                np = 1;
+            }
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_stop(h->ctrl, parts, np, le, st));
+            h->stats.kernel_launches++;
+        }
+    }
+    // ---- K1: Z = X x_1 u for the next trip (returns at once when the stop flag is up) ----
+    const double before = h->stats.streamed_bytes;
+    TRY(contraction(h, P, a, true));
+    h->body[a].tail_streamed = h->stats.streamed_bytes - before;
+    return 0;
+}
+
+// runs the trip body until the stop flag is up: a WHILE node while capturing, host-driven otherwise
+static int run_loop(tpls_handle h, const StreamPlan& P, int a) {
+    tpls_ctx::BodyCount& bc = h->body[a];
+    bc = tpls_ctx::BodyCount{};
+    const tpls_stats before = h->stats;
+    auto account = [&]() {
+        bc.launches = h->stats.kernel_launches - before.kernel_launches;
+        bc.collectives = h->stats.collectives - before.collectives;
+        bc.streamed = h->stats.streamed_bytes - before.streamed_bytes;
+    };
+    if (h->capturing) {
+        cudaStreamCaptureStatus status;
+        cudaGraph_t g = nullptr;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t n_deps = 0;
+        const cudaGraphEdgeData* edges = nullptr;  // programmatic (PDL) edges carry data a plain query would lose
+        CK(cudaStreamGetCaptureInfo_v3(h->stream, &status, nullptr, &g, &deps, &edges, &n_deps));
+        if (status != cudaStreamCaptureStatusActive) return fail(h, "internal error: capture is not active");
+        cudaGraphConditionalHandle cond;
+        CK(cudaGraphConditionalHandleCreate(&cond, g, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np{};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        // full dependencies on whatever precedes the loop (the edge kind is a property of the downstream launch)
+        CK(cudaGraphAddNode(&node, g, deps, n_deps, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        cudaStream_t outer = h->stream;
+        CK(cudaStreamBeginCaptureToGraph(h->body_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        h->stream = h->body_stream;
+        int rc = trip_body(h, P, a, (unsigned long long)cond, true);
+        h->stream = outer;
+        cudaGraph_t ended = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->body_stream, &ended);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(h, "capturing the trip body -> %s", cudaGetErrorString(e));
+        CK(cudaStreamUpdateCaptureDependencies(outer, &node, 1, cudaStreamSetCaptureDependencies));
+        pdl_hold_next();
+        account();
+        bc.enqueued = 1;
+        return 0;
+    }
+    const int LOOK = 1;
+    for (int trip = 0; trip < P.max_iter; ++trip) {
+        char nm[48];
+        snprintf(nm, sizeof nm, "component %d trip %d (enqueue)", a, trip);
+        NvtxRange nvtx_trip(nm);
+        if (trip >= 1 + LOOK) {
+            const int back = trip - 1 - LOOK;
+            CK(cudaEventSynchronize(h->ev_trip[back & 3]));
+            if (h->h_done[back] != 0) break;
+        }
+        TRY(trip_body(h, P, a, 0ull, false));
+        if (trip == 0) account();
+        bc.enqueued++;
+        CK(cudaMemcpyAsync(&h->h_done[trip], &h->ctrl->stop, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_trip[trip & 3], h->stream));
+    }
+    // the loop body was counted once; the stats of the whole fit are rebuilt from the trip counts at the end
+    h->stats.kernel_launches = before.kernel_launches + bc.launches;
+    h->stats.collectives = before.collectives + bc.collectives;
+    h->stats.streamed_bytes = before.streamed_bytes + bc.streamed;
+    return 0;
+}
+
+static int fit_streaming(tpls_handle h, const StreamPlan& P) {
+    cudaStream_t st = h->stream;
+    const long long n = h->n;
+    const int L = P.L, R = P.R;
+    double* A = h->arena;
+    for (int l = 0; l < L; ++l)
+        if (h->x[l].masked) TRY(count_rows(h, h->x[l]));
+    if (!P.fused) {
+        ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+        CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U, st));  // u0 = first column of Y (tpls.py:78)
+        h->stats.kernel_launches++;
+    }
+    for (int a = 0; a <= R; ++a) {
+        // ---- centring (a == 0) or the deflation by component a-1 (tpls.py:109), fused with the first contraction
+        //      of component a (u0 = Y e0) and with the residual norm; after the last component: the norm alone ----
+        SetList ss;
+        for (int l = 0; l < L; ++l) {
+            Tensor& t = h->x[l];
+            ColPassArgs c{};
+            c.g = t.g;
+            c.x_in = a == 0 ? t.src : t.work;
+            c.x_out = t.work;
+            c.row_a = a == 0 ? nullptr : h->T + (size_t)(a - 1) * n;
+            c.col_w = a == 0 ? t.mean_d : t.wkron + (size_t)(a - 1) * t.pitch;
+            c.sspart = t.sspart;
+            c.row_sw = h->row_w;
+            if (a < R) {
+                c.zpart = t.zpart;
+                if (P.fused) {
+                    c.y = h->y_work;
+                    c.q = h->e0vec;
+                    c.pitch_y = h->pitch_y;
+                } else {
+                    c.row_u = h->U + (size_t)a * n;
+                }
+                TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ, c));
+            } else {
+                TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_SUMSQ, c));
+            }
+            ss.add(t.sspart, t.g.grid_x * t.g.n_slabs, 1, 1, t.off_ss + a - h->off_ss);
+        }
+        if (a > 0) ss.add(h->sspart_y, h->gy.grid_x * h->gy.n_slabs, 1, 1, (size_t)(P.ss_y + a - A) - h->off_ss);
+        TRY(fold_sum(h, ss, h->off_ss, h->ss_len, nullptr, true));
+        if (a == R) break;
+
+        char nm[32];
+        snprintf(nm, sizeof nm, "component %d", a);
+        NvtxRange nvtx_comp(nm);
+        double* Ua = h->U + (size_t)a * n;
+        {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_reset_ctrl(h->ctrl, st));
+            h->stats.kernel_launches++;
+        }
+        if (P.fused) TRY(gram_y(h));
+        TRY(run_loop(h, P, a));
+        if (P.fused) {
+            // u = Y q of the last trip (tpls.py:102): inside the loop it only ever exists row by row
+            RowPassArgs r{};
+            r.g = h->gy_row;
+            r.x_in = h->y_work;
+            r.col_w = h->qvec;
+            r.t_out = Ua;
+            r.epi = 0;
+            r.div = 1.0;
+            TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
+        }
+        TRY(component_tail(h, R, a, P.ss_y, true));
+        if (!P.fused && a + 1 < R) {
+            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+            CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U + (size_t)(a + 1) * n, st));
+            h->stats.kernel_launches++;
+        }
+    }
+    return 0;
+}
+
+static unsigned long long fnv(unsigned long long hsh, const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) hsh = (hsh ^ b[i]) * 1099511628211ull;
+    return hsh;
+}
+
+// everything the captured launches depend on: buffers, shapes, options, what the statistics pass decided
+static unsigned long long graph_key_of(tpls_handle h, int L, int R, double tol, int max_iter, int flags, bool cov_mode) {
+    unsigned long long k = 1469598103934665603ull;
+#define KEY(v) k = fnv(k, &(v), sizeof(v))
+    KEY(L); KEY(R); KEY(tol); KEY(max_iter); KEY(flags); KEY(cov_mode);
+    KEY(h->n); KEY(h->m); KEY(h->n_total); KEY(h->world); KEY(h->rank); KEY(h->xchg_ready); KEY(h->xchg_buf);
+    KEY(h->y_src); KEY(h->y_work); KEY(h->row_w); KEY(h->slab); KEY(h->slab_need);
+    const bool pdl = pdl_enabled();
+    KEY(pdl);
+    for (int l = 0; l < L; ++l) {
+        Tensor& t = h->x[l];
+        KEY(t.src); KEY(t.work); KEY(t.dtype); KEY(t.ndim); KEY(t.masked);
+        for (int d = 0; d < t.ndim; ++d) KEY(t.shape[d]);
+    }
+#undef KEY
+    return k ? k : 1;
 }
 
 int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max_iter, int flags) {
@@ -865,6 +1347,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             return fail(h, "tpls_fit: X[%d] has %lld samples, Y has %lld", l, h->x[l].n, h->n);
     }
     CK(cudaSetDevice(h->device));
+    NvtxRange nvtx_fit("tpls_fit");
     cudaStream_t st = h->stream;
     const double h2d = h->h2d_bytes;
     h->stats = tpls_stats{};
@@ -873,24 +1356,30 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     h->profile = (flags & TPLS_FIT_PROFILE) != 0;
     h->cov_alloc = (flags & TPLS_FIT_COVARIANCE) != 0 && h->m <= 8;
     TRY(alloc_fit(h, L, R));
+    if (h->xchg_ready)  // a time-out of an earlier fit must not fail this one
+        CK(cudaMemsetAsync(static_cast<char*>(h->xchg_buf) + 520, 0, sizeof(int), st));
     CK(cudaEventRecord(h->ev_start, st));
     const long long n = h->n;
     double* A = h->arena;
 
-    // ---- column statistics (np.nanmean, tpls.py:66-67) ----
-    for (int l = 0; l < L; ++l) {
-        Tensor& t = h->x[l];
-        ColPassArgs c{};
-        c.g = t.g;
-        c.x_in = t.src;
-        c.zpart = t.zpart;
-        c.cntpart = t.cntpart;
-        c.row_sw = h->row_w;
-        TRY(col_pass(h, t.dtype, true, PF_COLSTAT, c));
-        TRY(reduce_cols(h, t.zpart, A + t.off_colsum, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, nullptr, 0));
-        TRY(reduce_cols(h, t.cntpart, A + t.off_colcnt, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, nullptr, 0));
-    }
+    // ---- column statistics (np.nanmean, tpls.py:66-67): sums, weighted counts, the sample count and an
+    //      UNWEIGHTED census of the NaNs, folded and summed over the ranks in one launch ----
+    nvtxRangePushA("tpls_fit: column statistics");
     {
+        SetList sl;
+        for (int l = 0; l < L; ++l) {
+            Tensor& t = h->x[l];
+            ColPassArgs c{};
+            c.g = t.g;
+            c.x_in = t.src;
+            c.zpart = t.zpart;
+            c.cntpart = t.cntpart;
+            c.sspart = t.sspart;
+            c.row_sw = h->row_w;
+            TRY(col_pass(h, t.dtype, true, PF_COLSTAT, c));
+            sl.add(t.zpart, t.g.grid_x, t.pitch, t.pitch, t.off_colsum);
+            sl.add(t.cntpart, t.g.grid_x, t.pitch, t.pitch, t.off_colcnt);
+        }
         ColPassArgs c{};
         c.g = h->gy;
         c.x_in = h->y_src;
@@ -898,12 +1387,13 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         c.cntpart = h->cntpart_y;
         c.row_sw = h->row_w;
         TRY(col_pass(h, TPLS_F64, true, PF_COLSTAT, c, TPLS_K_YSIDE));
-        TRY(reduce_cols(h, h->zpart_y, A + h->off_ysum, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, nullptr, 0));
-        TRY(reduce_cols(h, h->cntpart_y, A + h->off_ycnt, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, nullptr, 0));
+        sl.add(h->zpart_y, h->gy.grid_x, h->pitch_y, h->pitch_y, h->off_ysum);
+        sl.add(h->cntpart_y, h->gy.grid_x, h->pitch_y, h->pitch_y, h->off_ycnt);
         if (h->row_w == nullptr) {
             ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-            CK(launch_fill(A + h->off_n, 1, (double)n, st));
+            CK(launch_fill(h->nloc, 1, (double)n, st));
             h->stats.kernel_launches++;
+            sl.add(h->nloc, 1, 1, 1, h->off_n);
         } else {
             // sample count of the fold = sum of the 0/1 weights
             DotPairs d{};
@@ -914,23 +1404,27 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             int gx = 1;
             CK(launch_multi_dot(d, h->dotpart, &gx, st));
             h->stats.kernel_launches++;
-            TRY(reduce_cols(h, h->dotpart, A + h->off_n, 1, 1, gx, nullptr, nullptr, 0, nullptr, 0));
+            sl.add(h->dotpart, gx, 1, 1, h->off_n);
         }
+        for (int l = 0; l < L; ++l) {
+            Tensor& t = h->x[l];
+            sl.add(t.sspart, t.g.grid_x * t.g.n_slabs, 1, 1, h->off_nmiss + l);
+        }
+        TRY(fold_sum(h, sl, 0, h->off_stats_end, nullptr));
     }
-    TRY(allreduce(h, A, h->off_stats_end));
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
-        {
-            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-            CK(launch_finalize_mean(t.dtype, A + t.off_colsum, A + t.off_colcnt, A + h->off_n, t.p, t.pitch, t.mean_d,
-                                t.mean_native, t.miss_flag, st));
-            h->stats.kernel_launches++;
-        }
+        ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
+        CK(launch_finalize_mean(t.dtype, A + t.off_colsum, A + t.off_colcnt, A + h->off_n, t.p, t.pitch, t.mean_d,
+                                t.mean_native, t.miss_flag, A + h->off_nmiss + l, st));
+        h->stats.kernel_launches++;
     }
     {
         ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
         CK(launch_finalize_mean(TPLS_F64, A + h->off_ysum, A + h->off_ycnt, A + h->off_n, h->m, h->pitch_y, h->ymean_d,
-                            nullptr, h->ymiss_flag, st));
+                                nullptr, h->ymiss_flag, nullptr, st));
+        h->stats.kernel_launches++;
+        CK(launch_fill(h->e0vec, 1, 1.0, st));  // e0 = (1, 0, ...): u0 = Y e0 (tpls.py:78); the slab is zeroed
         h->stats.kernel_launches++;
     }
     {
@@ -946,10 +1440,35 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             t.gr_cnt = make_row_geom(n, t.p, t.pitch, t.elem, h->sm_count, true);
         }
     }
+    nvtxRangePop();
 
-    // ---- centre Y (tpls.py:71), u0 = first column (tpls.py:78) ----
-    double* ss_y = A + h->off_ss + (size_t)L * (R + 1);
-    {
+    const bool cov_mode = (flags & TPLS_FIT_COVARIANCE) != 0 && cov_supported(h, L);
+    h->stats.covariance_mode = cov_mode ? 1 : 0;
+    StreamPlan P{};
+    P.L = L;
+    P.R = R;
+    P.tol = tol;
+    P.max_iter = max_iter;
+    P.flags = flags;
+    P.fused = h->pitch_y <= kMaxFusedResp;
+    P.ss_y = A + h->off_ss + (size_t)L * (R + 1);
+    r1_config(h, L, &P.r1_smem, &P.r1_use_smem);
+
+    // Everything from here to the residual norms is ONE sequence of launches with no host decision in it: captured
+    // into a CUDA graph (and kept for the next fit with the same key) unless the fit is profiled, some collective
+    // has to go through NCCL, or TPLS_NO_GRAPH is set.
+    bool use_graph = !h->profile && getenv("TPLS_NO_GRAPH") == nullptr;
+    if (h->world > 1) {
+        const size_t biggest = std::max(h->zcat_len, cov_mode ? h->cov_len : (size_t)0);
+        if (!xchg_fits(h, biggest)) use_graph = false;
+    }
+    h->fit_mode = use_graph ? 1 : 0;
+    for (auto& b : h->body) b = tpls_ctx::BodyCount{};
+    const tpls_stats pre = h->stats;
+
+    auto enqueue_main = [&]() -> int {
+        cudaStream_t s2 = h->stream;
+        // ---- centre Y (tpls.py:71) ----
         ColPassArgs c{};
         c.g = h->gy;
         c.x_in = h->y_src;
@@ -958,269 +1477,63 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         c.sspart = h->sspart_y;
         c.row_sw = h->row_w;
         TRY(col_pass(h, TPLS_F64, false, PF_DEFLATE | PF_WRITE | PF_SUMSQ, c, TPLS_K_YSIDE));
-        TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, h->sspart_y, ss_y, h->gy.grid_x * h->gy.n_slabs, nullptr, 0));
+        {
+            SetList sl;
+            sl.add(h->sspart_y, h->gy.grid_x * h->gy.n_slabs, 1, 1, (size_t)(P.ss_y - A) - h->off_ss);
+            TRY(fold_sum(h, sl, h->off_ss, h->ss_len, nullptr, true));
+        }
         if (h->row_w != nullptr) {
             // held-out rows of the centred Y are zeroed: they then drop out of u, Z, q and the stop test
-            CK(launch_scale_rows(h->y_work, n, h->pitch_y, h->row_w, st));
+            CK(launch_scale_rows(h->y_work, n, h->pitch_y, h->row_w, s2));
             h->stats.kernel_launches++;
         }
-        {
-            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-            CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U, st));
-            h->stats.kernel_launches++;
+        return cov_mode ? fit_covariance(h, L, R, tol, max_iter, flags, P.ss_y) : fit_streaming(h, P);
+    };
+
+    if (use_graph) {
+        const unsigned long long key = graph_key_of(h, L, R, tol, max_iter, flags, cov_mode);
+        if (h->graph_exec == nullptr || key != h->graph_key) {
+            drop_graph(h);
+            if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+            if (!h->body_stream) CK(cudaStreamCreateWithFlags(&h->body_stream, cudaStreamNonBlocking));
+            NvtxRange nvtx_cap("tpls_fit: capture + instantiate");
+            CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
+            h->stream = h->cap_stream;
+            h->capturing = true;
+            int rc = enqueue_main();
+            h->capturing = false;
+            h->stream = st;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) return fail(h, "tpls_fit: capturing the fit -> %s", cudaGetErrorString(e));
+            h->graph = g;
+            e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+            if (e != cudaSuccess) {
+                drop_graph(h);
+                return fail(h, "tpls_fit: cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+            }
+            h->graph_key = key;
+            // static launches of the captured fit (the loop bodies were captured once each)
+            h->g_static = h->stats;
+            h->g_static.kernel_launches -= pre.kernel_launches;
+            h->g_static.collectives -= pre.collectives;
+            h->g_static.streamed_bytes -= pre.streamed_bytes;
+            for (int a = 0; a < R; ++a) h->g_body[a] = h->body[a];
+        } else {
+            for (int a = 0; a < R; ++a) h->body[a] = h->g_body[a];
+            h->stats.kernel_launches = pre.kernel_launches + h->g_static.kernel_launches;
+            h->stats.collectives = pre.collectives + h->g_static.collectives;
+            h->stats.streamed_bytes = pre.streamed_bytes + h->g_static.streamed_bytes;
         }
-    }
-    const bool cov_mode = (flags & TPLS_FIT_COVARIANCE) != 0 && cov_supported(h, L);
-    h->stats.covariance_mode = cov_mode ? 1 : 0;
-    if (cov_mode) {
-        TRY(fit_covariance(h, L, R, tol, max_iter, flags, ss_y));
+        CK(cudaGraphLaunch(h->graph_exec, st));
+        h->stats.graph_launches = 1;
     } else {
-    // ---- centre X fused with the first contraction ----
-    for (int l = 0; l < L; ++l) {
-        Tensor& t = h->x[l];
-        ColPassArgs c{};
-        c.g = t.g;
-        c.x_in = t.src;
-        c.x_out = t.work;
-        c.col_w = t.mean_d;
-        c.row_u = h->U;
-        c.zpart = t.zpart;
-        c.sspart = t.sspart;
-        c.row_sw = h->row_w;
-        TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ, c));
-        TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, t.sspart, A + t.off_ss,
-                        t.g.grid_x * t.g.n_slabs, nullptr, 0));
+        TRY(enqueue_main());
     }
-
-    // rank-1 launch configuration
-    size_t r1_smem = 0;
-    bool r1_use_smem = true;
-    for (int l = 0; l < L; ++l) r1_smem = std::max(r1_smem, h->x[l].r1_ws * sizeof(double));
-    if (r1_smem > 200 * 1024) {
-        r1_use_smem = false;
-        r1_smem = 0;
-    }
-
-    const int LOOK = 1;
-    const bool fused_xchg = h->world > 1 && h->xchg_ready && h->zcat_len <= (size_t)h->xchg_cap;
-    const bool gram_stop = h->m <= 8 && getenv("TPLS_NO_GRAM_STOP") == nullptr;
-    for (int a = 0; a < R; ++a) {
-        double* Ta = h->T + (size_t)a * n;
-        double* Ua = h->U + (size_t)a * n;
-        {
-            ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-            CK(launch_reset_ctrl(h->ctrl, st));
-            h->stats.kernel_launches++;
-        }
-        if (gram_stop) {
-            // Y'Y of the current (deflated) Y: the stop test then needs no pass over the samples and no
-            // collective of its own (||u_old - u_new||^2 = dq^T Y'Y dq, u = Y q)
-            int gx = 1;
-            {
-                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                CK(launch_gram_rows(h->y_work, n, h->pitch_y, h->m, h->grampart, &gx, st));
-                h->stats.kernel_launches++;
-            }
-            TRY(reduce_cols(h, h->grampart, A + h->off_gram_y, h->m * h->m, h->m * h->m, gx, nullptr, nullptr, 0, nullptr, 0));
-            TRY(allreduce(h, A + h->off_gram_y, (size_t)h->m * h->m));
-        }
-        for (int trip = 0; trip < max_iter; ++trip) {
-            if (trip >= 1 + LOOK) {
-                const int back = trip - 1 - LOOK;
-                CK(cudaEventSynchronize(h->ev_trip[back & 3]));
-                if (h->h_done[back] >= 0) break;
-            }
-            // K1: Z = X x_1 u (trip 0 got it from the fused centring / deflation pass)
-            if (trip > 0) {
-                for (int l = 0; l < L; ++l) {
-                    Tensor& t = h->x[l];
-                    ColPassArgs c{};
-                    c.g = t.g;
-                    c.x_in = t.work;
-                    c.row_u = Ua;
-                    c.zpart = t.zpart;
-                    c.ctrl = h->ctrl;
-                    c.trip = trip;
-                    TRY(col_pass(h, t.dtype, t.masked, PF_CONTRACT, c));
-                    if (!fused_xchg)
-                        TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
-                }
-            }
-            if (fused_xchg && trip > 0) {
-                // second reduction stage of every tensor + the cross-GPU sum in ONE kernel
-                XchgArgs xa{};
-                xa.n_sets = L;
-                for (int l = 0; l < L; ++l) {
-                    Tensor& t = h->x[l];
-                    xa.sets[l] = XchgSet{t.zpart, t.g.grid_x, t.pitch, t.pitch, (int)(t.off_z - h->off_zcat)};
-                }
-                xa.out = A + h->off_zcat;
-                xa.count = (int)h->zcat_len;
-                TRY(xchg_launch(h, xa));
-            } else {
-                TRY(allreduce(h, A + h->off_zcat, h->zcat_len));
-            }
-            // K3: rank-1 weight vectors, one CTA per tensor
-            {
-                Rank1Args ra{};
-                ra.n_tasks = L;
-                ra.tol = tol;
-                ra.normalize_on_break = (flags & TPLS_FIT_NORMALIZE_ON_BREAK) ? 1 : 0;
-                ra.ctrl = h->ctrl;
-                ra.trip = trip;
-                for (int l = 0; l < L; ++l) fill_rank1_task(h, h->x[l], a, ra.t[l], r1_use_smem);
-                ProfScope ps(h, TPLS_K_RANK1, 0.0);
-                CK(launch_rank1(ra, r1_smem, st));
-                h->stats.kernel_launches++;
-            }
-            // K2: t = X x_2 w2 x_3 w3 ..., averaged over the coupled tensors (cmtf.py:120)
-            for (int l = 0; l < L; ++l) {
-                Tensor& t = h->x[l];
-                RowPassArgs r{};
-                const int rmode = !t.masked ? 0 : (t.rowcnt_ready ? 1 : 2);
-                r.g = rmode == 2 ? t.gr_cnt : t.gr;
-                r.x_in = t.work;
-                r.col_w = t.wkron + (size_t)a * t.pitch;
-                r.t_out = Ta;
-                r.tpart = t.tpart;
-                r.cpart = t.cpart;
-                r.rowcnt = t.rowcnt;
-                r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
-                r.div = (double)L;
-                r.ctrl = h->ctrl;
-                r.trip = trip;
-                // the first projection of a masked tensor also counts the observed entries of every row
-                // (trip 0 of component 0 always executes, so the counts are there for every later trip)
-                TRY(row_pass(h, t.dtype, rmode, r));
-                t.rowcnt_ready = true;
-            }
-            // K4: q = Y't / ||.||, u = Y q, stop test (tpls.py:100-107)
-            {
-                ColPassArgs c{};
-                c.g = h->gy;
-                c.x_in = h->y_work;
-                c.row_u = Ta;
-                c.zpart = h->zpart_y;
-                c.ctrl = h->ctrl;
-                c.trip = trip;
-                TRY(col_pass(h, TPLS_F64, false, PF_CONTRACT, c, TPLS_K_YSIDE));
-                // with the Y'Y stop test the normalisation of q and the stop decision ride on the kernel that
-                // finishes the q reduction (the exchange kernel, or the second reduction stage on one GPU)
-                const bool q_fused = gram_stop && h->pitch_y <= 32 && (fused_xchg || h->world == 1);
-                if (fused_xchg) {
-                    XchgArgs xa{};
-                    xa.n_sets = 1;
-                    xa.sets[0] = XchgSet{h->zpart_y, h->gy.grid_x, h->pitch_y, h->pitch_y, 0};
-                    xa.out = A + h->off_q;
-                    xa.count = h->pitch_y;
-                    if (q_fused) {
-                        xa.do_qstop = 1;
-                        xa.q_m = h->m;
-                        xa.q_pitch = h->pitch_y;
-                        xa.qcol = h->Q + (size_t)a * h->m;
-                        xa.qvec = h->qvec;
-                        xa.gram = A + h->off_gram_y;
-                        xa.q_prev = h->q_prev;
-                        xa.ctrl = h->ctrl;
-                        xa.trip = trip;
-                        xa.tol = tol;
-                    }
-                    TRY(xchg_launch(h, xa));
-                } else if (q_fused) {
-                    ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                    CK(launch_reduce_q_stop(h->zpart_y, h->gy.grid_x, h->pitch_y, A + h->off_q, h->m, h->pitch_y,
-                                            h->Q + (size_t)a * h->m, h->qvec, A + h->off_gram_y, h->q_prev, h->ctrl, trip, tol, st));
-                    h->stats.kernel_launches++;
-                } else {
-                    TRY(reduce_cols(h, h->zpart_y, A + h->off_q, h->pitch_y, h->pitch_y, h->gy.grid_x, nullptr, nullptr, 0, h->ctrl, trip));
-                    TRY(allreduce(h, A + h->off_q, h->pitch_y));
-                }
-                if (!q_fused) {
-                    ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                    if (gram_stop)
-                        CK(launch_normalize_q_stop(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec,
-                                                   A + h->off_gram_y, h->q_prev, h->ctrl, trip, tol, st));
-                    else
-                        CK(launch_normalize_q(A + h->off_q, h->m, h->pitch_y, h->Q + (size_t)a * h->m, h->qvec, h->ctrl, trip, st));
-                    h->stats.kernel_launches++;
-                }
-                RowPassArgs r{};
-                r.g = h->gy_row;
-                r.x_in = h->y_work;
-                r.col_w = h->qvec;
-                r.t_out = Ua;
-                r.epi = 0;
-                r.div = 1.0;
-                r.d2part = gram_stop ? nullptr : h->d2part;
-                r.ctrl = h->ctrl;
-                r.trip = trip;
-                TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
-                const int nd2 = d2_grid(h->gy_row);
-                if (gram_stop) {
-                    // the stop test already ran inside normalize_q_stop
-                } else if (fused_xchg) {
-                    // partial sums of ||u_old - u_new||^2 -> global sum -> stop test, one kernel
-                    XchgArgs xa{};
-                    xa.n_sets = 1;
-                    xa.sets[0] = XchgSet{h->d2part, nd2, 1, 1, 0};
-                    xa.out = A + h->off_d2;
-                    xa.count = 1;
-                    xa.ctrl = h->ctrl;
-                    xa.trip = trip;
-                    xa.tol = tol;
-                    xa.do_stop = 1;
-                    TRY(xchg_launch(h, xa));
-                } else if (h->world > 1) {
-                    {
-                        ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                        CK(launch_sum_small(h->d2part, nd2, A + h->off_d2, h->ctrl, trip, st));
-                        h->stats.kernel_launches++;
-                    }
-                    TRY(allreduce(h, A + h->off_d2, 1));
-                    CK(launch_stop(h->ctrl, trip, A + h->off_d2, 1, tol, st));
-                    h->stats.kernel_launches++;
-                } else {
-                    CK(launch_stop(h->ctrl, trip, h->d2part, nd2, tol, st));
-                    h->stats.kernel_launches++;
-                }
-            }
-            CK(cudaMemcpyAsync(&h->h_done[trip], &h->ctrl->done_trip, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaEventRecord(h->ev_trip[trip & 3], st));
-        }
-
-        TRY(component_tail(h, R, a, ss_y, true));
-        // ---- X deflation (tpls.py:109) fused with the next component's first contraction ----
-        if (a + 1 < R) {
-            {
-                ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
-                CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U + (size_t)(a + 1) * n, st));
-                h->stats.kernel_launches++;
-            }
-        }
-        for (int l = 0; l < L; ++l) {
-            Tensor& t = h->x[l];
-            ColPassArgs c{};
-            c.g = t.g;
-            c.x_in = t.work;
-            c.x_out = t.work;
-            c.row_a = Ta;
-            c.col_w = t.wkron + (size_t)a * t.pitch;
-            c.sspart = t.sspart;
-            c.row_sw = h->row_w;
-            if (a + 1 < R) {
-                c.row_u = h->U + (size_t)(a + 1) * n;
-                c.zpart = t.zpart;
-                TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_WRITE | PF_CONTRACT | PF_SUMSQ, c));
-                TRY(reduce_cols(h, t.zpart, A + t.off_z, t.pitch, t.pitch, t.g.grid_x, t.sspart, A + t.off_ss + a + 1,
-                                t.g.grid_x * t.g.n_slabs, nullptr, 0));
-            } else {
-                TRY(col_pass(h, t.dtype, t.masked, PF_DEFLATE | PF_SUMSQ, c));
-                TRY(reduce_cols(h, nullptr, nullptr, 0, 0, 0, t.sspart, A + t.off_ss + a + 1, t.g.grid_x * t.g.n_slabs, nullptr, 0));
-            }
-        }
-    }
-
-    }  // streaming mode
 
     // ---- R2X / R2Y from the residual norms ----
     // through NCCL on purpose: it cannot complete before every peer has finished all earlier exchanges,
@@ -1228,8 +1541,10 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     TRY(allreduce_nccl(h, A + h->off_ss, h->ss_len));
     std::vector<double> ss(h->ss_len);
     h->trips.assign(R, 0);
+    h->converged.assign(R, 0);
     CK(cudaMemcpyAsync(ss.data(), A + h->off_ss, sizeof(double) * h->ss_len, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->trips.data(), h->trips_dev, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->converged.data(), h->conv_dev, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->ev_stop, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -1253,6 +1568,19 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     long long total = 0;
     for (int a = 0; a < R; ++a) total += h->trips[a];
     h->stats.total_trips = total;
+    // launches / collectives / streamed bytes of the loops: one body was counted per component
+    if (!cov_mode) {
+        int per_trip = 0;
+        for (int a = 0; a < R; ++a) {
+            const tpls_ctx::BodyCount& b = h->body[a];
+            const long long runs = use_graph ? h->trips[a] : b.enqueued;
+            h->stats.kernel_launches += b.launches * (runs - 1);
+            h->stats.collectives += b.collectives * (runs - 1);
+            h->stats.streamed_bytes += b.streamed * (h->trips[a] - 1) - b.tail_streamed;
+            per_trip = std::max<long long>(per_trip, b.launches);
+        }
+        h->stats.launches_per_trip = per_trip;
+    }
     double alg = 0.0;
     for (int l = 0; l < L; ++l) alg += (double)h->x[l].elem * n * h->x[l].p * (2.0 * total + R + 2);
     h->stats.alg_bytes = alg;
@@ -1330,6 +1658,12 @@ int tpls_get_has_missing(tpls_handle h, int index, int* out) {
 int tpls_get_trips(tpls_handle h, int* out) {
     NEED_FIT();
     memcpy(out, h->trips.data(), sizeof(int) * h->R);
+    return 0;
+}
+
+int tpls_get_converged(tpls_handle h, int* out) {
+    NEED_FIT();
+    memcpy(out, h->converged.data(), sizeof(int) * h->R);
     return 0;
 }
 

@@ -6,6 +6,7 @@
 #include "../../include/tpls_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -70,7 +71,7 @@ using namespace tpls_drv;
 struct tpls_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool own_stream = false;
+    cudaStream_t private_stream = nullptr;  // created on demand; used when the caller gives no stream
     int sm_count = 148;
     std::string error;
     // comm
@@ -81,7 +82,6 @@ struct tpls_ctx {
     void* xchg_peer[kXchgMaxRanks] = {nullptr};
     int xchg_cap = 0;
     bool xchg_ready = false;
-    unsigned long long xchg_seq = 0;
     // data
     Tensor x[TPLS_MAX_TENSORS];
     long long n = 0;
@@ -125,6 +125,26 @@ struct tpls_ctx {
     bool cov_alloc = false;  // the last alloc_fit reserved the covariance-mode buffers
     size_t off_cov = 0, cov_len = 0, off_gram_y = 0;
     double *grampart = nullptr, *q_prev = nullptr;
+    double *qpart = nullptr, *e0vec = nullptr, *nloc = nullptr;
+    size_t off_nmiss = 0;
+    int* conv_dev = nullptr;
+    std::vector<int> converged;
+    // device-resident fit (CUDA graph, one WHILE node per component): the instantiated graph of the last fit is
+    // kept and relaunched when the next fit has the same key (same buffers, shapes, options)
+    cudaStream_t cap_stream = nullptr, body_stream = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    unsigned long long graph_key = 0;
+    bool capturing = false;
+    // launch accounting of the trip body of every component (launches / collectives / streamed bytes of ONE body,
+    // bytes of the trailing contraction that the last body skips, bodies the host enqueued)
+    struct BodyCount {
+        long long launches = 0, collectives = 0, enqueued = 0;
+        double streamed = 0, tail_streamed = 0;
+    };
+    BodyCount body[32], g_body[32];
+    tpls_stats g_static{};  // launches / collectives / bytes of one pass through the captured graph
+    int fit_mode = 0;  // 0 host-driven loop, 1 graph
     tpls_stats stats{};
     // optional per-kernel-class timing (TPLS_FIT_PROFILE): event pairs on the launching stream
     bool profile = false;
@@ -140,6 +160,12 @@ struct tpls_ctx {
 };
 
 namespace tpls_drv {
+
+// NVTX range over a scope of host code (fit stages, components and host-enqueued trips)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(tpls_handle h, const char* fmt, ...);
 
@@ -168,6 +194,7 @@ void pool_put(tpls_handle h, void* p);
 void pool_trim(tpls_handle h);
 int dev_alloc(tpls_handle h, void** out, size_t bytes, std::vector<void*>* track);
 void free_fit(tpls_handle h);
+void drop_graph(tpls_handle h);  // forget the captured fit (its buffers or peers are about to change)
 void free_tensor(tpls_handle h, Tensor& t);
 
 // ---- per-class timing (TPLS_FIT_PROFILE): an event pair around every launch ----
@@ -195,6 +222,18 @@ void prof_collect(tpls_handle h);
 int allreduce_nccl(tpls_handle h, double* buf, size_t count);
 int xchg_launch(tpls_handle h, XchgArgs& a);
 int allreduce(tpls_handle h, double* buf, size_t count);
+
+// Several per-CTA partial blocks -> their sums in the arena, summed over the ranks: ONE launch on one GPU
+// (fold_sets) and ONE launch per rank with the peer-memory exchange; fold + ncclAllReduce otherwise.
+// Set offsets are relative to arena + base_off; [base_off, base_off + count) is what crosses the ranks.
+struct SetList {
+    FoldSet s[kMaxFoldSets];
+    int n = 0;
+    void add(const double* part, int n_parts, int stride, int n_cols, size_t off) {
+        s[n++] = FoldSet{part, n_parts, stride, n_cols, (int)off};
+    }
+};
+int fold_sum(tpls_handle h, const SetList& sl, size_t base_off, size_t count, const Ctrl* ctrl, bool local_only = false);
 
 // pass wrappers that keep the launch / byte counters
 int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a, int cls = -1);

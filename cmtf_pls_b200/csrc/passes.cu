@@ -23,7 +23,7 @@ static int pow2_ceil(int v) {
     return p;
 }
 
-PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count) {
+PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, int y_row_bytes) {
     PassGeom g{};
     const int vec = 16 / elem_size;
     g.n_rows = n_rows;
@@ -48,8 +48,9 @@ PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_cou
     long long tr = std::max<long long>(1, ((long long)tune_env("TPLS_TILE_KB", 32) * 1024) / row_bytes);
     tr = std::min<long long>(tr, std::max<long long>(1, n_rows));
     tr = std::min<long long>(tr, 4096);
+    if (y_row_bytes > 0) tr = std::min<long long>(tr, std::max<long long>(2, 16384 / y_row_bytes));  // staged rows of Y <= 16 KB
     g.tile_rows = (int)tr;
-    const long long stage_bytes = tr * row_bytes;
+    const long long stage_bytes = tr * (row_bytes + y_row_bytes);
     g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)tune_env("TPLS_SMEM_KB", 100) * 1024) / stage_bytes));
     const long long n_tiles = (n_rows + tr - 1) / tr;
     const long long want = std::max(1, (sm_count * tune_env("TPLS_CTAS_PER_SM", 2)) / g.n_slabs);
@@ -61,10 +62,10 @@ static size_t stage_bytes_of(const PassGeom& g) {
     return (size_t)g.tile_rows * (g.n_slabs == 1 ? g.pitch : g.slab_w) * g.elem_size;
 }
 
-size_t colpass_smem(const PassGeom& g) {
-    const size_t tiles = g.stages * stage_bytes_of(g);
+size_t colpass_smem(const PassGeom& g, int pitch_y) {
+    const size_t tiles = g.stages * (stage_bytes_of(g) + (size_t)g.tile_rows * pitch_y * sizeof(double));
     const size_t red = (size_t)kConsumers * g.cpt * (16 / g.elem_size) * sizeof(double);  // row-lane fold
-    return std::max(tiles, red) + 128;
+    return std::max(tiles, red) + 256;  // + barriers (128) + q (kMaxFusedResp doubles)
 }
 
 // ---------------------------------------------------------------------------
@@ -94,9 +95,16 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
     const int srow = FULL ? kConsumers * VecOf<XT>::N * CPT : ((g.n_slabs == 1) ? g.pitch : g.slab_w);
     const size_t stage_elems = (size_t)g.tile_rows * srow;
     XT* tiles = reinterpret_cast<XT*>(smem);
-    const size_t tile_area = max((size_t)g.stages * stage_elems * sizeof(XT), (size_t)kConsumers * CPT * VEC * sizeof(double));
+    // u = Y q formed here (CONTRACT with a.y): the rows of Y are staged behind the X tiles of the ring
+    const bool use_y = CONTRACT && a.y != nullptr;
+    const int pitch_y = use_y ? a.pitch_y : 0;
+    const size_t ystage = (size_t)g.tile_rows * pitch_y;
+    double* ytiles = reinterpret_cast<double*>(smem + (size_t)g.stages * stage_elems * sizeof(XT));
+    const size_t tile_area = max((size_t)g.stages * (stage_elems * sizeof(XT) + ystage * sizeof(double)),
+                                 (size_t)kConsumers * CPT * VEC * sizeof(double));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + tile_area);
     uint64_t* empty = full + kMaxStages;
+    double* qs = reinterpret_cast<double*>(smem + tile_area + 128);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
@@ -105,11 +113,13 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
         }
         fence_mbar_init();
     }
+    if (use_y && threadIdx.x < kMaxFusedResp) qs[threadIdx.x] = (int)threadIdx.x < pitch_y ? a.q[threadIdx.x] : 0.0;
     __syncthreads();
 
     if (threadIdx.x >= kConsumers) {
         if (threadIdx.x == kConsumers)
-            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow);
+            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow,
+                              use_y ? a.y : nullptr, pitch_y, ytiles);
         return;
     }
 
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
         }
     }
     double ss = 0.0;
+    int nmiss = 0;  // COLSTAT: unobserved entries seen by this thread, whatever the row weights
 
     XT* xo = reinterpret_cast<XT*>(a.x_out);
     const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
@@ -145,11 +156,23 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
         const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
         mbar_wait(&full[s], ph);
         const XT* tp = tiles + s * stage_elems;
+        const double* yp = ytiles + s * ystage;
         for (int r = rl; r < rows; r += rpt) {
             const long long grow = r0 + r;
             double ar = 1.0, ur = 0.0;
             if (DEFLATE && a.row_a != nullptr) ar = __ldg(a.row_a + grow);
-            if (CONTRACT) ur = __ldg(a.row_u + grow);
+            if (CONTRACT) {
+                if (use_y) {
+                    const double2* yr = reinterpret_cast<const double2*>(yp + (size_t)r * pitch_y);
+                    for (int m = 0; m < pitch_y; m += 2) {
+                        const double2 yv = yr[m >> 1];
+                        ur = fma(yv.x, qs[m], ur);
+                        ur = fma(yv.y, qs[m + 1], ur);
+                    }
+                } else {
+                    ur = __ldg(a.row_u + grow);
+                }
+            }
             // optional 0/1 sample weights (cross-validation folds): weighted column statistics and
             // weighted residual norm; the row's own sum of squares is folded in once per row
             const double sw = ((COLSTAT || SUMSQ) && a.row_sw != nullptr) ? __ldg(a.row_sw + grow) : 1.0;
@@ -175,6 +198,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
                     if (COLSTAT) {
                         zacc[k][j] = fma(xd, sw, zacc[k][j]);
                         cacc[k][j] += ob ? sw : 0.0;
+                        nmiss += ob ? 0 : 1;
                     }
                     if (SUMSQ) ss = fma(xd, xd, ss);
                 }
@@ -223,8 +247,9 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
             }
         }
     }
-    if (SUMSQ) {
+    if (SUMSQ || (COLSTAT && a.sspart != nullptr)) {
         double* red = reinterpret_cast<double*>(smem);
+        if (COLSTAT) ss = (double)nmiss;
         named_bar_sync(1, kConsumers);
         ss = warp_sum(ss);
         if (lane == 0) red[tid >> 5] = ss;
@@ -282,11 +307,39 @@ cudaError_t launch_reduce_cols(const ReduceArgs& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) fold_sets_kernel(const __grid_constant__ FoldArgs a) {
+    pdl_prologue();
+    if (trip_is_dead(a.ctrl, 0)) return;
+    __shared__ double fold[8][33];
+    const int cl = threadIdx.x & 31, q = threadIdx.x >> 5;
+    int c_base = 0;
+    const FoldSet& S = a.sets[fold_locate(a.sets, a.n_sets, blockIdx.x, &c_base)];
+    const int c = c_base + cl;
+    fold[q][cl] = fold_share(S, c, q);
+    __syncthreads();
+    if (q == 0 && c < S.n_cols) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += fold[k][cl];
+        a.out[S.off + c] = t;
+    }
+}
+
+cudaError_t launch_fold_sets(const FoldArgs& a, cudaStream_t s) {
+    if (a.n_sets < 1 || a.n_sets > kMaxFoldSets) return cudaErrorInvalidValue;
+    const int blocks = std::max(1, fold_chunks(a.sets, a.n_sets));
+    launch_k(fold_sets_kernel, dim3(blocks), dim3(256), 0, s, a);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) row_finish_kernel(const RowFinishArgs a) {
     pdl_prologue();
     if (trip_is_dead(a.ctrl, a.trip)) return;
     __shared__ double red[40];
     double d2 = 0.0;
+    double qacc[kMaxFusedResp];
+#pragma unroll
+    for (int m = 0; m < kMaxFusedResp; ++m) qacc[m] = 0.0;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_rows;
          r += (long long)gridDim.x * blockDim.x) {
         double v = 0.0, cnt = 0.0;
@@ -310,10 +363,22 @@ __global__ void __launch_bounds__(256) row_finish_kernel(const RowFinishArgs a) 
         a.t_out[r] = nv;
         const double d = old - nv;
         d2 = fma(d, d, d2);
+        if (a.qpart != nullptr) {
+#pragma unroll
+            for (int m = 0; m < kMaxFusedResp; ++m)
+                if (m < a.pitch_y) qacc[m] = fma(a.y[r * a.pitch_y + m], nv, qacc[m]);
+        }
     }
     if (a.d2part != nullptr) {
         d2 = block_sum(d2, red);
         if (threadIdx.x == 0) a.d2part[blockIdx.x] = d2;
+    }
+    if (a.qpart != nullptr) {
+#pragma unroll
+        for (int m = 0; m < kMaxFusedResp; ++m) {
+            const double t = block_sum(qacc[m], red);
+            if (threadIdx.x == 0) a.qpart[(size_t)blockIdx.x * kMaxFusedResp + m] = t;
+        }
     }
 }
 
@@ -334,7 +399,7 @@ cudaError_t launch_row_finish(const RowFinishArgs& a, int* grid_out, cudaStream_
 template <typename XT, int CPT, bool MASKED, int FLAGS, bool FULL>
 static cudaError_t run_colpass_impl(const ColPassArgs& a, cudaStream_t s) {
     auto kern = colpass_kernel<XT, CPT, MASKED, FLAGS, FULL>;
-    const size_t smem = colpass_smem(a.g);
+    const size_t smem = colpass_smem(a.g, ((FLAGS & PF_CONTRACT) && a.y != nullptr) ? a.pitch_y : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);

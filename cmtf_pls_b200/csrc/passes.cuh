@@ -50,9 +50,11 @@ struct PassGeom {
     int elem_size;  // 4 or 8
 };
 
-// Chooses slab width, thread layout, tile size and grid for a shard.
-PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count);
-size_t colpass_smem(const PassGeom& g);
+// Chooses slab width, thread layout, tile size and grid for a shard.  y_row_bytes > 0: contractions over this
+// shard stage the matching rows of Y (pitch_y doubles each) beside every X tile (ColPassArgs::y).
+PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, int y_row_bytes = 0);
+size_t colpass_smem(const PassGeom& g, int pitch_y);
+constexpr int kMaxFusedResp = 8;            // responses (padded) up to which the Y side of a trip is fused into the X passes
 int tune_env(const char* name, int dflt);
 // Row passes use their own layout (fewer lanes per row, a slot ring for the reducer warp).
 PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked);
@@ -64,11 +66,14 @@ struct ColPassArgs {
     void* x_out;            // PF_WRITE (may alias x_in)
     const double* row_a;    // PF_DEFLATE per-row scalar, nullptr => 1
     const double* col_w;    // PF_DEFLATE per-column vector [pitch]
-    const double* row_u;    // PF_CONTRACT per-row weights
+    const double* row_u;    // PF_CONTRACT per-row weights (used when y == nullptr)
+    const double* y;        // PF_CONTRACT, optional: responses [n_rows][pitch_y]; then u[row] = y[row,:] . q is formed
+    const double* q;        //   in the kernel (tpls.py:102 fused into tpls.py:83) and row_u is not read
+    int pitch_y;            //   pitch_y <= kMaxFusedResp, even; the rows of Y ride in the same bulk-copy ring as X
     const double* row_sw;   // optional 0/1 sample weights for PF_COLSTAT / PF_SUMSQ (nullptr => 1)
     double* zpart;          // [grid_x][pitch] per-CTA column partials
     double* cntpart;        // PF_COLSTAT [grid_x][pitch]
-    double* sspart;         // PF_SUMSQ [n_slabs * grid_x]
+    double* sspart;         // PF_SUMSQ [n_slabs * grid_x]; PF_COLSTAT (optional): unobserved entries seen, UNWEIGHTED
     const Ctrl* ctrl;
     int trip;
 };
@@ -84,6 +89,10 @@ struct RowPassArgs {
     int epi;                // 0: t = v   1: t += v   2: t = (t + v) / div
     double div;
     double* d2part;         // optional [grid_x]: sum over rows of (t_old - t_new)^2
+    const double* y;        // optional (with qpart): responses [n_rows][pitch_y], pitch_y <= kMaxFusedResp
+    int pitch_y;
+    double* qpart;          // optional [grid_x or row_finish grid][kMaxFusedResp]: partials of q = Y't over the FINAL t
+                            //   of this CTA's rows (tpls.py:100 fused into the projection's epilogue)
     const Ctrl* ctrl;
     int trip;
 };
@@ -130,6 +139,29 @@ struct ReduceArgs {
 };
 cudaError_t launch_reduce_cols(const ReduceArgs& a, cudaStream_t s);
 
+// Several second-stage folds in ONE launch: out[set.off + c] = sum_b set.part[b*set.stride + c], c < set.n_cols, in the
+// association order of reduce_cols (8 interleaved groups of 4 chains).  A vector of per-CTA scalars (sum of squares) is a
+// set with stride 1 and one column.  Also the first phase of the peer-memory exchange (xchg.cuh).
+constexpr int kMaxFoldSets = 32;
+struct FoldSet {
+    const double* part;
+    int n_parts, stride, n_cols, off;
+};
+struct FoldArgs {
+    FoldSet sets[kMaxFoldSets];
+    int n_sets;
+    double* out;
+    const Ctrl* ctrl;
+};
+cudaError_t launch_fold_sets(const FoldArgs& a, cudaStream_t s);
+
+// chunk (32 consecutive columns of one set) -> set index and first column; chunks are numbered set by set
+__host__ __device__ inline int fold_chunks(const FoldSet* sets, int n_sets) {
+    int n = 0;
+    for (int s = 0; s < n_sets; ++s) n += (sets[s].n_cols + 31) >> 5;
+    return n;
+}
+
 // n_slabs > 1 only: t = epilogue(sum over slabs of tpart), masked scaling included.
 struct RowFinishArgs {
     long long n_rows;
@@ -143,6 +175,9 @@ struct RowFinishArgs {
     int epi;
     double div;
     double* d2part;         // [gridDim.x]
+    const double* y;        // see RowPassArgs
+    int pitch_y;
+    double* qpart;          // [gridDim.x][kMaxFusedResp]
     const Ctrl* ctrl;
     int trip;
 };

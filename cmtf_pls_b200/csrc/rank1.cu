@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid
     if (threadIdx.x < 8) q_last[threadIdx.x] = threadIdx.x == 0 ? 1.0 : 0.0;  // u_0 = Y[:, 0] = Y e_0 (tpls.py:78)
     __syncthreads();
     int trips = 0;
+    bool converged = false;
     for (int trip = 0; trip < a.max_iter; ++trip) {
         trips = trip + 1;
         if (threadIdx.x < 8) r_acc[threadIdx.x] = 0.0;
@@ -832,14 +833,20 @@ __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid
         __syncthreads();
         if (threadIdx.x < 8) q_last[threadIdx.x] = threadIdx.x < M ? q_new[threadIdx.x] : 0.0;
         __syncthreads();
-        if (stop) break;
+        if (stop) {
+            converged = true;
+            break;
+        }
     }
     for (int i = threadIdx.x; i < a.pitch_y; i += NTH) {
         const double v = i < M ? q_last[i] : 0.0;
         a.qvec[i] = v;
         if (i < M) a.q_out[i] = v;
     }
-    if (threadIdx.x == 0) *a.trips_out = trips;
+    if (threadIdx.x == 0) {
+        *a.trips_out = trips;
+        if (a.conv_out != nullptr) *a.conv_out = converged ? 1 : 0;
+    }
 }
 
 }  // namespace

@@ -60,6 +60,7 @@ struct CovLoopArgs {
     double* qvec;                      // [pitch_y] the same, zero-padded
     int pitch_y;
     int* trips_out;                    // inner trips taken
+    int* conv_out;                     // optional: 1 when the stop test was met
 };
 cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_smem, cudaStream_t s);
 

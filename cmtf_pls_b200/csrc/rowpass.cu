@@ -76,13 +76,13 @@ PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm
 }
 
 size_t rowpass_smem(const PassGeom& g, bool masked) {
-    return g.stages * row_stage_bytes(g) + 256 + kSlots * row_slot_doubles(g, masked) * sizeof(double);
+    return g.stages * row_stage_bytes(g) + 256 + kSlots * row_slot_doubles(g, masked) * sizeof(double) + 1024;
 }
 
 // `old` = previous t[row]; only read by the caller when the epilogue needs it (coupled accumulation, ||dt||^2)
 __device__ __forceinline__ bool epilogue_needs_old(const RowPassArgs& a) { return a.epi != 0 || a.d2part != nullptr; }
 
-__device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long grow, double v, double old, double& d2) {
+__device__ __forceinline__ double row_epilogue(const RowPassArgs& a, long long grow, double v, double old, double& d2) {
     double* tp = a.t_out + grow;
     double nv = v;
     if (a.epi == 1) nv = old + v;
@@ -91,6 +91,24 @@ __device__ __forceinline__ void row_epilogue(const RowPassArgs& a, long long gro
     if (a.d2part != nullptr) {
         const double d = old - nv;
         d2 = fma(d, d, d2);
+    }
+    return nv;
+}
+
+// q = Y't fused into the projection (tpls.py:100): qacc[m] += Y[row, m] * t[row] for the row's FINAL t
+__device__ __forceinline__ void q_accumulate(double (&qacc)[kMaxFusedResp], const double (&yv)[kMaxFusedResp], double t) {
+#pragma unroll
+    for (int m = 0; m < kMaxFusedResp; ++m) qacc[m] = fma(yv[m], t, qacc[m]);
+}
+
+__device__ __forceinline__ void load_y_row(const RowPassArgs& a, long long grow, double (&yv)[kMaxFusedResp]) {
+    const double2* yr = reinterpret_cast<const double2*>(a.y + grow * a.pitch_y);
+#pragma unroll
+    for (int m = 0; m < kMaxFusedResp; m += 2) {
+        double2 t = make_double2(0.0, 0.0);
+        if (m < a.pitch_y) t = yr[m >> 1];
+        yv[m] = t.x;
+        yv[m + 1] = t.y;
     }
 }
 
@@ -160,7 +178,11 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         const int rows_per_round = 32 / G;
         const int rg = lane / G, gl = lane - rg * G;
         const bool need_old = epilogue_needs_old(a);
+        const bool want_q = a.qpart != nullptr && !slabbed;
         double d2 = 0.0;
+        double qacc[kMaxFusedResp], y_pf[kMaxFusedResp];
+#pragma unroll
+        for (int m = 0; m < kMaxFusedResp; ++m) qacc[m] = y_pf[m] = 0.0;
         long long it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int sl = (int)(it % kSlots);
@@ -173,6 +195,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
             if (gl == 0 && rg < rows && !slabbed) {
                 if (need_old) old_pf = a.t_out[r0 + rg];
                 if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + rg];
+                if (want_q) load_y_row(a, r0 + rg, y_pf);
             }
             mbar_wait(&red_full[sl], ph);
             const double* sp = slots + (size_t)sl * slot_doubles;
@@ -223,7 +246,11 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
                         const double old = !need_old ? 0.0 : (rb == 0 ? old_pf : a.t_out[grow]);
-                        row_epilogue(a, grow, v, old, d2);
+                        const double nv = row_epilogue(a, grow, v, old, d2);
+                        if (want_q) {
+                            if (rb != 0) load_y_row(a, grow, y_pf);
+                            q_accumulate(qacc, y_pf, nv);
+                        }
                     }
                 }
             }
@@ -233,6 +260,13 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         if (a.d2part != nullptr && !slabbed) {
             d2 = warp_sum(d2);
             if (lane == 0) a.d2part[blockIdx.x] = d2;
+        }
+        if (want_q) {
+#pragma unroll
+            for (int m = 0; m < kMaxFusedResp; ++m) {
+                const double t = warp_sum(qacc[m]);
+                if (lane == 0) a.qpart[(size_t)blockIdx.x * kMaxFusedResp + m] = t;
+            }
         }
         return;
     }
@@ -250,6 +284,11 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         for (int j = 0; j < VEC; ++j) wreg[k][j] = cvalid[k] ? a.col_w[c0 + cg * VEC + j] : 0.0;
     }
     double d2 = 0.0;
+    // (rows narrower than 32 column groups always have CPT == 1, see make_row_geom: wider layouts never take this path)
+    const bool want_q = CPT == 1 && !use_slots && a.qpart != nullptr && !slabbed;
+    double qacc[kMaxFusedResp];
+#pragma unroll
+    for (int m = 0; m < kMaxFusedResp; ++m) qacc[m] = 0.0;
 
     long long it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -329,7 +368,12 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                             }
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        row_epilogue(a, grow, v, epilogue_needs_old(a) ? a.t_out[grow] : 0.0, d2);
+                        const double nv = row_epilogue(a, grow, v, epilogue_needs_old(a) ? a.t_out[grow] : 0.0, d2);
+                        if (want_q) {
+                            double yv[kMaxFusedResp];
+                            load_y_row(a, grow, yv);
+                            q_accumulate(qacc, yv, nv);
+                        }
                     }
                 }
             }
@@ -351,6 +395,21 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
             double t = 0.0;
             for (int w = 0; w < kConsumers / 32; ++w) t += r2[w];
             a.d2part[blockIdx.x] = t;
+        }
+    }
+    if (want_q) {
+        double* r2 = slots;  // no slot ring on this path: the 1 KB scratch behind the barriers; [warp][kMaxFusedResp]
+        named_bar_sync(1, kConsumers);
+#pragma unroll
+        for (int m = 0; m < kMaxFusedResp; ++m) {
+            const double t = warp_sum(qacc[m]);
+            if (lane == 0) r2[(tid >> 5) * kMaxFusedResp + m] = t;
+        }
+        named_bar_sync(1, kConsumers);
+        if (tid < kMaxFusedResp) {
+            double t = 0.0;
+            for (int w = 0; w < kConsumers / 32; ++w) t += r2[w * kMaxFusedResp + tid];
+            a.qpart[(size_t)blockIdx.x * kMaxFusedResp + tid] = t;
         }
     }
 }

@@ -15,11 +15,20 @@ bool pdl_enabled() {
     return on;
 }
 
+static thread_local bool g_pdl_hold = false;
+void pdl_hold_next() { g_pdl_hold = true; }
+bool pdl_take_hold() {
+    const bool h = g_pdl_hold;
+    g_pdl_hold = false;
+    return h;
+}
+
 template <typename XT>
 __global__ void finalize_mean_kernel(const double* colsum, const double* colcnt, const double* n_total, int p, int pitch,
-                                     double* mean_d, XT* native_out, int* miss_flag) {
+                                     double* mean_d, XT* native_out, int* miss_flag, const double* nmiss) {
     pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nmiss != nullptr && *nmiss > 0.0) atomicOr(miss_flag, 1);  // NaNs in rows of weight 0 count too
     if (c >= pitch) return;
     if (c >= p) {
         mean_d[c] = 0.0;
@@ -33,14 +42,15 @@ __global__ void finalize_mean_kernel(const double* colsum, const double* colcnt,
 }
 
 cudaError_t launch_finalize_mean(int dtype, const double* colsum, const double* colcnt, const double* n_total, int p,
-                                 int pitch, double* mean_d, void* native_out, int* miss_flag, cudaStream_t s) {
+                                 int pitch, double* mean_d, void* native_out, int* miss_flag, const double* nmiss,
+                                 cudaStream_t s) {
     const int blocks = (pitch + 255) / 256;
     if (dtype == 0)
         launch_k(finalize_mean_kernel<float>, dim3(blocks), dim3(256), 0, s, colsum, colcnt, n_total, p, pitch, mean_d,
-                                                           (float*)native_out, miss_flag);
+                                                           (float*)native_out, miss_flag, nmiss);
     else
         launch_k(finalize_mean_kernel<double>, dim3(blocks), dim3(256), 0, s, colsum, colcnt, n_total, p, pitch, mean_d,
-                                                            (double*)native_out, miss_flag);
+                                                            (double*)native_out, miss_flag, nmiss);
     return cudaGetLastError();
 }
 
@@ -77,20 +87,12 @@ cudaError_t launch_normalize_q(const double* qraw, int m, int pitch, double* qco
     return cudaGetLastError();
 }
 
-__global__ void normalize_q_stop_kernel(const double* qraw, int m, int pitch, double* qcol, double* qvec,
-                                        const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol) {
-    pdl_prologue();
-    if (trip_is_dead(ctrl, trip)) return;
-    if (threadIdx.x != 0) return;
-    normalize_q_stop_body(qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
-}
-
 // 32 columns x 8 part-groups, the fold of reduce_cols_kernel (passes.cu) for one 32-column chunk
 __global__ void __launch_bounds__(256) reduce_q_stop_kernel(const double* part, int n_parts, int stride, double* qraw, int m,
                                                             int pitch, double* qcol, double* qvec, const double* gram,
-                                                            double* q_prev, Ctrl* ctrl, int trip, double tol) {
+                                                            double* q_prev, Ctrl* ctrl, const LoopEnd e) {
     pdl_prologue();
-    if (trip_is_dead(ctrl, trip)) return;
+    if (trip_is_dead(ctrl, 0)) return;
     __shared__ double fold[8][33];
     const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
     double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
@@ -114,20 +116,14 @@ __global__ void __launch_bounds__(256) reduce_q_stop_kernel(const double* part, 
         qraw[c] = t;
     }
     __syncthreads();
-    if (threadIdx.x == 0) normalize_q_stop_body(fold[0], m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
+    if (threadIdx.x == 0) normalize_q_stop_body(fold[0], m, pitch, qcol, qvec, gram, q_prev, ctrl, e);
 }
 
 cudaError_t launch_reduce_q_stop(const double* part, int n_parts, int stride, double* qraw, int m, int pitch, double* qcol,
-                                 double* qvec, const double* gram, double* q_prev, Ctrl* ctrl, int trip, double tol,
+                                 double* qvec, const double* gram, double* q_prev, Ctrl* ctrl, const LoopEnd& e,
                                  cudaStream_t s) {
     if (pitch > 32 || m > 8) return cudaErrorInvalidValue;
-    launch_k(reduce_q_stop_kernel, dim3(1), dim3(256), 0, s, part, n_parts, stride, qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_normalize_q_stop(const double* qraw, int m, int pitch, double* qcol, double* qvec, const double* gram,
-                                    double* q_prev, Ctrl* ctrl, int trip, double tol, cudaStream_t s) {
-    launch_k(normalize_q_stop_kernel, dim3(1), dim3(32), 0, s, qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, trip, tol);
+    launch_k(reduce_q_stop_kernel, dim3(1), dim3(256), 0, s, part, n_parts, stride, qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, e);
     return cudaGetLastError();
 }
 
@@ -147,23 +143,18 @@ cudaError_t launch_sum_small(const double* parts, int n, double* out, const Ctrl
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) stop_kernel(Ctrl* ctrl, int trip, const double* parts, int n, double tol) {
+__global__ void __launch_bounds__(256) stop_kernel(Ctrl* ctrl, const double* parts, int n, const LoopEnd e) {
     pdl_prologue();
-    if (trip_is_dead(ctrl, trip)) return;
+    if (trip_is_dead(ctrl, 0)) return;
     __shared__ double red[40];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s += parts[i];
     s = block_sum(s, red);
-    if (threadIdx.x == 0) {
-        ctrl->trips_taken = trip + 1;
-        ctrl->last_d2 = s;
-        // trip 0 compares against +inf in the reference (tpls.py:77) and can never stop
-        if (trip >= 1 && sqrt(s) < tol) ctrl->done_trip = trip;
-    }
+    if (threadIdx.x == 0) ctrl_decide(ctrl, s, e);
 }
 
-cudaError_t launch_stop(Ctrl* ctrl, int trip, const double* parts, int n, double tol, cudaStream_t s) {
-    launch_k(stop_kernel, dim3(1), dim3(256), 0, s, ctrl, trip, parts, n, tol);
+cudaError_t launch_stop(Ctrl* ctrl, const double* parts, int n, const LoopEnd& e, cudaStream_t s) {
+    launch_k(stop_kernel, dim3(1), dim3(256), 0, s, ctrl, parts, n, e);
     return cudaGetLastError();
 }
 
@@ -172,6 +163,8 @@ __global__ void reset_ctrl_kernel(Ctrl* ctrl) {
     ctrl->done_trip = -1;
     ctrl->trips_taken = 0;
     ctrl->last_d2 = 0.0;
+    ctrl->trip = 0;
+    ctrl->stop = 0;
 }
 
 cudaError_t launch_reset_ctrl(Ctrl* ctrl, cudaStream_t s) {
@@ -200,7 +193,7 @@ cudaError_t launch_multi_dot(const DotPairs& d, double* part, int* grid_out, cud
 }
 
 __global__ void solve_coef_kernel(const double* dots, double* gram, double* coef, int R, int a, const Ctrl* ctrl,
-                                  int* trips_out) {
+                                  int* trips_out, int* conv_out) {
     pdl_prologue();
     if (threadIdx.x != 0) return;
     const int k = a + 1;
@@ -230,11 +223,12 @@ __global__ void solve_coef_kernel(const double* dots, double* gram, double* coef
     }
     for (int b = 0; b < k; ++b) coef[b * R + a] = x[b];
     if (trips_out != nullptr && ctrl != nullptr) trips_out[a] = ctrl->trips_taken;
+    if (conv_out != nullptr && ctrl != nullptr) conv_out[a] = ctrl->done_trip >= 0 ? 1 : 0;
 }
 
 cudaError_t launch_solve_coef(const double* dots, double* gram, double* coef, int R, int a, const Ctrl* ctrl,
-                              int* trips_out, cudaStream_t s) {
-    launch_k(solve_coef_kernel, dim3(1), dim3(32), 0, s, dots, gram, coef, R, a, ctrl, trips_out);
+                              int* trips_out, int* conv_out, cudaStream_t s) {
+    launch_k(solve_coef_kernel, dim3(1), dim3(32), 0, s, dots, gram, coef, R, a, ctrl, trips_out, conv_out);
     return cudaGetLastError();
 }
 

@@ -1,6 +1,6 @@
 // One-shot peer-memory all-reduce fused with the local second-stage reduction -- see xchg.cuh.
 #include "xchg.cuh"
-#include "small.cuh"
+#include "stream_common.cuh"
 
 #include <algorithm>
 
@@ -26,45 +26,37 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
 __global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgArgs a) {
     pdl_prologue();
     __shared__ double fold[8][33];
-    const int slot = (int)(a.seq & 1ull);
+    // the sequence number of THIS exchange: the counter is advanced by the last CTA to finish phase 1, i.e. after
+    // every CTA of the launch has read it
+    const unsigned long long seq = *reinterpret_cast<const volatile unsigned long long*>(a.seq_ctr) + 1ull;
+    const int slot = (int)(seq & 1ull);
     const size_t base = (size_t)slot * a.cap;
     double* mine = a.data[a.rank] + base;
     const int cl = threadIdx.x & 31, q = threadIdx.x >> 5;
     const int n_chunks = (a.count + 31) >> 5;
 
     // ---- phase 1: fold the local partials of my chunks into the local slot ----
-    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const int idx = chunk * 32 + cl;
-        double v = 0.0;
-        if (a.n_sets == 0) {
-            if (q == 0 && idx < a.count) v = a.in[idx];
-        } else if (idx < a.count) {
-            // which block of partials does this element belong to?
-            int s = 0;
-            while (s + 1 < a.n_sets && idx >= a.sets[s + 1].off) ++s;
-            const XchgSet& S = a.sets[s];
-            const int c = idx - S.off;
-            if (c < S.n_cols) {
-                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-                int b = q;
-                for (; b + 24 < S.n_parts; b += 32) {
-                    t0 += S.part[(size_t)(b + 0) * S.stride + c];
-                    t1 += S.part[(size_t)(b + 8) * S.stride + c];
-                    t2 += S.part[(size_t)(b + 16) * S.stride + c];
-                    t3 += S.part[(size_t)(b + 24) * S.stride + c];
-                }
-                for (; b < S.n_parts; b += 8) t0 += S.part[(size_t)b * S.stride + c];
-                v = (t0 + t1) + (t2 + t3);
-            }
+    if (a.n_sets == 0) {
+        for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+            const int idx = chunk * 32 + cl;
+            if (q == 0 && idx < a.count) mine[idx] = a.in[idx];
         }
-        __syncthreads();
-        fold[q][cl] = v;
-        __syncthreads();
-        if (q == 0 && idx < a.count) {
-            double t = 0.0;
+    } else {
+        const int n_fold = fold_chunks(a.sets, a.n_sets);
+        for (int chunk = blockIdx.x; chunk < n_fold; chunk += gridDim.x) {
+            int c_base = 0;
+            const FoldSet& S = a.sets[fold_locate(a.sets, a.n_sets, chunk, &c_base)];
+            const int c = c_base + cl;
+            const double v = fold_share(S, c, q);
+            __syncthreads();
+            fold[q][cl] = v;
+            __syncthreads();
+            if (q == 0 && c < S.n_cols) {
+                double t = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) t += fold[k][cl];
-            mine[idx] = t;
+                for (int k = 0; k < 8; ++k) t += fold[k][cl];
+                mine[S.off + c] = t;
+            }
         }
     }
     __syncthreads();
@@ -73,13 +65,14 @@ __global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgA
         const unsigned int old = atomicAdd(a.done_ctr, 1u);
         if (old == gridDim.x - 1) {
             atomicExch(a.done_ctr, 0u);
+            *reinterpret_cast<volatile unsigned long long*>(a.seq_ctr) = seq;
             __threadfence_system();
-            for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, a.seq);
+            for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, seq);
         }
         // ---- phase 2: wait for every rank's announcement in the LOCAL flag words ----
         const long long t0 = clock64();
         for (int r = 0; r < a.world; ++r) {
-            while (ld_acquire_sys(a.flags[a.rank] + r) < a.seq) {
+            while (ld_acquire_sys(a.flags[a.rank] + r) < seq) {
                 if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died
                     atomicExch(a.err, 1);
                     break;
@@ -101,23 +94,20 @@ __global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgA
 #pragma unroll
             for (int k = 0; k < 8; ++k) t += fold[k][cl];
             a.out[idx] = t;
-            if (a.do_stop && idx == 0 && !trip_is_dead(a.ctrl, a.trip)) {
-                a.ctrl->trips_taken = a.trip + 1;
-                a.ctrl->last_d2 = t;
-                if (a.trip >= 1 && sqrt(t) < a.tol) a.ctrl->done_trip = a.trip;
-            }
+            if (a.do_stop && idx == 0 && !trip_is_dead(a.ctrl, 0)) ctrl_decide(a.ctrl, t, a.loop_end);
         }
     }
     if (a.do_qstop) {  // count <= 32: this is the only CTA and a.out is complete after the barrier
         __syncthreads();
-        if (threadIdx.x == 0 && !trip_is_dead(a.ctrl, a.trip))
-            normalize_q_stop_body(a.out, a.q_m, a.q_pitch, a.qcol, a.qvec, a.gram, a.q_prev, a.ctrl, a.trip, a.tol);
+        if (threadIdx.x == 0 && !trip_is_dead(a.ctrl, 0))
+            normalize_q_stop_body(a.out, a.q_m, a.q_pitch, a.qcol, a.qvec, a.gram, a.q_prev, a.ctrl, a.loop_end);
     }
 }
 
 cudaError_t launch_xchg(const XchgArgs& a, cudaStream_t s) {
-    const int n_chunks = (a.count + 31) / 32;
+    const int n_chunks = std::max((a.count + 31) / 32, a.n_sets > 0 ? fold_chunks(a.sets, a.n_sets) : 0);
     if (a.do_qstop && (a.count > 32 || a.q_m > 8)) return cudaErrorInvalidValue;
+    if (a.n_sets > kMaxFoldSets) return cudaErrorInvalidValue;
     const int blocks = std::max(1, std::min(444, n_chunks));  // all CTAs must be co-resident: 3 per SM is safe
     launch_k(xchg_kernel, dim3(blocks), dim3(256), 0, s, a);
     return cudaGetLastError();

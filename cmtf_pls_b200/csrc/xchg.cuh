@@ -5,6 +5,7 @@
 //   flags[r]      sequence number of the latest exchange rank r has published here
 //   data[2][cap]  two slots, used alternately
 // One kernel per exchange and rank:
+//   (0) every CTA reads the sequence number of this exchange from the device counter (+1);
 //   (1) fold this rank's per-CTA partials (or copy a ready vector) straight into the local slot,
 //       fence at system scope, and let the last CTA announce `seq` in every peer's flag word with
 //       a remote store;
@@ -17,40 +18,37 @@
 // Replaces reduce_cols + ncclAllReduce (+ stop) on the per-trip critical path.
 #pragma once
 
-#include "common.cuh"
+#include "passes.cuh"
+#include "small.cuh"
 
 namespace tpls {
 
 constexpr int kXchgMaxRanks = 16;
-constexpr int kXchgMaxSets = 8;
 constexpr size_t kXchgHeaderBytes = 1024;
-
-struct XchgSet {          // one block of per-CTA partials to fold: out[off + c] = sum_b part[b*stride + c]
-    const double* part;
-    int n_parts, stride, n_cols, off;
-};
+// header of an exchange buffer: flags[kXchgMaxRanks] (u64) | +512 done counter (u32) | +520 error word (i32) |
+// +528 sequence number of the last exchange this rank completed (u64; kept on the DEVICE so that an exchange can
+// sit in the body of a CUDA-graph loop)
 
 struct XchgArgs {
-    // input: either `n_sets` partial blocks, or (n_sets == 0) the ready vector `in`
-    XchgSet sets[kXchgMaxSets];
+    // input: either `n_sets` partial blocks (folded into the slot at their `off`), or (n_sets == 0) the ready vector `in`
+    FoldSet sets[kMaxFoldSets];
     int n_sets;
     const double* in;
     double* out;             // summed vector [count] (may alias in)
     int count;
     int cap;                 // doubles per slot
     int rank, world;
-    unsigned long long seq;  // 1, 2, 3, ... identical on all ranks
+    unsigned long long* seq_ctr;               // local: exchanges completed so far (identical on all ranks)
     unsigned long long* flags[kXchgMaxRanks];  // flags[r] = rank r's flag array (flags[rank] is local)
     double* data[kXchgMaxRanks];               // data[r] = rank r's slots
     unsigned int* done_ctr;                    // local: CTAs that finished phase 1
     int* err;                                  // local: set to 1 on a wait timeout
-    // optional stop test on out[0] (tpls.py:103): trip >= 1 and sqrt(out[0]) < tol
+    // optional stop test on out[0] = ||u_old - u_new||^2 (tpls.py:103), see ctrl_decide
     Ctrl* ctrl;
-    int trip;
-    double tol;
+    LoopEnd loop_end;
     int do_stop;
     // optional (count <= 32, one CTA): `out` is the raw q = Y't -- normalise it and run the stop test through
-    // dq^T (Y'Y) dq in this kernel (small.cuh normalize_q_stop_body); uses ctrl / trip / tol above
+    // dq^T (Y'Y) dq in this kernel (small.cuh normalize_q_stop_body); uses ctrl / loop_end above
     int do_qstop;
     int q_m, q_pitch;
     double* qcol;

@@ -81,29 +81,30 @@ class tPLS(Mapping):
         self.X_hasMiss = st["has_miss"][0]
         if self.X_hasMiss:
             print("X has missing values")
-        self._X_ref = X
-        self._Y_ref = Y
+        self._X_ref = _core.weak_ref(X)   # for X_miss / get_q2y only; the caller's arrays are not kept alive
+        self._Y_ref = _core.weak_ref(Y)
         self.X_mean = st["X_mean"][0]
         self.Y_mean = st["Y_mean"]
         self.coef_ = st["coef"]
         self.n_iter_ = st["trips"]
         # the reference is silent when max_iter is exhausted (tpls.py:79-107); here it can be asked
-        self.converged_ = st["trips"] < max_iter
+        self.converged_ = st["converged"]
         self.stats_ = st["stats"]
         self._profile = st["profile"]
         self._device = st["device"]
         if verbose:
             for a, k in enumerate(self.n_iter_):
-                if k < max_iter:
+                if self.converged_[a]:
                     print("Comp {}: converged after {} iterations".format(a, k - 1))
 
     @property
     def X_miss(self):
-        """Positions of missing values of the training X (tpls.py:64), computed on demand."""
-        X = self._X_ref
-        if _core._is_torch(X):
-            return X.isnan().cpu().numpy()
-        return np.isnan(X)
+        """Positions of missing values of the training X (tpls.py:64).  The reference materialises this N x P
+        boolean tensor in every fit; here it is computed on demand: all False when the fit saw no NaN, else
+        from the training array, which is referenced WEAKLY (it is neither kept alive nor pickled)."""
+        if not self.X_hasMiss:
+            return np.zeros(self.X_shape, dtype=bool)
+        return _core.isnan_of(getattr(self, "_X_ref", None), "X_miss")
 
     @property
     def profile_(self):

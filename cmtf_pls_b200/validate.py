@@ -119,13 +119,18 @@ def get_q2y(pls_tensor, X=None, Y=None, n_splits=None, seed=0):
     """Q2Y of a fitted estimator's configuration (validate.py:7): leave-one-out by
     default like the reference, K-fold when ``n_splits`` is given.  ``X`` / ``Y``
     default to the arrays the estimator was fitted on."""
+    def alive(ref):   # the estimators reference their training arrays weakly
+        return ref() if ref is not None else None
     if X is None:
-        X = getattr(pls_tensor, "_X_ref", None)
-        if X is None:
-            X = getattr(pls_tensor, "_Xs_ref", None)
+        if hasattr(pls_tensor, "_X_ref"):
+            X = alive(pls_tensor._X_ref)
+        elif hasattr(pls_tensor, "_Xs_ref"):
+            X = [alive(r) for r in pls_tensor._Xs_ref]
+            X = None if any(x is None for x in X) else X
     if Y is None:
-        Y = getattr(pls_tensor, "_Y_ref", None)
-    assert X is not None and Y is not None, "PLS Tensor must be fit prior to calculating Q2Y"
+        Y = alive(getattr(pls_tensor, "_Y_ref", None))
+    assert X is not None and Y is not None, \
+        "PLS Tensor must be fit prior to calculating Q2Y (and its training arrays still alive, or passed as X / Y)"
     q2 = q2y_sweep(X, Y, pls_tensor.n_components, n_splits=n_splits, seed=seed,
                    device=getattr(pls_tensor, "_device", None))
     return float(q2[-1])

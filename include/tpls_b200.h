@@ -58,7 +58,8 @@ enum {
     TPLS_K_RANK1 = 5,            /* single-CTA rank-1 step (tpls.py:84-88) */
     TPLS_K_YSIDE = 6,            /* passes over Y (q, u, Y deflation) */
     TPLS_K_OTHER = 7,            /* second reduction stages and the scalar tail of a trip */
-    TPLS_K_NCCL = 8              /* all-reduces */
+    TPLS_K_NCCL = 8,             /* ncclAllReduce calls */
+    TPLS_K_XCHG = 9              /* peer-memory exchange kernels (second reduction stage + sum over the ranks) */
 };
 #define TPLS_N_KERNEL_CLASSES 10
 
@@ -73,6 +74,9 @@ const char* tpls_last_error(tpls_handle h);
  * enqueue on, or NULL for a private non-blocking stream. */
 int tpls_create(tpls_handle* out, int device, void* cuda_stream);
 int tpls_destroy(tpls_handle h);
+/* Rebinds the handle to another stream (NULL: back to the private one).  Work already enqueued is waited for
+ * first, so one handle per device can follow the caller's current stream from call to call. */
+int tpls_set_stream(tpls_handle h, void* cuda_stream);
 
 /* Multi-GPU (one process per GPU).  Rank 0 obtains a 128-byte id, the caller
  * broadcasts it by any means, every rank calls tpls_comm_init. */
@@ -115,6 +119,8 @@ int tpls_get_x_mean(tpls_handle h, int index, void* out);                /* shap
 int tpls_get_y_mean(tpls_handle h, double* out);                         /* (m,) */
 int tpls_get_has_missing(tpls_handle h, int index, int* out);
 int tpls_get_trips(tpls_handle h, int* out);                             /* (R,) inner iterations taken */
+int tpls_get_converged(tpls_handle h, int* out);                         /* (R,) 1 = the component met the stop test of
+                                                                            tpls.py:103 (possibly on the last allowed trip) */
 
 typedef struct tpls_stats {
     double fit_ms;              /* device time of the last tpls_fit (CUDA events on the handle's stream) */
@@ -126,6 +132,10 @@ typedef struct tpls_stats {
     double h2d_bytes;           /* bytes staged host->device by tpls_set_x / tpls_set_y since the last fit */
     int64_t covariance_mode;    /* 1 when the last fit ran the cross-covariance loop */
     int64_t last_transform_path; /* last tpls_transform: 1 = read-only path (complete data), 2 = sequential path */
+    int64_t graph_launches;     /* 1 when the last fit ran as ONE CUDA graph (a WHILE node per component: the host takes
+                                   no part in the inner loops), 0 when the host enqueued the trips */
+    int64_t launches_per_trip;  /* kernels in one inner trip of the last streaming fit (3 + 2 * n_tensors when the Y side
+                                   is fused into the X passes) */
 } tpls_stats;
 int tpls_get_stats(tpls_handle h, tpls_stats* out);
 
