@@ -43,6 +43,11 @@ DIMS = (64, 64)
 M, LATENT, ERROR, R = 4, 12, 1.0, 10
 CPU_SAMPLE_ROWS = int(os.environ.get("CMTF_BENCH_CPU_ROWS", "4096"))   # rows of the bounded CPU sample (tests shrink it)
 CPU_SAMPLE_R = 3
+# golden cases of the parity gate (fp64; tests/golden/*.npz): coupled pair, NaNs, 4-way X, 30 responses (the path with
+# an explicit ||u_old - u_new||^2 exchange), a non-converging 4-way case
+PARITY_CASES = ["ct_90x32x16_90x24_m4_r5", "t3_miss_70x12x8_m4_r4", "t4_60x8x6x4_m3_r4", "t2_same_xy_40x30_r4",
+                "t4_maxiter_20x6x5x4_m5_r2"]
+PARITY_TOL = 1e-8
 
 
 def measured_peak_gbs():
@@ -242,6 +247,29 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity gate (before anything is timed): golden cases minted from the reference's unmodified source,
+    #      fitted with their rows sharded over the N ranks, against the stored single-process result.  The files hold
+    #      the answers, so no oracle code runs here.  A failure ends the run with a non-zero exit code.
+    parity = None
+    if not args.no_parity:
+        from cmtf_pls_b200.selfcheck import sharded_golden_check
+
+        def gather_rows(local_rows, n_all, lo, hi):
+            full = torch.zeros((n_all,) + tuple(local_rows.shape[1:]), dtype=torch.float64, device=dev)
+            full[lo:hi] = torch.from_numpy(np.ascontiguousarray(local_rows)).to(dev)
+            dist.all_reduce(full)
+            return full.cpu().numpy()
+
+        parity = sharded_golden_check(PARITY_CASES, local, process_group=group, rank=rank, world=world, gather=gather_rows)
+        parity["tolerance"] = PARITY_TOL
+        parity["ok"] = bool(parity["trips_equal"] and parity["max_err"] < PARITY_TOL)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"parity_check": parity, "error": "sharded fit does not match the golden vectors"}), flush=True)
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(3)
+
     est = ctPLS(R, device=local, process_group=group)
     for _ in range(args.warmup):
         est.fit(Xs, Y)
@@ -427,6 +455,7 @@ def run_ours(args):
                    "host_ms_last_fit": host_ms_last,
                    "covariance_mode": cov, "transform": xform},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "parity_check": parity,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
@@ -444,6 +473,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the total sample count (debugging)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity gate (debugging)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
