@@ -338,25 +338,54 @@ def run_ours(args):
     except Exception as exc:  # noqa: BLE001
         cov = {"error": repr(exc)[:200]}
 
-    # ---- transform of the resident shard through the fitted model: complete data is read
-    #      in place, R projection passes + the score recurrence; the (n, R) scores come back to the host ----
+    # ---- transform of the resident shard through the fitted model: complete data is read in
+    #      place ONCE (all R projections in one pass on the fp64 tensor-core path + the score recurrence); the
+    #      (n, R) scores come back to the host.  Beside it: the masked (sequential) path on a NaN-carrying copy of
+    #      the first rows, and the device reconstruction X_hat = T W + mean of a block of rows ----
     xform = None
     try:
+        from cmtf_pls_b200 import _core as _c
         est.transform(Xs)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(2):
+        for _ in range(3):
             est.transform(Xs)
         barrier()
-        dt = (time.perf_counter() - t0) / 2
+        dt = (time.perf_counter() - t0) / 3
+        st_x = _c.get_engine(local).stats()
         tt2 = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
-        moved = 2 * 4.0 * n_total * 4096 * R
+        passes = 1 if st_x["last_transform_path"] == 1 else 2 * R + 1
+        moved = 2 * 4.0 * n_total * 4096 * passes
         xform = {"s_per_call": tt2.item(), "rows_per_s": n_total / tt2.item(), "gbs_on_bytes_moved": moved / tt2.item() / 1e9,
-                 "passes": R, "includes": "D2H of the scores, host clock"}
+                 "passes": passes, "kernel_launches": int(st_x["kernel_launches"]),
+                 "fp64_fma_per_call": 2.0 * n_total * 4096 * R,
+                 "includes": "D2H of the scores, host clock; R=10 makes the pass as heavy in fp64 FMAs (P*R per row, padded "
+                             "to 16 components on the DMMA path) as in HBM bytes"}
+        nm = min(n_loc, 100_000)
+        Xm = [x[:nm].clone() for x in Xs]
+        for x in Xm:
+            x.view(-1)[::17] = float("nan")
+        est.transform(Xm)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        est.transform(Xm)
+        torch.cuda.synchronize()
+        dtm = time.perf_counter() - t0
+        xform["masked"] = {"rows": nm, "nan_fraction": 1 / 17, "s_per_call": dtm, "rows_per_s": nm / dtm,
+                           "gbs_on_bytes_moved": 2 * 4.0 * nm * 4096 * (3 * R + 1) / dtm / 1e9,
+                           "passes": "centre r+w, then per component a masked projection and a deflation r+w"}
+        del Xm
+        nr = min(n_loc, 20_000)
+        t0 = time.perf_counter()
+        xr = _c.run_reconstruct([est.factor_T[:nr]] + est.Xs_factors[0][1:], est.Xs_mean[0], device=local)
+        dtr = time.perf_counter() - t0
+        xform["reconstruct"] = {"rows": nr, "s_per_call": dtr, "out_gb": xr.nbytes / 1e9,
+                                "note": "device writer + D2H of the (rows, 64, 64) float64 result, host clock"}
+        del xr
     except Exception as exc:  # noqa: BLE001
-        xform = {"error": repr(exc)[:200]}
+        xform = {"error": repr(exc)[:300]}
 
     # ---- end to end through the estimator API with pinned host arrays ----
     e2e = None
@@ -371,7 +400,7 @@ def run_ours(args):
         Yh.copy_(Y)
         torch.cuda.synchronize()
         n_iter_resident = est.n_iter_.tolist()
-        del Xs, est                                # the estimator keeps a reference to its training arrays
+        del Xs, est                                # free the resident shard before the host-array fits
         torch.cuda.empty_cache()
         Xn, Yn = [h.numpy() for h in Xh], Yh.numpy()
         est2 = ctPLS(R, device=local, process_group=group)

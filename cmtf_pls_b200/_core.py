@@ -291,9 +291,12 @@ def y_scores(Y, Y_mean, Y_shape, X_scores, coef, Q):
     return out
 
 
-def rank_r_dense(factors):
-    """sum_r a_r o b_r o ... (util.py:18-20) -- used only by X_reconstructed."""
-    rest = np.ones((1, factors[0].shape[1]))
-    for f in factors[1:]:
-        rest = (rest[:, None, :] * f[None, :, :]).reshape(-1, f.shape[1])
-    return (factors[0] @ rest.T).reshape([f.shape[0] for f in factors])
+def run_reconstruct(factors, mean, device=None):
+    """sum_r a_r o b_r o ... + mean (util.py:18-20, tpls.py:188-189) on the device: one rank-R outer-product
+    writer over the (N, P) result; only the (R, P) Kronecker rows are formed on the host."""
+    R = factors[0].shape[1]
+    eng = get_engine(_device_of([], device))
+    wk = kron_rows(factors[1:], R)
+    mu = None if mean is None else np.ascontiguousarray(np.asarray(mean).reshape(-1))
+    out = eng.reconstruct(factors[0], wk, mu)
+    return out.reshape([f.shape[0] for f in factors])

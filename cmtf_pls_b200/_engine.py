@@ -87,6 +87,7 @@ SIGNATURES = {
     "tpls_trim": (C.c_int, [_H]),
     "tpls_transform": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(C.c_int), C.c_int64,
                                  C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
+    "tpls_reconstruct": (C.c_int, [_H, C.c_int, _P, C.c_int64, C.c_int64, _P, _P, C.c_int, _P]),
     "tpls_op_contract": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P, C.POINTER(C.c_float), C.c_int]),
     "tpls_op_project": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P, C.POINTER(C.c_float), C.c_int]),
     "tpls_op_deflate_contract": (C.c_int, [_H, _P, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, C.c_int, _P, _P,
@@ -296,6 +297,17 @@ class Engine:
 
     def release_data(self):
         self._ck(self.lib.tpls_release_data(self.h))
+
+    def reconstruct(self, scores, wkron, mean):
+        """(n, p) float64: mean + scores @ wkron, formed on the device (tpls.py:188-189)."""
+        scores = np.ascontiguousarray(scores, dtype=np.float64)
+        wkron = np.ascontiguousarray(wkron, dtype=np.float64)
+        n, R = scores.shape
+        p = wkron.shape[1]
+        out = self._host_out(n, p)
+        mp, md = (None, 0) if mean is None else (mean.ctypes.data, dtype_code(mean))
+        self._ck(self.lib.tpls_reconstruct(self.h, R, scores.ctypes.data, n, p, wkron.ctypes.data, mp, md, out.ctypes.data))
+        return out
 
     def transform(self, xs, means, wkrons, proj_offset=None, proj_gram=None):
         """xs[l]: (n_new, ...) array/tensor; means[l]: numpy, X's dtype; wkrons[l]: (R, P) float64 numpy;

@@ -131,4 +131,5 @@ class ctPLS(Mapping):
         return X_scores
 
     def Xs_reconstructed(self):
-        return [_core.rank_r_dense(self.Xs_factors[ti]) + self.Xs_mean[ti] for ti in range(self.Xs_len)]
+        return [_core.run_reconstruct(self.Xs_factors[ti], self.Xs_mean[ti], device=getattr(self, "_device", self.device))
+                for ti in range(self.Xs_len)]

@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
             // optional 0/1 sample weights (cross-validation folds): weighted column statistics and
             // weighted residual norm; the row's own sum of squares is folded in once per row
             const double sw = ((COLSTAT || SUMSQ) && a.row_sw != nullptr) ? __ldg(a.row_sw + grow) : 1.0;
-            const double ss_before = ss;
+            // the row's sum of squares in two independent chains (one long chain of dependent DFMAs held the
+            // read-only residual pass at half the bandwidth), folded into ss once per row
+            double rs[2] = {0.0, 0.0};
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
                 if (!FULL && !cvalid[k]) continue;
@@ -200,13 +202,15 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
                         cacc[k][j] += ob ? sw : 0.0;
                         nmiss += ob ? 0 : 1;
                     }
-                    if (SUMSQ) ss = fma(xd, xd, ss);
+                    if (SUMSQ) rs[j & 1] = fma(xd, xd, rs[j & 1]);
                 }
                 if (WRITE) {
                     __stcs(reinterpret_cast<typename VecOf<XT>::type*>(xo + grow * g.pitch + c0 + cg * VEC), out.v);
                 }
             }
-            if (SUMSQ && a.row_sw != nullptr) ss = fma(sw, ss - ss_before, ss_before);
+            if (SUMSQ) {
+                ss = fma(sw, rs[0] + rs[1], ss);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);

@@ -123,6 +123,43 @@ size_t covpass_smem(const PassGeom& g, int pitch_y, int mr);
 // mr = accumulators per column: next power of two >= m (dense) or >= 2m (masked: second block row-rescaled)
 cudaError_t launch_covpass(int dtype, bool masked, int mr, const CovPassArgs& a, cudaStream_t s);
 
+// Single-pass multi-component projection (multiproj.cu): part[slab][row][a] = sum over the slab's columns of
+// x[row, c] * w[a][c], a < n_comp <= 32, on the fp64 tensor-core path.  Complete data only (a NaN poisons its row,
+// which the finishing kernel reports).
+struct MultiProjArgs {
+    const void* x;          // [n_rows][pitch] in the storage type
+    long long n_rows;
+    int p, pitch;
+    const double* w;        // [n_comp][w_pitch]
+    int w_pitch, n_comp;
+    double* part;           // [n_slabs][n_rows][n_comp]
+};
+int multiproj_slabs(int dtype, int n_comp, int pitch);
+cudaError_t launch_multiproj(int dtype, const MultiProjArgs& a, int sm_count, cudaStream_t s);
+
+struct MultiProjFinishArgs {
+    const double* part[8];  // per coupled tensor
+    int n_slabs[8];
+    int n_tensors, n_comp;
+    long long n_rows;
+    const double* c;        // [n_comp] offsets  mean_l <mean_l, w_l[a]>
+    const double* G;        // [n_comp][n_comp]  mean_l <w_l[b], w_l[a]>
+    double* S;              // out: scores, column-major n_rows x n_comp
+    int* flag;              // |= 1 when a row holds NaNs
+};
+cudaError_t launch_multiproj_finish(const MultiProjFinishArgs& a, cudaStream_t s);
+
+// X_hat = T W + mean (util.py:18-20): out [n_rows][p] fp64
+struct ReconstructArgs {
+    const double* T;        // [n_rows][n_comp], C order
+    const double* w;        // [n_comp][w_pitch]
+    const double* mean;     // [p] or nullptr
+    long long n_rows;
+    int p, w_pitch, n_comp;
+    double* out;
+};
+cudaError_t launch_reconstruct(const ReconstructArgs& a, cudaStream_t s);
+
 // out[c] = sum_b part[b*stride + c]  (fixed order => bit-reproducible); optionally
 // ss_out[0] = sum of sspart[0..n_ss).
 struct ReduceArgs {

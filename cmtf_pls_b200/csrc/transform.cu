@@ -11,7 +11,10 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
     const int L = n_tensors, R = n_components;
     if (L < 1 || L > TPLS_MAX_TENSORS || R < 1 || R > 64 || n_new <= 0) return fail(h, "tpls_transform: bad sizes");
     CK(cudaSetDevice(h->device));
+    NvtxRange nvtx_tr("tpls_transform");
     cudaStream_t st = h->stream;
+    h->stats.kernel_launches = 0;
+    h->stats.streamed_bytes = 0;
     std::vector<void*> tmp;
     double *S = nullptr, *sspart = nullptr, *pc = nullptr, *pg = nullptr;
     int* flag = nullptr;
@@ -77,12 +80,15 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
         }
         if (rc) break;
 
-        // ---- read-only path for complete data: R raw projections of the UNTOUCHED rows, then the
-        //      deflation recurrence on the scores alone.  With x_c = x - mean and no NaN,
+        // ---- single-pass path for complete data: ALL R raw projections of the untouched rows in ONE read of X
+        //      (multiproj.cu, fp64 tensor-core path), then the deflation recurrence on the scores alone.  With
+        //      x_c = x - mean and no NaN,
         //        t_a = mean_l (x_c - sum_{b<a} t_b w_lb) . w_la = r_a - c_a - sum_{b<a} t_b G_ba,
         //      r_a = mean_l x . w_la,  c_a = mean_l mean_l . w_la,  G_ba = mean_l w_lb . w_la  (passed in).
+        //      A NaN poisons the raw projections of its row; the finishing kernel reports it and the call falls
+        //      through to the sequential masked path.
         bool done = false;
-        if (proj_offset != nullptr && proj_gram != nullptr) {
+        if (proj_offset != nullptr && proj_gram != nullptr && R <= 32) {
             cudaError_t e = cudaMemcpyAsync(pc, proj_offset, sizeof(double) * R, cudaMemcpyDefault, st);
             if (e == cudaSuccess) e = cudaMemcpyAsync(pg, proj_gram, sizeof(double) * R * R, cudaMemcpyDefault, st);
             if (e == cudaSuccess) e = cudaMemsetAsync(flag, 0, sizeof(int) * 4, st);
@@ -90,26 +96,45 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
                 rc = fail(h, "tpls_transform: %s", cudaGetErrorString(e));
                 break;
             }
-            // component 0 doubles as the NaN census: a counting masked pass fills the per-row observed counts
+            MultiProjFinishArgs f{};
+            f.n_tensors = L;
+            f.n_comp = R;
+            f.n_rows = n_new;
+            f.c = pc;
+            f.G = pg;
+            f.S = S;
+            f.flag = flag;
             for (int l = 0; l < L && !rc; ++l) {
-                RowPassArgs r{};
-                r.g = grs_cnt[l];
-                r.x_in = src[l];
-                r.col_w = wk[l];
-                r.t_out = S;
-                r.tpart = tpart[l];
-                r.cpart = cpart[l];
-                r.rowcnt = rowcnt[l];
-                r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
-                r.div = (double)L;
-                rc = row_pass(h, dtypes[l], 2, r);
-                if (!rc) {
-                    cudaError_t e2 = launch_rows_complete(rowcnt[l], n_new, (double)ps[l], flag, st);
-                    if (e2 != cudaSuccess) rc = fail(h, "rows_complete -> %s", cudaGetErrorString(e2));
-                    h->stats.kernel_launches++;
+                const int ns = multiproj_slabs(dtypes[l], R, pitch[l]);
+                double* part = nullptr;
+                if ((rc = dev_alloc(h, (void**)&part, sizeof(double) * (size_t)ns * n_new * R, &tmp))) break;
+                MultiProjArgs m{};
+                m.x = src[l];
+                m.n_rows = n_new;
+                m.p = (int)ps[l];
+                m.pitch = pitch[l];
+                m.w = wk[l];
+                m.w_pitch = pitch[l];
+                m.n_comp = R;
+                m.part = part;
+                const double bytes = (double)n_new * pitch[l] * elem[l];
+                {
+                    ProfScope psx(h, TPLS_K_PROJECT, bytes);
+                    cudaError_t e2 = launch_multiproj(dtypes[l], m, h->sm_count, st);
+                    if (e2 != cudaSuccess) rc = fail(h, "multiproj -> %s", cudaGetErrorString(e2));
                 }
+                h->stats.kernel_launches++;
+                h->stats.streamed_bytes += bytes;
+                f.part[l] = part;
+                f.n_slabs[l] = ns;
             }
             if (rc) break;
+            cudaError_t e4 = launch_multiproj_finish(f, st);
+            if (e4 != cudaSuccess) {
+                rc = fail(h, "multiproj_finish -> %s", cudaGetErrorString(e4));
+                break;
+            }
+            h->stats.kernel_launches++;
             int incomplete = 1;
             cudaError_t e3 = cudaMemcpyAsync(&incomplete, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
             if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(st);
@@ -117,29 +142,7 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
                 rc = fail(h, "tpls_transform: %s", cudaGetErrorString(e3));
                 break;
             }
-            if (!incomplete) {
-                for (int a = 1; a < R && !rc; ++a)
-                    for (int l = 0; l < L && !rc; ++l) {
-                        RowPassArgs r{};
-                        r.g = grs[l];
-                        r.x_in = src[l];
-                        r.col_w = wk[l] + (size_t)a * pitch[l];
-                        r.t_out = S + (size_t)a * n_new;
-                        r.tpart = tpart[l];
-                        r.cpart = cpart[l];
-                        r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
-                        r.div = (double)L;
-                        rc = row_pass(h, dtypes[l], 0, r);
-                    }
-                if (rc) break;
-                cudaError_t e4 = launch_score_recurrence(S, n_new, R, pc, pg, st);
-                if (e4 != cudaSuccess) {
-                    rc = fail(h, "score_recurrence -> %s", cudaGetErrorString(e4));
-                    break;
-                }
-                h->stats.kernel_launches++;
-                done = true;
-            }
+            done = !incomplete;
         }
 
         // ---- sequential path (NaNs present, or no projection constants): centre a private copy, then per
@@ -188,6 +191,64 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
     } while (0);
     cudaStreamSynchronize(st);
     for (void* p : tmp) pool_put(h, p);
+    return rc;
+}
+
+int tpls_reconstruct(tpls_handle h, int n_components, const double* scores, int64_t n, int64_t p, const double* wkron,
+                     const void* mean, int mean_dtype, double* out) {
+    if (!h) return fail(nullptr, "NULL handle");
+    const int R = n_components;
+    if (R < 1 || R > 32 || n <= 0 || p <= 0 || p > (1ll << 30)) return fail(h, "tpls_reconstruct: bad sizes");
+    if (mean != nullptr && mean_dtype != TPLS_F32 && mean_dtype != TPLS_F64) return fail(h, "tpls_reconstruct: bad mean dtype");
+    CK(cudaSetDevice(h->device));
+    NvtxRange nvtx_rc("tpls_reconstruct");
+    cudaStream_t st = h->stream;
+    std::vector<void*> tmp;
+    int rc = 0;
+    do {
+        double *T = nullptr, *W = nullptr, *mean_d = nullptr, *blk = nullptr;
+        void* mean_nat = nullptr;
+        if ((rc = dev_alloc(h, (void**)&T, sizeof(double) * n * R, &tmp))) break;
+        if ((rc = dev_alloc(h, (void**)&W, sizeof(double) * p * R, &tmp))) break;
+        cudaError_t e = cudaMemcpyAsync(T, scores, sizeof(double) * n * R, cudaMemcpyDefault, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(W, wkron, sizeof(double) * p * R, cudaMemcpyDefault, st);
+        if (e == cudaSuccess && mean != nullptr) {
+            const size_t me = mean_dtype == TPLS_F32 ? 4 : 8;
+            if ((rc = dev_alloc(h, (void**)&mean_d, sizeof(double) * p, &tmp))) break;
+            if ((rc = dev_alloc(h, &mean_nat, me * p, &tmp))) break;
+            e = cudaMemcpyAsync(mean_nat, mean, me * p, cudaMemcpyDefault, st);
+            if (e == cudaSuccess) e = launch_widen(mean_dtype, mean_nat, mean_d, (int)p, st);
+        }
+        if (e != cudaSuccess) {
+            rc = fail(h, "tpls_reconstruct: staging -> %s", cudaGetErrorString(e));
+            break;
+        }
+        const bool out_dev = is_device_ptr(out);
+        // a host result is produced block by block through one device buffer of at most 256 MB
+        const long long blk_rows = out_dev ? n : std::max<long long>(32, std::min<long long>(n, (256ll << 20) / (8 * p)));
+        if (!out_dev && (rc = dev_alloc(h, (void**)&blk, sizeof(double) * blk_rows * p, &tmp))) break;
+        for (long long r0 = 0; r0 < n && !rc; r0 += blk_rows) {
+            const long long rows = std::min<long long>(blk_rows, n - r0);
+            ReconstructArgs a{};
+            a.T = T + r0 * R;
+            a.w = W;
+            a.mean = mean_d;
+            a.n_rows = rows;
+            a.p = (int)p;
+            a.w_pitch = (int)p;
+            a.n_comp = R;
+            a.out = out_dev ? out + r0 * p : blk;
+            cudaError_t e2 = launch_reconstruct(a, st);
+            h->stats.kernel_launches++;
+            if (e2 == cudaSuccess && !out_dev) {
+                e2 = cudaMemcpyAsync(out + r0 * p, blk, sizeof(double) * rows * p, cudaMemcpyDeviceToHost, st);
+                if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+            }
+            if (e2 != cudaSuccess) rc = fail(h, "tpls_reconstruct -> %s", cudaGetErrorString(e2));
+        }
+    } while (0);
+    cudaStreamSynchronize(st);
+    for (void* q : tmp) pool_put(h, q);
     return rc;
 }
 

@@ -131,4 +131,4 @@ class tPLS(Mapping):
         return X_scores
 
     def X_reconstructed(self):
-        return _core.rank_r_dense(self.X_factors) + self.X_mean
+        return _core.run_reconstruct(self.X_factors, self.X_mean, device=getattr(self, "_device", self.device))

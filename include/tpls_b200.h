@@ -168,6 +168,13 @@ int tpls_transform(tpls_handle h, int n_tensors, int n_components, const void* c
                    int64_t n_new, const int64_t* ps, const void* const* means, const double* const* wkrons,
                    const double* proj_offset, const double* proj_gram, double* scores_out);
 
+/* Dense reconstruction from a fitted model (X_reconstructed, tpls.py:188-189 = util.py:18-20 + the mean; the
+ * imputation path of tests/test_missingvals.py:83-91):  out[i, c] = mean[c] + sum_a scores[i, a] * wkron[a, c].
+ * scores: (n, R) float64 C-ordered; wkron: (R, p) float64; mean: p values in `mean_dtype` (or NULL);
+ * out: (n, p) float64 C-ordered.  Host or device pointers; a host `out` is filled block by block. */
+int tpls_reconstruct(tpls_handle h, int n_components, const double* scores, int64_t n, int64_t p, const double* wkron,
+                     const void* mean, int mean_dtype, double* out);
+
 /* ---- single operators (used by the parity tests and by bench.py's per-kernel roofline) ----
  * All pointers here are DEVICE pointers; x is (n, p) C-ordered with p*elem a multiple of 16. */
 /* z[p] = sum_i x[i,:] * u[i]                      tpls.py:83  (masked: missingvals.py:7-20, n_total = n) */

@@ -287,3 +287,111 @@ def test_all_missing_row_gives_nan_score_like_the_reference():
     want = orc.transform(ref, [Xn.copy()])
     keep = np.arange(6) != 2
     assert col_err(s[keep], want[keep]) < FP64_TOL
+
+
+# ---------------------------------------------------------------------------
+# single-pass multi-component projection (fp64 tensor-core path) and device reconstruction
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,extra,R,dtype", [((700, 64, 64), [], 10, np.float32), ((333, 33, 17), [(333, 24)], 12, np.float64),
+                                                 ((120, 40), [], 3, np.float64), ((90, 8, 6, 4), [(90, 50, 3)], 17, np.float32),
+                                                 ((64, 70, 30), [], 30, np.float64)])
+def test_single_pass_transform_matches_sequential_and_oracle(shape, extra, R, dtype):
+    """One read of X with R accumulators per row (multiproj.cu) == the per-component project/deflate sequence."""
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import ctPLS, _core
+    Xs, Y, _ = orc.synthetic(shape, 3, 5, error=0.5, seed=21, extra_dims=extra)
+    Xs = [x.astype(dtype) for x in (Xs if extra else [Xs])]
+    est = ctPLS(R)
+    est.fit(Xs, Y, max_iter=30)
+    Xn, _, _ = orc.synthetic((77,) + shape[1:], 3, 5, error=0.5, seed=22, extra_dims=[(77,) + e[1:] for e in extra])
+    Xn = [x.astype(dtype) for x in (Xn if extra else [Xn])]
+    eng = _core.get_engine(0)
+    got = est.transform(Xn)
+    st = eng.stats()
+    assert st["last_transform_path"] == 1
+    assert st["kernel_launches"] == len(Xs) + 1          # one pass per tensor + the finishing kernel
+    # the sequential path on the same rows: a NaN in a pad row forces it, the other rows must agree
+    Xm = [np.concatenate([x, x[:1]]) for x in Xn]
+    Xm[0][-1].reshape(-1)[0] = np.nan
+    seq = est.transform(Xm)[:-1]
+    assert eng.stats()["last_transform_path"] == 2
+    tol = FP32_TOL if dtype == np.float32 else FP64_TOL
+    assert col_err(got, seq) < tol
+    if R <= 12:   # and the oracle's transform through its own refit (later components of an over-fitted model are noise)
+        ref = orc.fit([x.copy() for x in Xs], Y.copy(), R, max_iter=30, r2_mode="residual")
+        want = orc.transform(ref, [x.copy() for x in Xn])
+        assert col_err(got[:, :3], want[:, :3]) < tol
+
+
+def test_transform_of_training_rows_reproduces_scores_config4_shape():
+    import torch
+    from cmtf_pls_b200 import ctPLS
+    torch.manual_seed(1)
+    n = 20000
+    T = torch.randn(n, 5, dtype=torch.float64, device="cuda")
+    X0 = (T @ torch.randn(5, 4096, dtype=torch.float64, device="cuda") + torch.randn(n, 4096, dtype=torch.float64, device="cuda")).float().reshape(n, 64, 64)
+    X1 = (T @ torch.randn(5, 4096, dtype=torch.float64, device="cuda") + torch.randn(n, 4096, dtype=torch.float64, device="cuda")).float().reshape(n, 64, 64)
+    Y = T @ torch.randn(5, 4, dtype=torch.float64, device="cuda")
+    est = ctPLS(10)
+    est.fit([X0, X1], Y)
+    s = est.transform([X0, X1])
+    assert col_err(s[:, :5], est.factor_T[:, :5]) < 1e-4
+
+
+@pytest.mark.parametrize("case", ["t3_60x16x12_m4_r5", "ct_90x32x16_90x24_m4_r5", "t4_miss_f32_50x6x5x4_m3_r3", "t2_50x12_m1_r3"])
+def test_device_reconstruction_matches_numpy(case):
+    """X_reconstructed (tpls.py:188-189): factors_to_tensor(X_factors) + X_mean, formed by the device writer."""
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import tPLS, ctPLS
+    g = load_golden(case)
+    R = int(g["n_components"])
+    if bool(g["coupled"]):
+        est = ctPLS(R)
+        est.fit([x.copy() for x in g["Xs"]], g["Y"].copy())
+        got, facs, means = est.Xs_reconstructed(), est.Xs_factors, est.Xs_mean
+    else:
+        est = tPLS(R)
+        est.fit(g["Xs"][0].copy(), g["Y"].copy())
+        got, facs, means = [est.X_reconstructed()], [est.X_factors], [est.X_mean]
+    for xr, f, mu, x in zip(got, facs, means, g["Xs"]):
+        want = orc.rank_r_tensor(f) + mu
+        assert xr.shape == x.shape and xr.dtype == np.float64
+        assert np.max(np.abs(xr - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+
+
+def test_stop_test_met_on_the_last_allowed_trip_counts_as_converged():
+    """trips == max_iter does not mean 'not converged'."""
+    from cmtf_pls_b200 import tPLS
+    g = load_golden("t3_60x16x12_m4_r5")
+    est = tPLS(2)
+    est.fit(g["Xs"][0].copy(), g["Y"].copy())
+    k = int(est.n_iter_[0])
+    assert est.converged_.all() and k >= 2
+    est2 = tPLS(2)
+    est2.fit(g["Xs"][0].copy(), g["Y"].copy(), max_iter=k)      # component 0 meets the test exactly on its last trip
+    assert int(est2.n_iter_[0]) == k and bool(est2.converged_[0])
+    est3 = tPLS(2)
+    est3.fit(g["Xs"][0].copy(), g["Y"].copy(), max_iter=k - 1)
+    assert int(est3.n_iter_[0]) == k - 1 and not bool(est3.converged_[0])
+
+
+def test_fit_runs_as_one_graph_and_reports_its_launches():
+    """The streaming fit is ONE CUDA-graph launch (a WHILE node per component); 3 + 2 L kernels per inner trip."""
+    import os
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import ctPLS
+    Xs, Y, _ = orc.synthetic((400, 16, 8), 3, 4, error=0.4, seed=3, extra_dims=[(400, 20)])
+    est = ctPLS(3)
+    est.fit(Xs, Y)
+    st = est.stats_
+    assert st["launches_per_trip"] == 3 + 2 * 2
+    if os.environ.get("TPLS_NO_GRAPH") is None:
+        assert st["graph_launches"] == 1
+    first = (est.n_iter_.tolist(), est.factor_T.copy())
+    est.fit(Xs, Y)                                   # same key: the instantiated graph is relaunched
+    assert est.n_iter_.tolist() == first[0] and np.array_equal(est.factor_T, first[1])
+    est.fit(Xs, Y, profile=True)                     # host-enqueued trips, same kernels, same numbers
+    assert est.stats_["graph_launches"] == 0
+    assert est.n_iter_.tolist() == first[0] and np.array_equal(est.factor_T, first[1])
+    ref = orc.fit([x.copy() for x in Xs], Y.copy(), 3, r2_mode="residual")
+    assert est.n_iter_.tolist() == ref["trips"].tolist()

@@ -48,3 +48,20 @@ def test_weights_of_one_change_nothing():
     for k in ("T", "U", "Q", "coef", "R2Y"):
         assert np.max(np.abs(a[k] - b[k])) < 1e-12, k
     assert np.max(np.abs(a["R2X"][0] - b["R2X"][0])) < 1e-12
+
+
+def test_cv_fold_with_all_nans_in_held_out_rows_stays_finite():
+    """the missing-data flag must come from an UNWEIGHTED NaN census -- a fold whose NaNs all sit in
+    held-out rows still needs the masked kernels (the dense ones would turn 0 * NaN into NaN everywhere)."""
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import q2y_sweep
+    from cmtf_pls_b200.validate import _folds
+    X, Y, _ = orc.synthetic((60, 10, 6), 3, 4, error=0.3, seed=31)
+    folds = _folds(60, 5, 1)
+    X[folds[2][0], 3, 2] = np.nan          # the only NaNs sit in ONE sample, held out by fold 2
+    X[folds[2][0], 7, 1] = np.nan
+    q_ref, cv_ref = orc.q2y_kfold(X, Y, 3, folds)
+    for alg in ("stream", "covariance"):
+        q, cv = q2y_sweep(X, Y, 3, folds=folds, return_scores=True, algorithm=alg)
+        assert np.all(np.isfinite(q)) and np.all(np.isfinite(cv))
+        assert np.max(np.abs(q - q_ref)) < 1e-8, alg
