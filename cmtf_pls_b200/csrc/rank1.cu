@@ -29,7 +29,11 @@ constexpr int NTH = kRank1Threads;
 constexpr int NWARP = NTH / 32;
 
 __host__ __device__ inline int up4(int v) { return (v + 3) & ~3; }
-__host__ __device__ inline int ldp(int v) { return up4(v) + 2; }  // leading dimension of a padded matrix of order v
+__host__ __device__ inline int up8(int v) { return (v + 7) & ~7; }
+// Leading dimension of a padded matrix of order v.  Orders are padded to a multiple of 8 (the fp64 MMA tile) and
+// the rows by 4 more doubles: ld = 4 or 12 (mod 16), so the four k-rows x four columns a half-warp touches in one
+// fragment load (address = k * ld + column) fall on 16 different bank pairs.
+__host__ __device__ inline int ldp(int v) { return up8(v) + 4; }
 
 // Workspace of the HOSVD start of one mode of a >= 3-way Z (doubles): the unfolding copy, the Gram matrix and
 // the two squaring buffers, two vectors.  Every mode has its own area because the modes are worked on
@@ -47,7 +51,7 @@ __host__ __device__ inline ModeWs mode_ws(int dk, int mk) {
     w.n = dk <= mk ? dk : mk;
     w.ld = ldp(w.n);
     w.mt = up4((dk <= mk ? mk : dk) * w.ld);
-    w.gram = up4(w.n) * w.ld;
+    w.gram = up8(w.n) * w.ld;
     w.vec = up4(dk);
     w.total = w.mt + 3 * w.gram + 2 * w.vec;
     return w;
@@ -140,84 +144,58 @@ __device__ __forceinline__ int argmax_abs(const double* a, int n, Grp& g) {
     return bi;
 }
 
-// C = scale * Mt^T Mt on the leading n4 x n4 block (n4 % 4 == 0; Mt is krows x n4 with leading dimension
-// ldm, C has leading dimension ldc, pads of Mt are zero).  C is symmetric: only the 4x4 tiles on or above
-// the diagonal are computed, then mirrored.  The active tiles are packed into consecutive threads (an fp64
-// instruction costs the same pipe time for a warp with one active lane) and the contraction index is split
-// over S lanes of a warp that meet in a shuffle tree, so that small matrices with a long contraction (the
-// Gram matrix of a wide unfolding) and the squarings of small matrices still use the whole group.  Fixed
-// association order => bit-reproducible.
-// TRACE: returns trace(C) through one group reduction whose barrier also publishes C.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// C = scale * Mt^T Mt on the leading n8 x n8 block (n8 % 8 == 0; Mt is krows x n8 with leading dimension ldm, C has
+// leading dimension ldc).  C is symmetric: only the 8x8 tiles on or above the diagonal are computed, then mirrored.
+// TRACE: returns trace(C) through one group reduction whose barrier also publishes C.  On the fp64 tensor-core path
+// (mma.sync.m8n8k4.f64, SASS DMMA): one 8x8 tile on or above the diagonal per warp and round, the contraction in
+// steps of 8 rows of Mt on two accumulator pairs.  A 4x4 register tile of DFMAs needs an LDS.128 per 4 FMAs and is
+// bound by shared-memory issue (tools/micro/fp64_lat.cu); a DMMA does 256 FMAs for two conflict-free LDS.64, so a
+// 64 x 64 squaring drops from ~7.7 k cycles to the ~2.5 k of the fp64 pipe itself.  Rows of Mt past krows are
+// treated as zero; pad columns of Mt must BE zero.  Fixed association order => bit-reproducible.
 template <bool TRACE>
-__device__ __forceinline__ double syrk_tri(double* __restrict__ C, int ldc, const double* __restrict__ Mt, int ldm, int krows,
-                                           int n4, double scale, Grp& g) {
-    const int nt = n4 >> 2;
+__device__ __forceinline__ double syrk_dmma(double* __restrict__ C, int ldc, const double* __restrict__ Mt, int ldm, int krows,
+                                            int n8, double scale, Grp& g) {
+    const int nt = n8 >> 3;
     const int ntri = (nt * (nt + 1)) >> 1;
-    int S = 1;
-    while (S < 32 && ntri * (S * 2) <= g.nth && S * 2 <= krows) S <<= 1;
-    const int ks = g.tid & (S - 1);
-    const int slot = g.tid / S;
-    const int per_round = g.nth / S;
+    const int warp = g.tid >> 5, lane = g.tid & 31, nw = g.nth >> 5;
+    const int gq = lane >> 2, t4 = lane & 3;
     double tr = 0.0;
-    for (int base = 0; base < ntri; base += per_round) {  // warp-uniform trip count: the shuffles below stay converged
-        const int t = base + slot;
-        const bool active = t < ntri;
-        int ti = 0, tj = 0;
-        if (active) {
-            int rem = t, len = nt;
-            while (rem >= len) {
-                rem -= len;
-                --len;
-                ++ti;
-            }
-            tj = ti + rem;
+    for (int t = warp; t < ntri; t += nw) {  // warp-uniform: the MMAs stay converged
+        int ti = 0, rem = t, len = nt;
+        while (rem >= len) {
+            rem -= len;
+            --len;
+            ++ti;
         }
-        double acc[4][4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[q][r] = 0.0;
-        if (active) {
-            const double* pa = Mt + 4 * ti;
-            const double* pb = Mt + 4 * tj;
-#pragma unroll 2
-            for (int k = ks; k < krows; k += S) {
-                const double2 a01 = *reinterpret_cast<const double2*>(pa + (size_t)k * ldm);
-                const double2 a23 = *reinterpret_cast<const double2*>(pa + (size_t)k * ldm + 2);
-                const double2 b01 = *reinterpret_cast<const double2*>(pb + (size_t)k * ldm);
-                const double2 b23 = *reinterpret_cast<const double2*>(pb + (size_t)k * ldm + 2);
-                const double ai[4] = {a01.x, a01.y, a23.x, a23.y};
-                const double bj[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) acc[q][r] = fma(ai[q], bj[r], acc[q][r]);
-            }
+        const int tj = ti + rem;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        const double* pa = Mt + 8 * ti + gq;   // A[i][k] = Mt[k][8 ti + i]
+        const double* pb = Mt + 8 * tj + gq;   // B[k][j] = Mt[k][8 tj + j]
+        for (int k = 0; k < krows; k += 8) {
+            const int ka = k + t4, kb = k + 4 + t4;
+            const double a0 = ka < krows ? pa[(size_t)ka * ldm] : 0.0;
+            const double b0 = ka < krows ? pb[(size_t)ka * ldm] : 0.0;
+            const double a1 = kb < krows ? pa[(size_t)kb * ldm] : 0.0;
+            const double b1 = kb < krows ? pb[(size_t)kb * ldm] : 0.0;
+            dmma884(c0, c1, a0, b0);
+            dmma884(d0, d1, a1, b1);
         }
-        __syncwarp();
-        for (int m = S >> 1; m >= 1; m >>= 1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) acc[q][r] += shfl_xor_d(acc[q][r], m);
-        }
-        if (active && ks == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                double* row = C + (size_t)(4 * ti + q) * ldc + 4 * tj;
-                *reinterpret_cast<double2*>(row) = make_double2(acc[q][0] * scale, acc[q][1] * scale);
-                *reinterpret_cast<double2*>(row + 2) = make_double2(acc[q][2] * scale, acc[q][3] * scale);
-            }
-            if (ti != tj) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    double* row = C + (size_t)(4 * tj + r) * ldc + 4 * ti;
-                    *reinterpret_cast<double2*>(row) = make_double2(acc[0][r] * scale, acc[1][r] * scale);
-                    *reinterpret_cast<double2*>(row + 2) = make_double2(acc[2][r] * scale, acc[3][r] * scale);
-                }
-            } else if (TRACE) {
-                tr += ((acc[0][0] + acc[1][1]) + (acc[2][2] + acc[3][3])) * scale;
-            }
+        c0 = (c0 + d0) * scale;
+        c1 = (c1 + d1) * scale;
+        // this lane holds C[8 ti + gq][8 tj + 2 t4 + {0, 1}]
+        *reinterpret_cast<double2*>(C + (size_t)(8 * ti + gq) * ldc + 8 * tj + 2 * t4) = make_double2(c0, c1);
+        if (ti != tj) {
+            C[(size_t)(8 * tj + 2 * t4) * ldc + 8 * ti + gq] = c0;
+            C[(size_t)(8 * tj + 2 * t4 + 1) * ldc + 8 * ti + gq] = c1;
+        } else if (TRACE) {
+            if (gq == 2 * t4) tr += c0;
+            if (gq == 2 * t4 + 1) tr += c1;
         }
     }
     if (TRACE) return bsum(tr, g);
@@ -257,12 +235,12 @@ __device__ __forceinline__ double normalize_into(double* dst, const double* src,
     return nv;
 }
 
-// Leading eigenpair of the symmetric PSD matrix G (order n, stored up4(n) x up4(n) with zero pads, leading
+// Leading eigenpair of the symmetric PSD matrix G (order n, stored up8(n) x up8(n) with zero pads, leading
 // dimension ld).  A, B: work buffers of the same shape.  v (n) receives the unit eigenvector; returns the
 // eigenvalue when asked for it.
 __device__ __forceinline__ double lead_eig(const double* G, double* A, double* B, double* v, double* tmp, int n, int ld, Grp& g,
                                            int polish, bool want_lambda) {
-    const int n4 = up4(n);
+    const int n8 = up8(n);
     double s = 0.0;
     for (int i = g.tid; i < n; i += g.nth) s += G[(size_t)i * ld + i];
     const double tr = bsum(s, g);
@@ -278,7 +256,7 @@ __device__ __forceinline__ double lead_eig(const double* G, double* A, double* B
     const long long c0 = g.dbg != nullptr ? clock64() : 0;
     for (int it = 0; it < 64; ++it) {
         // dst = (src / tr(src))^2; tau = its trace = sum of squared normalised eigenvalues, -> 1 at rank one
-        const double tau = syrk_tri<true>(dst, ld, src, ld, n4, n4, scale, g);
+        const double tau = syrk_dmma<true>(dst, ld, src, ld, n8, n8, scale, g);
         if (g.dbg != nullptr && g.tid == 0) g.dbg[12] += 1;
         src = dst;
         double* sw = dst;
@@ -361,26 +339,26 @@ __device__ __forceinline__ double hosvd_mode(const double* zs, const Geo& geo, d
     double* B = A + m.gram;
     double* tmp = B + m.gram;
     double* tmp2 = tmp + m.vec;
-    const int n4 = up4(m.n), ld = m.ld;
+    const int n8 = up8(m.n), ld = m.ld;
     double sigma = 0.0;
     if (geo.dk <= geo.mk) {
         // Mt[j][a] = Zk(a, j): rows are the columns of the unfolding
-        for (int i = g.tid; i < geo.mk * n4; i += g.nth) {
-            const int j = i / n4, a = i - j * n4;
+        for (int i = g.tid; i < geo.mk * n8; i += g.nth) {
+            const int j = i / n8, a = i - j * n8;
             mt[(size_t)j * ld + a] = a < geo.dk ? zs[unf_index(geo, a, j)] : 0.0;
         }
         g.sync();
-        syrk_tri<false>(G, ld, mt, ld, geo.mk, n4, 1.0, g);
+        syrk_dmma<false>(G, ld, mt, ld, geo.mk, n8, 1.0, g);
         const double lam = lead_eig(G, A, B, fk, tmp, geo.dk, ld, g, 2, want_sigma);
         sigma = sqrt(lam);
     } else {
         // tall unfolding: eigenvector of the small side, then one multiplication by the unfolding
-        for (int i = g.tid; i < geo.dk * n4; i += g.nth) {
-            const int a = i / n4, j = i - a * n4;
+        for (int i = g.tid; i < geo.dk * n8; i += g.nth) {
+            const int a = i / n8, j = i - a * n8;
             mt[(size_t)a * ld + j] = j < geo.mk ? zs[unf_index(geo, a, j)] : 0.0;
         }
         g.sync();
-        syrk_tri<false>(G, ld, mt, ld, geo.dk, n4, 1.0, g);
+        syrk_dmma<false>(G, ld, mt, ld, geo.dk, n8, 1.0, g);
         lead_eig(G, A, B, tmp2, tmp, geo.mk, ld, g, 2, false);
         unf_matvec(tmp, zs, geo, tmp2, g);
         sigma = normalize_into(fk, tmp, geo.dk, g);
@@ -587,12 +565,12 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
     double* mt2 = rest;  // nm == 2: padded Z^T
     double s = 0.0;
     if (nm == 2) {
-        // padded row-major Z in zs and padded Z^T in mt2 (the pads up to a multiple of four are read as zeros)
-        if (up4(d1) != d1)
+        // padded row-major Z in zs and padded Z^T in mt2 (the pads up to a multiple of eight are read as zeros)
+        if (up8(d1) != d1)
             for (int i = threadIdx.x; i < d0 * ld1; i += NTH) zs[i] = 0.0;
-        if (up4(d0) != d0)
+        if (up8(d0) != d0)
             for (int i = threadIdx.x; i < d1 * ld0; i += NTH) mt2[i] = 0.0;
-        if (up4(d1) != d1 || up4(d0) != d0) __syncthreads();
+        if (up8(d1) != d1 || up8(d0) != d0) __syncthreads();
     }
     for (int i = threadIdx.x; i < p; i += NTH) {
         double z = T.z[i];  // plain load: the covariance loop rewrites Z between calls
@@ -624,14 +602,14 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         const int ks = d0 <= d1 ? 0 : 1;
         const int n = T.dims[ks], no = T.dims[1 - ks];
         const int ldg = ldp(n);
-        const size_t n2 = (size_t)up4(n) * ldg;
+        const size_t n2 = (size_t)up8(n) * ldg;
         double* G = mt2 + T.mt_len;
         double* A = G + n2;
         double* B = A + n2;
         double* tmp = B + n2;
         // rows of Mt are the columns of the mode-ks unfolding: Z^T for ks == 0, Z for ks == 1
         const double* Mt = ks == 0 ? mt2 : zs;
-        syrk_tri<false>(G, ldg, Mt, ks == 0 ? ld0 : ld1, no, up4(n), 1.0, cta);
+        syrk_dmma<false>(G, ldg, Mt, ks == 0 ? ld0 : ld1, no, up8(n), 1.0, cta);
         double* const f0 = fac;        // the two factor vectors, back to back
         double* const f1 = fac + d0;
         lead_eig(G, A, B, ks == 0 ? f0 : f1, tmp, n, ldg, cta, /*polish=*/1, /*want_lambda=*/false);
@@ -878,7 +856,7 @@ size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* 
         nmax = std::min(dims[0], dims[1]);
         zs_len = ((long long)dims[0] * ldp(dims[1]) + 3) & ~3ll;
         mt_len = ((long long)dims[1] * ldp(dims[0]) + 3) & ~3ll;
-        rest = mt_len + 3ll * up4((int)nmax) * ldp((int)nmax) + up4(maxd);
+        rest = mt_len + 3ll * up8((int)nmax) * ldp((int)nmax) + up4(maxd);
     } else if (nmodes >= 3) {
         // [Z | factors | per-mode HOSVD areas, reused afterwards for the index table and the unfolding copies]
         long long areas = 0;

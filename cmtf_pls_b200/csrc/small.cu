@@ -201,27 +201,47 @@ __global__ void solve_coef_kernel(const double* dots, double* gram, double* coef
         gram[b * R + a] = dots[b];
         gram[a * R + b] = dots[b];
     }
-    // Cholesky of the leading k x k block (k <= 64), solve gram * x = rhs
+    // Normal equations of the leading k x k block (k <= 64) on UNIT-NORM score columns: with D = diag(||t_b||),
+    // (D^-1 G D^-1) (D x) = D^-1 rhs.  The scaling keeps the Cholesky factor well conditioned when a score column
+    // is merely tiny (components past the rank of the data: ||t|| ~ 1e-15 ||t_0||, where the plain Gram matrix
+    // loses its pivot and everything downstream turns NaN).  A column that is zero, or dependent on the earlier
+    // ones to rounding, gets coefficient 0 -- the reference's lstsq (rcond = machine precision, tpls.py:110-112)
+    // drops such directions too.
     double Lm[64 * 64];
-    double y[64], x[64];
+    double y[64], x[64], dinv[64];
+    bool drop[64];
+    for (int i = 0; i < k; ++i) {
+        const double g = gram[i * R + i];
+        drop[i] = !(g > 0.0);
+        dinv[i] = drop[i] ? 0.0 : 1.0 / sqrt(g);
+    }
     for (int i = 0; i < k; ++i) {
         for (int j = 0; j <= i; ++j) {
-            double s = gram[i * R + j];
+            double s = (drop[i] || drop[j]) ? (i == j ? 1.0 : 0.0) : gram[i * R + j] * dinv[i] * dinv[j];
             for (int q = 0; q < j; ++q) s -= Lm[i * 64 + q] * Lm[j * 64 + q];
-            Lm[i * 64 + j] = (i == j) ? sqrt(s) : s / Lm[j * 64 + j];
+            if (i == j) {
+                if (!(s > 1e-14)) {  // no independent part left in column i
+                    drop[i] = true;
+                    for (int q = 0; q < i; ++q) Lm[i * 64 + q] = 0.0;
+                    s = 1.0;
+                }
+                Lm[i * 64 + i] = sqrt(s);
+            } else {
+                Lm[i * 64 + j] = s / Lm[j * 64 + j];
+            }
         }
     }
     for (int i = 0; i < k; ++i) {
-        double s = dots[k + i];
+        double s = drop[i] ? 0.0 : dots[k + i] * dinv[i];
         for (int q = 0; q < i; ++q) s -= Lm[i * 64 + q] * y[q];
         y[i] = s / Lm[i * 64 + i];
     }
     for (int i = k - 1; i >= 0; --i) {
         double s = y[i];
         for (int q = i + 1; q < k; ++q) s -= Lm[q * 64 + i] * x[q];
-        x[i] = s / Lm[i * 64 + i];
+        x[i] = drop[i] ? 0.0 : s / Lm[i * 64 + i];
     }
-    for (int b = 0; b < k; ++b) coef[b * R + a] = x[b];
+    for (int b = 0; b < k; ++b) coef[b * R + a] = x[b] * dinv[b];
     if (trips_out != nullptr && ctrl != nullptr) trips_out[a] = ctrl->trips_taken;
     if (conv_out != nullptr && ctrl != nullptr) conv_out[a] = ctrl->done_trip >= 0 ? 1 : 0;
 }

@@ -103,8 +103,9 @@ def sharded_golden_check(cases, device, process_group=None, rank=0, world=1, gat
         lo, hi = row_block(n, rank, world)
         import contextlib
         import io
+        kw = {"max_iter": 4} if "maxiter" in case else {}     # that case was minted with max_iter=4 (oracle/make_golden.py)
         with contextlib.redirect_stdout(io.StringIO()):       # the "missing values" notice of the reference
-            est.fit(shard_rows(list(g["Xs"]), rank, world), shard_rows(g["Y"], rank, world))
+            est.fit(shard_rows(list(g["Xs"]), rank, world), shard_rows(g["Y"], rank, world), **kw)
         T, U = est.factor_T, est.Y_factors[0]
         if world > 1:
             T, U = gather(T, n, lo, hi), gather(U, n, lo, hi)

@@ -56,6 +56,7 @@ def main():
         torch.cuda.empty_cache()
     torch.manual_seed(0)
     for dims, kind in [((64, 64), "easy"), ((32, 16, 8), "easy"), ((64, 32), "easy"), ((24,), "easy"), ((38, 65), "easy"),
+                       ((8, 6), "easy"), ((32, 16), "easy"), ((32, 16), "hard"),
                        ((64, 64), "hard"), ((32, 16, 8), "hard"), ((64, 32), "hard"), ((16, 8, 6, 4), "hard")]:
         Z = torch.randn(*dims, dtype=torch.float64, device="cuda")
         if kind == "easy":      # one dominant rank-1 term: large spectral gap, few squarings
