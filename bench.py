@@ -342,6 +342,8 @@ def run_ours(args):
     #      bytes it ACTUALLY streamed ----
     cov = None
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         est_c = ctPLS(R, device=local, process_group=group, algorithm="covariance")
         for _ in range(2):     # two warm-ups: the second fit of an estimator still pins fresh result buffers
             est_c.fit(Xs, Y)
@@ -372,6 +374,8 @@ def run_ours(args):
     #      the first rows, and the device reconstruction X_hat = T W + mean of a block of rows ----
     xform = None
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         from cmtf_pls_b200 import _core as _c
         est.transform(Xs)
         barrier()
@@ -419,8 +423,8 @@ def run_ours(args):
     e2e = None
     n_iter_resident = est.n_iter_.tolist()
     try:
-        if args.e2e_steps <= 0:
-            raise RuntimeError("skipped (--e2e-steps 0)")
+        if args.e2e_steps <= 0 or args.quick:
+            raise RuntimeError("skipped (--e2e-steps 0 / --quick)")
         Xh = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in Xs]
         for h, d in zip(Xh, Xs):
             h.copy_(d)
@@ -533,6 +537,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity gate (debugging)")
+    ap.add_argument("--quick", action="store_true", help="headline fit only: no covariance / transform / e2e legs (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
