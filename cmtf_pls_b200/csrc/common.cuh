@@ -33,15 +33,15 @@ __device__ __forceinline__ bool trip_is_dead(const Ctrl* c, int /*trip*/) {
 // Programmatic dependent launch (PDL).  Every kernel of the library starts with pdl_prologue(): it lets the
 // NEXT kernel in the stream be scheduled early (its CTAs then sit at their own griddepcontrol.wait instead of
 // paying the launch latency after this grid has drained) and waits until the PREVIOUS grid has completed and
-// flushed its writes.  Both instructions do nothing for a kernel launched without the PDL attribute, which is
-// the default: TPLS_PDL=1 makes launch_k() set it.  Nothing before the prologue may read or write global memory.
+// flushed its writes.  Both instructions do nothing for a kernel launched without the PDL attribute; launch_k()
+// sets it unless TPLS_PDL=0.  Nothing before the prologue may read or write global memory.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
-bool pdl_enabled();  // small.cu: TPLS_PDL=1 in the environment (read once)
+bool pdl_enabled();  // small.cu: on unless TPLS_PDL=0 in the environment (read once)
 // The next launch of this thread is a plain one even with PDL on (the first kernel after a graph WHILE node: a
 // conditional node cannot be the source of a programmatic edge).
 void pdl_hold_next();

@@ -373,6 +373,10 @@ int tpls_destroy(tpls_handle h) {
     }
     if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->h_done) cudaFreeHost(h->h_done);
+    for (int q = 0; q < 2; ++q) {
+        if (h->bounce[q]) cudaFreeHost(h->bounce[q]);
+        if (h->bounce_ev[q]) cudaEventDestroy(h->bounce_ev[q]);
+    }
     cudaEventDestroy(h->ev_start);
     cudaEventDestroy(h->ev_stop);
     for (auto& e : h->ev_trip) cudaEventDestroy(e);

@@ -116,6 +116,8 @@ struct tpls_ctx {
     bool slab_dry = false;
     void* tmp_buf = nullptr;
     size_t tmp_cap = 0;
+    void* bounce[2] = {nullptr, nullptr};          // pinned host buffers for block-wise results (tpls_reconstruct)
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
     size_t arena_doubles = 0, off_ysum = 0, off_ycnt = 0, off_n = 0, off_stats_end = 0, off_zcat = 0, zcat_len = 0,
            off_q = 0, off_d2 = 0, off_dots = 0, off_ss = 0, ss_len = 0;
     std::vector<double> r2x[TPLS_MAX_TENSORS];

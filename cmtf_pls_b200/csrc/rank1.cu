@@ -19,6 +19,8 @@
 // between them read conflict-free.
 #include "rank1.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 namespace tpls {
@@ -174,20 +176,24 @@ __device__ __forceinline__ double syrk_dmma(double* __restrict__ C, int ldc, con
             ++ti;
         }
         const int tj = ti + rem;
-        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        // four independent accumulator pairs: with four warps per sub-partition that keeps 16 MMAs in flight
+        double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
         const double* pa = Mt + 8 * ti + gq;   // A[i][k] = Mt[k][8 ti + i]
         const double* pb = Mt + 8 * tj + gq;   // B[k][j] = Mt[k][8 tj + j]
-        for (int k = 0; k < krows; k += 8) {
-            const int ka = k + t4, kb = k + 4 + t4;
-            const double a0 = ka < krows ? pa[(size_t)ka * ldm] : 0.0;
-            const double b0 = ka < krows ? pb[(size_t)ka * ldm] : 0.0;
-            const double a1 = kb < krows ? pa[(size_t)kb * ldm] : 0.0;
-            const double b1 = kb < krows ? pb[(size_t)kb * ldm] : 0.0;
-            dmma884(c0, c1, a0, b0);
-            dmma884(d0, d1, a1, b1);
+        for (int k = 0; k < krows; k += 16) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int kk = k + 4 * c + t4;
+                const bool in = kk < krows;
+                av[c] = in ? pa[kk * ldm] : 0.0;
+                bv[c] = in ? pb[kk * ldm] : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dmma884(acc[c][0], acc[c][1], av[c], bv[c]);
         }
-        c0 = (c0 + d0) * scale;
-        c1 = (c1 + d1) * scale;
+        const double c0 = ((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0])) * scale;
+        const double c1 = ((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1])) * scale;
         // this lane holds C[8 ti + gq][8 tj + 2 t4 + {0, 1}]
         *reinterpret_cast<double2*>(C + (size_t)(8 * ti + gq) * ldc + 8 * tj + 2 * t4) = make_double2(c0, c1);
         if (ti != tj) {
@@ -572,19 +578,29 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
             for (int i = threadIdx.x; i < d1 * ld0; i += NTH) mt2[i] = 0.0;
         if (up8(d1) != d1 || up8(d0) != d0) __syncthreads();
     }
-    for (int i = threadIdx.x; i < p; i += NTH) {
-        double z = T.z[i];  // plain load: the covariance loop rewrites Z between calls
-        if (T.colcnt != nullptr) {
-            const double c = __ldg(T.colcnt + i);
-            z = c > 0.0 ? z / c * T.n_total : 0.0;
+    // eight loads per thread in flight (a plain loop issued them one L2 round trip after the other)
+    for (int base = 0; base < p; base += NTH * 8) {
+        double zv[8], cv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = base + q * NTH + (int)threadIdx.x;
+            zv[q] = i < p ? T.z[i] : 0.0;  // plain load: the covariance loop rewrites Z between calls
+            cv[q] = (T.colcnt != nullptr && i < p) ? __ldg(T.colcnt + i) : 1.0;
         }
-        s = fma(z, z, s);
-        if (nm == 2) {
-            const int a = i / d1, j = i - a * d1;
-            zs[(size_t)a * ld1 + j] = z;
-            mt2[(size_t)j * ld0 + a] = z;
-        } else {
-            zs[i] = z;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = base + q * NTH + (int)threadIdx.x;
+            if (i >= p) continue;
+            double z = zv[q];
+            if (T.colcnt != nullptr) z = cv[q] > 0.0 ? z / cv[q] * T.n_total : 0.0;
+            s = fma(z, z, s);
+            if (nm == 2) {
+                const int a = i / d1, j = i - a * d1;
+                zs[(size_t)a * ld1 + j] = z;
+                mt2[(size_t)j * ld0 + a] = z;
+            } else {
+                zs[i] = z;
+            }
         }
     }
     const double normz2 = bsum(s, cta);
@@ -747,52 +763,62 @@ __global__ void __launch_bounds__(kRank1Threads, 1) rank1_kernel(const __grid_co
         rank1_task(T, a.tol, a.normalize_on_break, T.scratch);
 }
 
+// One CTA per coupled tensor, the CTAs of a fit forming ONE thread-block cluster: every CTA runs the rank-1 step of
+// its own tensor, the per-tensor contributions to q = Y't (m doubles) are stored into every CTA's shared memory
+// through distributed shared memory, one cluster barrier per trip, and every CTA then forms the same q (fixed
+// summation order) and takes the same stop decision.  Round 1 ran the tensors one after the other on a single CTA.
 template <bool SMEM>
 __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid_constant__ CovLoopArgs a) {
     pdl_prologue();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double dyn[];
-    __shared__ double q_last[8], q_new[8], r_acc[8], lred[4 * NWARP];
+    __shared__ double q_last[8], q_new[8], lred[4 * NWARP];
+    __shared__ double rbuf[2][kMaxTensors][8];   // [trip parity][tensor][response]: filled by the tensors' CTAs
     __shared__ int lired[2 * NWARP];
     Grp blk{(int)threadIdx.x, NTH, 0, lred, lired, 0, nullptr};
     const int M = a.m, L = a.n_tasks;
+    const int l = (int)cluster.block_rank();      // this CTA's tensor
+    const Rank1Task& T = a.t[l];
+    const double* Cl = a.C[l];
     if (threadIdx.x < 8) q_last[threadIdx.x] = threadIdx.x == 0 ? 1.0 : 0.0;  // u_0 = Y[:, 0] = Y e_0 (tpls.py:78)
     __syncthreads();
     int trips = 0;
     bool converged = false;
     for (int trip = 0; trip < a.max_iter; ++trip) {
         trips = trip + 1;
-        if (threadIdx.x < 8) r_acc[threadIdx.x] = 0.0;
-        for (int l = 0; l < L; ++l) {
-            const Rank1Task& T = a.t[l];
-            const double* Cl = a.C[l];
-            // Z = X x_1 u with u = Y q_last  ==  sum_m q_last[m] * C[m][:]
-            double* z = const_cast<double*>(T.z);
-            for (int i = threadIdx.x; i < T.p; i += NTH) {
-                double v = 0.0;
-                for (int m = 0; m < M; ++m) v = fma(q_last[m], Cl[(size_t)m * T.pitch + i], v);
-                z[i] = v;
-            }
-            __syncthreads();
-            if (SMEM)
-                rank1_task(T, a.tol, a.normalize_on_break, dyn);
-            else
-                rank1_task(T, a.tol, a.normalize_on_break, T.scratch);
-            __syncthreads();
-            // Y't for this tensor = C'^T kron(w): the row-rescaled block when masked (missingvals.py:23-38)
-            const double* Cq = Cl + (size_t)a.masked[l] * T.pitch;
-            for (int m = 0; m < M; ++m) {
-                double s = 0.0;
-                for (int i = threadIdx.x; i < T.p; i += NTH) s = fma(Cq[(size_t)m * T.pitch + i], T.wkron[i], s);
-                s = bsum(s, blk);
-                if (threadIdx.x == 0) r_acc[m] += s;
-            }
-            __syncthreads();
+        // Z = X x_1 u with u = Y q_last  ==  sum_m q_last[m] * C[m][:]
+        double* z = const_cast<double*>(T.z);
+        for (int i = threadIdx.x; i < T.p; i += NTH) {
+            double v = 0.0;
+            for (int m = 0; m < M; ++m) v = fma(q_last[m], Cl[(size_t)m * T.pitch + i], v);
+            z[i] = v;
         }
+        __syncthreads();
+        if (SMEM)
+            rank1_task(T, a.tol, a.normalize_on_break, dyn);
+        else
+            rank1_task(T, a.tol, a.normalize_on_break, T.scratch);
+        __syncthreads();
+        // Y't of this tensor = C'^T kron(w): the row-rescaled block when masked (missingvals.py:23-38);
+        // thread 0 publishes the m values in every CTA of the cluster
+        const double* Cq = Cl + (size_t)a.masked[l] * T.pitch;
+        for (int m = 0; m < M; ++m) {
+            double s = 0.0;
+            for (int i = threadIdx.x; i < T.p; i += NTH) s = fma(Cq[(size_t)m * T.pitch + i], T.wkron[i], s);
+            s = bsum(s, blk);
+            if (threadIdx.x == 0)
+                for (int r = 0; r < L; ++r) cluster.map_shared_rank(&rbuf[trip & 1][l][m], r)[0] = s;
+        }
+        cluster.sync();
         // q = Y't / ||Y't||, t = average of the tensors' projections (cmtf.py:120-122)
         if (threadIdx.x == 0) {
+            double r_acc[8];
             double nrm = 0.0;
             for (int m = 0; m < M; ++m) {
-                r_acc[m] /= (double)L;
+                double t = 0.0;
+                for (int r = 0; r < L; ++r) t += rbuf[trip & 1][r][m];
+                r_acc[m] = t / (double)L;
                 nrm = fma(r_acc[m], r_acc[m], nrm);
             }
             nrm = sqrt(nrm);
@@ -816,29 +842,45 @@ __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid
             break;
         }
     }
-    for (int i = threadIdx.x; i < a.pitch_y; i += NTH) {
-        const double v = i < M ? q_last[i] : 0.0;
-        a.qvec[i] = v;
-        if (i < M) a.q_out[i] = v;
+    if (l == 0) {
+        for (int i = threadIdx.x; i < a.pitch_y; i += NTH) {
+            const double v = i < M ? q_last[i] : 0.0;
+            a.qvec[i] = v;
+            if (i < M) a.q_out[i] = v;
+        }
+        if (threadIdx.x == 0) {
+            *a.trips_out = trips;
+            if (a.conv_out != nullptr) *a.conv_out = converged ? 1 : 0;
+        }
     }
-    if (threadIdx.x == 0) {
-        *a.trips_out = trips;
-        if (a.conv_out != nullptr) *a.conv_out = converged ? 1 : 0;
-    }
+    cluster.sync();  // no CTA may exit while a peer can still store into its shared memory
 }
 
 }  // namespace
 
 cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_smem, cudaStream_t s) {
-    if (use_smem && smem_bytes > 0) {
-        cudaError_t e =
-            cudaFuncSetAttribute(cov_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (a.n_tasks < 1 || a.n_tasks > 8 || a.m > 8) return cudaErrorInvalidValue;
+    auto kern = (use_smem && smem_bytes > 0) ? cov_loop_kernel<true> : cov_loop_kernel<false>;
+    const size_t smem = (use_smem && smem_bytes > 0) ? smem_bytes : 0;
+    if (smem > 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        launch_k(cov_loop_kernel<true>, dim3(1), dim3(kRank1Threads), smem_bytes, s, a);
-    } else {
-        launch_k(cov_loop_kernel<false>, dim3(1), dim3(kRank1Threads), 0, s, a);
     }
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.n_tasks);
+    cfg.blockDim = dim3(kRank1Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = a.n_tasks;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl_enabled() && !pdl_take_hold()) ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out,

@@ -8,9 +8,10 @@
 namespace tpls {
 
 bool pdl_enabled() {
+    // on by default since round 2 (all GPU tests and the 1/2/8-GPU benchmark run with it); TPLS_PDL=0 turns it off
     static const bool on = [] {
         const char* v = getenv("TPLS_PDL");
-        return v != nullptr && *v != '\0' && *v != '0';
+        return v == nullptr || *v == '\0' || *v != '0';
     }();
     return on;
 }

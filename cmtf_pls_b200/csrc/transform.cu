@@ -224,11 +224,36 @@ int tpls_reconstruct(tpls_handle h, int n_components, const double* scores, int6
             break;
         }
         const bool out_dev = is_device_ptr(out);
-        // a host result is produced block by block through one device buffer of at most 256 MB
-        const long long blk_rows = out_dev ? n : std::max<long long>(32, std::min<long long>(n, (256ll << 20) / (8 * p)));
-        if (!out_dev && (rc = dev_alloc(h, (void**)&blk, sizeof(double) * blk_rows * p, &tmp))) break;
-        for (long long r0 = 0; r0 < n && !rc; r0 += blk_rows) {
+        // A host result is produced block by block: two device blocks and two pinned bounce buffers (kept in the
+        // handle), so that the writer of block k+1, the DMA of block k and the host copy of block k-1 overlap --
+        // a pageable destination would otherwise be fed through the driver's own small staging buffers.
+        const size_t kBounce = 32u << 20;
+        const long long blk_rows = out_dev ? n : std::max<long long>(1, std::min<long long>(n, (long long)(kBounce / (8 * p))));
+        if (!out_dev) {
+            if ((size_t)blk_rows * p * 8 > kBounce) {  // a single row block larger than a bounce buffer (huge p)
+                rc = fail(h, "tpls_reconstruct: p = %lld too large for a host result", (long long)p);
+                break;
+            }
+            if ((rc = dev_alloc(h, (void**)&blk, sizeof(double) * 2 * blk_rows * p, &tmp))) break;
+            for (int q = 0; q < 2 && !rc; ++q) {
+                if (!h->bounce[q] && cudaMallocHost(&h->bounce[q], kBounce) != cudaSuccess) rc = fail(h, "cudaMallocHost failed");
+                if (!h->bounce_ev[q] && cudaEventCreateWithFlags(&h->bounce_ev[q], cudaEventDisableTiming) != cudaSuccess)
+                    rc = fail(h, "cudaEventCreate failed");
+            }
+            if (rc) break;
+        }
+        long long pend_r0[2] = {-1, -1}, pend_rows[2] = {0, 0};
+        auto drain = [&](int q) -> cudaError_t {   // host copy of the block that last used bounce buffer q
+            if (pend_r0[q] < 0) return cudaSuccess;
+            cudaError_t e3 = cudaEventSynchronize(h->bounce_ev[q]);
+            if (e3 == cudaSuccess) memcpy(out + pend_r0[q] * p, h->bounce[q], sizeof(double) * pend_rows[q] * p);
+            pend_r0[q] = -1;
+            return e3;
+        };
+        int q = 0;
+        for (long long r0 = 0; r0 < n && !rc; r0 += blk_rows, q ^= 1) {
             const long long rows = std::min<long long>(blk_rows, n - r0);
+            cudaError_t e2 = out_dev ? cudaSuccess : drain(q);
             ReconstructArgs a{};
             a.T = T + r0 * R;
             a.w = W;
@@ -237,15 +262,19 @@ int tpls_reconstruct(tpls_handle h, int n_components, const double* scores, int6
             a.p = (int)p;
             a.w_pitch = (int)p;
             a.n_comp = R;
-            a.out = out_dev ? out + r0 * p : blk;
-            cudaError_t e2 = launch_reconstruct(a, st);
+            a.out = out_dev ? out + r0 * p : blk + (size_t)q * blk_rows * p;
+            if (e2 == cudaSuccess) e2 = launch_reconstruct(a, st);
             h->stats.kernel_launches++;
             if (e2 == cudaSuccess && !out_dev) {
-                e2 = cudaMemcpyAsync(out + r0 * p, blk, sizeof(double) * rows * p, cudaMemcpyDeviceToHost, st);
-                if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+                e2 = cudaMemcpyAsync(h->bounce[q], a.out, sizeof(double) * rows * p, cudaMemcpyDeviceToHost, st);
+                if (e2 == cudaSuccess) e2 = cudaEventRecord(h->bounce_ev[q], st);
+                pend_r0[q] = r0;
+                pend_rows[q] = rows;
             }
             if (e2 != cudaSuccess) rc = fail(h, "tpls_reconstruct -> %s", cudaGetErrorString(e2));
         }
+        for (int k = 0; k < 2 && !rc && !out_dev; ++k)
+            if (drain(k) != cudaSuccess) rc = fail(h, "tpls_reconstruct: device-to-host copy failed");
     } while (0);
     cudaStreamSynchronize(st);
     for (void* q : tmp) pool_put(h, q);
