@@ -315,6 +315,19 @@ def run_ours(args):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     stats_timed = dict(est.stats_)
+    # how long every rank waited inside the exchange kernels of the last timed fit: the rank that waits least sets the pace
+    xw = torch.tensor([stats_timed.get("xchg_wait_ms", 0.0), stats_timed.get("xchg_ms", 0.0), stats_timed.get("fit_ms", 0.0)],
+                      dtype=torch.float64, device=dev)
+    xw_all = [torch.zeros_like(xw) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(xw_all, xw)
+    else:
+        xw_all = [xw]
+    xchg_diag = {"exchanges_per_fit": int(stats_timed.get("xchg_count", 0)),
+                 "wait_ms_per_rank": [round(float(t[0]), 2) for t in xw_all],
+                 "start_to_synchronised_ms_per_rank": [round(float(t[1]), 2) for t in xw_all],
+                 "fit_ms_per_rank": [round(float(t[2]), 2) for t in xw_all],
+                 "note": "summed over the exchanges of one fit, measured by CTA 0 of each exchange kernel with %globaltimer"}
     # per-kernel-class durations: the SAME fit enqueued kernel by kernel by the host (a graph cannot carry an event
     # pair per launch), CUDA events around every launch on the launching stream, K more steps right after the timed ones
     evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -514,7 +527,7 @@ def run_ours(args):
                    "fraction_of_hbm_peak": value / (world * peak), "fit_ms_device_last": fit_ms_device,
                    "loop": "device-resident (one CUDA graph per fit, a WHILE node per component)" if stats_timed.get("graph_launches") else "host-enqueued trips",
                    "launches_per_trip": stats_timed.get("launches_per_trip"), "exchange": stats_timed.get("exchange"),
-                   "launches_per_fit": stats_timed.get("kernel_launches"),
+                   "launches_per_fit": stats_timed.get("kernel_launches"), "exchange_wait": xchg_diag if world > 1 else None,
                    "host_ms_last_fit": host_ms_last,
                    "covariance_mode": cov, "transform": xform},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

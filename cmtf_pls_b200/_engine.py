@@ -44,6 +44,9 @@ class Stats(C.Structure):
         ("last_transform_path", C.c_int64),
         ("graph_launches", C.c_int64),
         ("launches_per_trip", C.c_int64),
+        ("xchg_count", C.c_int64),
+        ("xchg_ms", C.c_double),
+        ("xchg_wait_ms", C.c_double),
     ]
 
 

@@ -155,6 +155,7 @@ int xchg_launch(tpls_handle h, XchgArgs& a) {
     a.done_ctr = reinterpret_cast<unsigned int*>(mine + 512);
     a.err = reinterpret_cast<int*>(mine + 520);
     a.seq_ctr = reinterpret_cast<unsigned long long*>(mine + 528);
+    a.diag = reinterpret_cast<unsigned long long*>(mine + 536);
     CK(launch_xchg(a, h->stream));
     h->stats.kernel_launches++;
     h->stats.collectives++;
@@ -1360,8 +1361,10 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     h->profile = (flags & TPLS_FIT_PROFILE) != 0;
     h->cov_alloc = (flags & TPLS_FIT_COVARIANCE) != 0 && h->m <= 8;
     TRY(alloc_fit(h, L, R));
-    if (h->xchg_ready)  // a time-out of an earlier fit must not fail this one
+    if (h->xchg_ready) {  // a time-out of an earlier fit must not fail this one; the wait diagnostics start from zero
         CK(cudaMemsetAsync(static_cast<char*>(h->xchg_buf) + 520, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(static_cast<char*>(h->xchg_buf) + 536, 0, 3 * sizeof(unsigned long long), st));
+    }
     CK(cudaEventRecord(h->ev_start, st));
     const long long n = h->n;
     double* A = h->arena;
@@ -1556,8 +1559,13 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     h->stats.fit_ms = ms;
     if (h->xchg_ready) {
         int xerr = 0;
+        unsigned long long diag[3] = {0, 0, 0};
         CK(cudaMemcpy(&xerr, static_cast<char*>(h->xchg_buf) + 520, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(diag, static_cast<char*>(h->xchg_buf) + 536, sizeof diag, cudaMemcpyDeviceToHost));
         if (xerr) return fail(h, "tpls_fit: a peer-memory exchange timed out (a rank died or fell out of step)");
+        h->stats.xchg_wait_ms = 1e-6 * (double)diag[0];
+        h->stats.xchg_ms = 1e-6 * (double)diag[1];
+        h->stats.xchg_count = (int64_t)diag[2];
     }
     for (int l = 0; l < L; ++l) {
         h->r2x[l].assign(R, 0.0);

@@ -16,6 +16,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
     double v;
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -26,6 +32,7 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
 __global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgArgs a) {
     pdl_prologue();
     __shared__ double fold[8][33];
+    const unsigned long long t_start = (blockIdx.x == 0 && threadIdx.x == 0) ? global_ns() : 0ull;
     // the sequence number of THIS exchange: the counter is advanced by the last CTA to finish phase 1, i.e. after
     // every CTA of the launch has read it
     const unsigned long long seq = *reinterpret_cast<const volatile unsigned long long*>(a.seq_ctr) + 1ull;
@@ -70,6 +77,7 @@ __global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgA
             for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, seq);
         }
         // ---- phase 2: wait for every rank's announcement in the LOCAL flag words ----
+        const unsigned long long t_wait = blockIdx.x == 0 ? global_ns() : 0ull;
         const long long t0 = clock64();
         for (int r = 0; r < a.world; ++r) {
             while (ld_acquire_sys(a.flags[a.rank] + r) < seq) {
@@ -78,6 +86,12 @@ __global__ void __launch_bounds__(256) xchg_kernel(const __grid_constant__ XchgA
                     break;
                 }
             }
+        }
+        if (blockIdx.x == 0 && a.diag != nullptr) {  // how long this rank waited for the slowest one
+            const unsigned long long t_sync = global_ns();
+            a.diag[0] += t_sync - t_wait;
+            a.diag[1] += t_sync - t_start;
+            a.diag[2] += 1ull;
         }
     }
     __syncthreads();

@@ -27,7 +27,8 @@ constexpr int kXchgMaxRanks = 16;
 constexpr size_t kXchgHeaderBytes = 1024;
 // header of an exchange buffer: flags[kXchgMaxRanks] (u64) | +512 done counter (u32) | +520 error word (i32) |
 // +528 sequence number of the last exchange this rank completed (u64; kept on the DEVICE so that an exchange can
-// sit in the body of a CUDA-graph loop)
+// sit in the body of a CUDA-graph loop) | +536 diagnostics (u64 x 3, reset by every fit): nanoseconds CTA 0 spent
+// waiting for the peers' announcements, nanoseconds from its start to the end of that wait, exchanges counted
 
 struct XchgArgs {
     // input: either `n_sets` partial blocks (folded into the slot at their `off`), or (n_sets == 0) the ready vector `in`
@@ -43,6 +44,7 @@ struct XchgArgs {
     double* data[kXchgMaxRanks];               // data[r] = rank r's slots
     unsigned int* done_ctr;                    // local: CTAs that finished phase 1
     int* err;                                  // local: set to 1 on a wait timeout
+    unsigned long long* diag;                  // local: {wait ns, start-to-synchronised ns, exchanges}
     // optional stop test on out[0] = ||u_old - u_new||^2 (tpls.py:103), see ctrl_decide
     Ctrl* ctrl;
     LoopEnd loop_end;

@@ -136,6 +136,12 @@ typedef struct tpls_stats {
                                    no part in the inner loops), 0 when the host enqueued the trips */
     int64_t launches_per_trip;  /* kernels in one inner trip of the last streaming fit (3 + 2 * n_tensors when the Y side
                                    is fused into the X passes) */
+    /* peer-memory exchanges of the last fit on THIS rank (0 without them): how many, the time from the start of an
+     * exchange kernel until every rank's contribution had arrived, and the part of it spent waiting for the peers --
+     * the rank that waits least is the slowest one */
+    int64_t xchg_count;
+    double xchg_ms;
+    double xchg_wait_ms;
 } tpls_stats;
 int tpls_get_stats(tpls_handle h, tpls_stats* out);
 
