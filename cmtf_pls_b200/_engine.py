@@ -105,7 +105,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("TPLS_B200_LIB") or LIB_PATH   # TPLS_B200_LIB: another build of the library (A/B runs)
     if not os.path.exists(p):
         raise TplsError(
             f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -178,6 +178,11 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
             const double sw = ((COLSTAT || SUMSQ) && a.row_sw != nullptr) ? __ldg(a.row_sw + grow) : 1.0;
             // the row's sum of squares in two independent chains (one long chain of dependent DFMAs held the
             // read-only residual pass at half the bandwidth), folded into ss once per row
+#ifdef TPLS_SS_ONE_CHAIN
+            constexpr int kSsMask = 0;   // A/B switch for measurements: one chain per row
+#else
+            constexpr int kSsMask = 1;
+#endif
             double rs[2] = {0.0, 0.0};
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
                         cacc[k][j] += ob ? sw : 0.0;
                         nmiss += ob ? 0 : 1;
                     }
-                    if (SUMSQ) rs[j & 1] = fma(xd, xd, rs[j & 1]);
+                    if (SUMSQ) rs[j & kSsMask] = fma(xd, xd, rs[j & kSsMask]);
                 }
                 if (WRITE) {
                     __stcs(reinterpret_cast<typename VecOf<XT>::type*>(xo + grow * g.pitch + c0 + cg * VEC), out.v);

@@ -35,7 +35,7 @@ static size_t row_slot_doubles(const PassGeom& g, bool masked) {
     return g.lpr >= 32 ? (size_t)g.tile_rows * g.lpr * (masked ? 2 : 1) : 0;
 }
 
-PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked) {
+PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked, int aux_doubles) {
     PassGeom g{};
     const int vec = 16 / elem_size;
     g.n_rows = n_rows;
@@ -65,9 +65,13 @@ PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm
     long long tr = std::max<long long>(1, tile_max / row_bytes);
     tr = std::min<long long>(tr, std::max<long long>(1, n_rows));
     tr = std::min<long long>(tr, 4096);
+    if (aux_doubles > 0) {  // staged side inputs: <= 16 KB per stage, an even number of rows (16-byte bulk copies)
+        tr = std::min<long long>(tr, std::max<long long>(2, 16384 / (8 * aux_doubles)));
+        if (tr > 1) tr &= ~1ll;
+    }
     g.tile_rows = (int)tr;
     const size_t slots = kSlots * row_slot_doubles(g, masked) * sizeof(double);
-    const long long stage = (long long)row_stage_bytes(g);
+    const long long stage = (long long)row_stage_bytes(g) + (long long)tr * aux_doubles * 8;
     g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
     const long long n_tiles = (n_rows + tr - 1) / tr;
     const long long want = std::max(1, (sm_count * tune_env("TPLS_CTAS_PER_SM", 2)) / g.n_slabs);
@@ -75,8 +79,9 @@ PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm
     return g;
 }
 
-size_t rowpass_smem(const PassGeom& g, bool masked) {
-    return g.stages * row_stage_bytes(g) + 256 + kSlots * row_slot_doubles(g, masked) * sizeof(double) + 1024;
+size_t rowpass_smem(const PassGeom& g, bool masked, int aux_doubles) {
+    return g.stages * (row_stage_bytes(g) + (size_t)g.tile_rows * aux_doubles * 8) + 256 +
+           kSlots * row_slot_doubles(g, masked) * sizeof(double) + 1024;
 }
 
 // `old` = previous t[row]; only read by the caller when the epilogue needs it (coupled accumulation, ||dt||^2)
@@ -133,7 +138,17 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     const int srow = FULL ? kConsumers * VEC * CPT : ((g.n_slabs == 1) ? g.pitch : g.slab_w);
     const size_t stage_elems = (size_t)g.tile_rows * srow;
     XT* tiles = reinterpret_cast<XT*>(smem);
-    const size_t tile_area = (size_t)g.stages * stage_elems * sizeof(XT);
+    // side inputs of the epilogue staged with the tiles: the rows of Y (q = Y't partials) and the scores so far
+    const bool slabbed = g.n_slabs > 1;
+    const bool stage_aux = a.stage_aux != 0 && !slabbed && g.tile_rows > 1 && (g.tile_rows & 1) == 0;
+    const bool stage_old = stage_aux && epilogue_needs_old(a);
+    const bool stage_cnt = stage_aux && MASKED && !COUNT;
+    const int pitch_ys = stage_aux ? a.pitch_y : 0;
+    const size_t ystage = (size_t)g.tile_rows * pitch_ys;
+    double* ytiles = reinterpret_cast<double*>(smem + (size_t)g.stages * stage_elems * sizeof(XT));
+    double* vtiles = ytiles + (size_t)g.stages * ystage;                 // scores so far
+    double* ctiles = vtiles + (size_t)g.stages * g.tile_rows;            // observed entries per row (masked, known)
+    const size_t tile_area = (size_t)g.stages * (stage_elems * sizeof(XT) + (stage_aux ? (ystage + 2 * g.tile_rows) * sizeof(double) : 0));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + tile_area);
     uint64_t* empty = full + kMaxStages;
     uint64_t* red_full = empty + kMaxStages;
@@ -141,13 +156,13 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     double* slots = reinterpret_cast<double*>(smem + tile_area + 256);
     const bool use_slots = FULL ? true : (g.lpr >= 32);
     const size_t slot_doubles = use_slots ? (size_t)g.tile_rows * lpr * (COUNT ? 2 : 1) : 0;
-    const bool slabbed = g.n_slabs > 1;
     const double p_total = (double)g.p;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumers / 32);
+            // with staged side inputs the reducer warp reads the stage too and releases it last
+            mbar_init(&empty[s], kConsumers / 32 + ((stage_aux && use_slots) ? 1 : 0));
         }
         for (int s = 0; s < kSlots; ++s) {
             mbar_init(&red_full[s], kConsumers / 32);
@@ -164,7 +179,9 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     // ------------------------------------------------------------------ producer
     if (tid >= kConsumers && tid < kConsumers + 32) {
         if (tid == kConsumers)
-            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow);
+            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow,
+                              (stage_aux && a.y != nullptr) ? a.y : nullptr, pitch_ys, ytiles,
+                              stage_old ? a.t_out : nullptr, vtiles, stage_cnt ? a.rowcnt : nullptr, ctiles);
         return;
     }
 
@@ -193,11 +210,18 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
             // its latency (microseconds while the HBM is saturated) overlaps the consumers' work on the tile
             double old_pf = 0.0, cnt_pf = 1.0;
             if (gl == 0 && rg < rows && !slabbed) {
-                if (need_old) old_pf = a.t_out[r0 + rg];
-                if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + rg];
-                if (want_q) load_y_row(a, r0 + rg, y_pf);
+                if (need_old && !stage_old) old_pf = a.t_out[r0 + rg];
+                if (MASKED && !COUNT && !stage_cnt) cnt_pf = a.rowcnt[r0 + rg];
+                if (want_q && !stage_aux) load_y_row(a, r0 + rg, y_pf);
             }
             mbar_wait(&red_full[sl], ph);
+            // staged side inputs of this tile (the consumers waited for the stage; so does this warp, at no cost)
+            const int st_s = (int)(it % g.stages);
+            if (stage_aux) mbar_wait(&full[st_s], (uint32_t)((it / g.stages) & 1));
+            const double* ysm = ytiles + (size_t)st_s * ystage;
+            const double* vsm = vtiles + (size_t)st_s * g.tile_rows;
+            const double* csm = ctiles + (size_t)st_s * g.tile_rows;
+            const int rows_staged = rows & ~1;
             const double* sp = slots + (size_t)sl * slot_doubles;
             const double* cp = sp + (size_t)g.tile_rows * lpr;
             for (int rb = 0; rb < rows; rb += rows_per_round) {
@@ -240,22 +264,44 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                             if (COUNT) {
                                 cnt -= pads;
                                 if (a.rowcnt != nullptr) a.rowcnt[grow] = cnt;
+                            } else if (stage_cnt && r < rows_staged) {
+                                cnt = csm[r];
                             } else {
-                                cnt = rb == 0 ? cnt_pf : a.rowcnt[grow];
+                                cnt = (rb == 0 && !stage_cnt) ? cnt_pf : a.rowcnt[grow];
                             }
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        const double old = !need_old ? 0.0 : (rb == 0 ? old_pf : a.t_out[grow]);
+                        double old = 0.0;
+                        if (need_old) {
+                            if (stage_old && r < rows_staged)
+                                old = vsm[r];
+                            else
+                                old = (rb == 0 && !stage_old) ? old_pf : a.t_out[grow];
+                        }
                         const double nv = row_epilogue(a, grow, v, old, d2);
                         if (want_q) {
-                            if (rb != 0) load_y_row(a, grow, y_pf);
+                            if (stage_aux) {
+                                const double2* yr = reinterpret_cast<const double2*>(ysm + (size_t)r * pitch_ys);
+#pragma unroll
+                                for (int m = 0; m < kMaxFusedResp; m += 2) {
+                                    double2 t = make_double2(0.0, 0.0);
+                                    if (m < pitch_ys) t = yr[m >> 1];
+                                    y_pf[m] = t.x;
+                                    y_pf[m + 1] = t.y;
+                                }
+                            } else if (rb != 0) {
+                                load_y_row(a, grow, y_pf);
+                            }
                             q_accumulate(qacc, y_pf, nv);
                         }
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&red_empty[sl]);
+            if (lane == 0) {
+                mbar_arrive(&red_empty[sl]);
+                if (stage_aux) mbar_arrive(&empty[st_s]);
+            }
         }
         if (a.d2part != nullptr && !slabbed) {
             d2 = warp_sum(d2);
@@ -368,10 +414,24 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                             }
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        const double nv = row_epilogue(a, grow, v, epilogue_needs_old(a) ? a.t_out[grow] : 0.0, d2);
+                        double old = 0.0;
+                        if (epilogue_needs_old(a))
+                            old = (stage_old && r < (rows & ~1)) ? vtiles[(size_t)s * g.tile_rows + r] : a.t_out[grow];
+                        const double nv = row_epilogue(a, grow, v, old, d2);
                         if (want_q) {
                             double yv[kMaxFusedResp];
-                            load_y_row(a, grow, yv);
+                            if (stage_aux) {
+                                const double2* yr = reinterpret_cast<const double2*>(ytiles + (size_t)s * ystage + (size_t)r * pitch_ys);
+#pragma unroll
+                                for (int m = 0; m < kMaxFusedResp; m += 2) {
+                                    double2 t = make_double2(0.0, 0.0);
+                                    if (m < pitch_ys) t = yr[m >> 1];
+                                    yv[m] = t.x;
+                                    yv[m + 1] = t.y;
+                                }
+                            } else {
+                                load_y_row(a, grow, yv);
+                            }
                             q_accumulate(qacc, yv, nv);
                         }
                     }
@@ -420,7 +480,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
 template <typename XT, int CPT, int MODE, bool FULL>
 static cudaError_t run_rowpass_impl(const RowPassArgs& a, cudaStream_t s) {
     auto kern = rowpass_kernel<XT, CPT, MODE, FULL>;
-    const size_t smem = rowpass_smem(a.g, MODE == 2);
+    const size_t smem = rowpass_smem(a.g, MODE == 2, a.stage_aux ? 2 + a.pitch_y : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
