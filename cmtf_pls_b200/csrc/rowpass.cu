@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     // side inputs of the epilogue staged with the tiles: the rows of Y (q = Y't partials) and the scores so far
     const bool slabbed = g.n_slabs > 1;
     const bool stage_aux = a.stage_aux != 0 && !slabbed && g.tile_rows > 1 && (g.tile_rows & 1) == 0;
-    const bool stage_old = stage_aux && epilogue_needs_old(a);
-    const bool stage_cnt = stage_aux && MASKED && !COUNT;
+    // (a bulk copy needs a 16-byte aligned source: column a of the column-major scores is not, for an odd row count)
+    const bool stage_old = stage_aux && epilogue_needs_old(a) && (reinterpret_cast<uintptr_t>(a.t_out) & 15) == 0;
+    const bool stage_cnt = stage_aux && MASKED && !COUNT && (reinterpret_cast<uintptr_t>(a.rowcnt) & 15) == 0;
+    const bool stage_y = stage_aux && a.y != nullptr && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
     const int pitch_ys = stage_aux ? a.pitch_y : 0;
     const size_t ystage = (size_t)g.tile_rows * pitch_ys;
     double* ytiles = reinterpret_cast<double*>(smem + (size_t)g.stages * stage_elems * sizeof(XT));
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(&full[s], 1);
-            // with staged side inputs the reducer warp reads the stage too and releases it last
+            // with staged side inputs the reducer warp reads the stage too (into registers, right after the copy landed)
             mbar_init(&empty[s], kConsumers / 32 + ((stage_aux && use_slots) ? 1 : 0));
         }
         for (int s = 0; s < kSlots; ++s) {
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     if (tid >= kConsumers && tid < kConsumers + 32) {
         if (tid == kConsumers)
             produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow,
-                              (stage_aux && a.y != nullptr) ? a.y : nullptr, pitch_ys, ytiles,
+                              stage_y ? a.y : nullptr, pitch_ys, ytiles,
                               stage_old ? a.t_out : nullptr, vtiles, stage_cnt ? a.rowcnt : nullptr, ctiles);
         return;
     }
@@ -208,20 +210,41 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
             const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
             // what the first round's epilogue reads from global memory is requested BEFORE the wait, so that
             // its latency (microseconds while the HBM is saturated) overlaps the consumers' work on the tile
+            // With staged side inputs the FIRST round's values come out of the stage as soon as the copy has landed
+            // (long before the consumers are done with the tile) and the stage is released at once, so the ring keeps
+            // its depth; later rounds of a many-row tile read global memory like the unstaged path.
             double old_pf = 0.0, cnt_pf = 1.0;
-            if (gl == 0 && rg < rows && !slabbed) {
-                if (need_old && !stage_old) old_pf = a.t_out[r0 + rg];
-                if (MASKED && !COUNT && !stage_cnt) cnt_pf = a.rowcnt[r0 + rg];
-                if (want_q && !stage_aux) load_y_row(a, r0 + rg, y_pf);
+            const int rows_staged = rows & ~1;
+            if (stage_aux) {
+                const int st_s = (int)(it % g.stages);
+                mbar_wait(&full[st_s], (uint32_t)((it / g.stages) & 1));
+                if (gl == 0 && rg < rows) {
+                    const bool in_stage = rg < rows_staged;
+                    if (need_old) old_pf = (stage_old && in_stage) ? vtiles[(size_t)st_s * g.tile_rows + rg] : a.t_out[r0 + rg];
+                    if (MASKED && !COUNT) cnt_pf = (stage_cnt && in_stage) ? ctiles[(size_t)st_s * g.tile_rows + rg] : a.rowcnt[r0 + rg];
+                    if (want_q) {
+                        if (stage_y) {
+                            const double2* yr = reinterpret_cast<const double2*>(ytiles + (size_t)st_s * ystage + (size_t)rg * pitch_ys);
+#pragma unroll
+                            for (int m = 0; m < kMaxFusedResp; m += 2) {
+                                double2 t = make_double2(0.0, 0.0);
+                                if (m < pitch_ys) t = yr[m >> 1];
+                                y_pf[m] = t.x;
+                                y_pf[m + 1] = t.y;
+                            }
+                        } else {
+                            load_y_row(a, r0 + rg, y_pf);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st_s]);
+            } else if (gl == 0 && rg < rows && !slabbed) {
+                if (need_old) old_pf = a.t_out[r0 + rg];
+                if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + rg];
+                if (want_q) load_y_row(a, r0 + rg, y_pf);
             }
             mbar_wait(&red_full[sl], ph);
-            // staged side inputs of this tile (the consumers waited for the stage; so does this warp, at no cost)
-            const int st_s = (int)(it % g.stages);
-            if (stage_aux) mbar_wait(&full[st_s], (uint32_t)((it / g.stages) & 1));
-            const double* ysm = ytiles + (size_t)st_s * ystage;
-            const double* vsm = vtiles + (size_t)st_s * g.tile_rows;
-            const double* csm = ctiles + (size_t)st_s * g.tile_rows;
-            const int rows_staged = rows & ~1;
             const double* sp = slots + (size_t)sl * slot_doubles;
             const double* cp = sp + (size_t)g.tile_rows * lpr;
             for (int rb = 0; rb < rows; rb += rows_per_round) {
@@ -264,44 +287,22 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                             if (COUNT) {
                                 cnt -= pads;
                                 if (a.rowcnt != nullptr) a.rowcnt[grow] = cnt;
-                            } else if (stage_cnt && r < rows_staged) {
-                                cnt = csm[r];
                             } else {
-                                cnt = (rb == 0 && !stage_cnt) ? cnt_pf : a.rowcnt[grow];
+                                cnt = rb == 0 ? cnt_pf : a.rowcnt[grow];
                             }
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        double old = 0.0;
-                        if (need_old) {
-                            if (stage_old && r < rows_staged)
-                                old = vsm[r];
-                            else
-                                old = (rb == 0 && !stage_old) ? old_pf : a.t_out[grow];
-                        }
+                        const double old = !need_old ? 0.0 : (rb == 0 ? old_pf : a.t_out[grow]);
                         const double nv = row_epilogue(a, grow, v, old, d2);
                         if (want_q) {
-                            if (stage_aux) {
-                                const double2* yr = reinterpret_cast<const double2*>(ysm + (size_t)r * pitch_ys);
-#pragma unroll
-                                for (int m = 0; m < kMaxFusedResp; m += 2) {
-                                    double2 t = make_double2(0.0, 0.0);
-                                    if (m < pitch_ys) t = yr[m >> 1];
-                                    y_pf[m] = t.x;
-                                    y_pf[m + 1] = t.y;
-                                }
-                            } else if (rb != 0) {
-                                load_y_row(a, grow, y_pf);
-                            }
+                            if (rb != 0) load_y_row(a, grow, y_pf);
                             q_accumulate(qacc, y_pf, nv);
                         }
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&red_empty[sl]);
-                if (stage_aux) mbar_arrive(&empty[st_s]);
-            }
+            if (lane == 0) mbar_arrive(&red_empty[sl]);
         }
         if (a.d2part != nullptr && !slabbed) {
             d2 = warp_sum(d2);
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                         const double nv = row_epilogue(a, grow, v, old, d2);
                         if (want_q) {
                             double yv[kMaxFusedResp];
-                            if (stage_aux) {
+                            if (stage_y) {
                                 const double2* yr = reinterpret_cast<const double2*>(ytiles + (size_t)s * ystage + (size_t)r * pitch_ys);
 #pragma unroll
                                 for (int m = 0; m < kMaxFusedResp; m += 2) {

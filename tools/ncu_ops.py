@@ -3,7 +3,7 @@
 deflate + contract pass and the NaN-masked variants.
 
     python tools/ncu_ops.py                       # must exit 0 on its own first
-    ncu --set full --clock-control none -k regex:'colpass_kernel|rowpass_kernel' -c 8 -f -o gpurun_out/prof_ops python tools/ncu_ops.py
+    ncu --set full --clock-control none -k regex:'colpass_kernel|rowpass_kernel|multiproj_kernel|covpass_kernel' -c 14 -f -o gpurun_out/prof_ops python tools/ncu_ops.py
 """
 import ctypes as C
 import sys
@@ -34,6 +34,14 @@ def main():
                                              z.data_ptr(), ss.data_ptr(), None, 1))
         torch.cuda.synchronize()
         del X
+    # the single-pass multi-component projection of transform (multiproj.cu) and one cross-covariance pass
+    from cmtf_pls_b200 import ctPLS
+    X = torch.randn(n, 64, 64, dtype=torch.float32, device="cuda")
+    Y = torch.randn(n, 4, dtype=torch.float64, device="cuda")
+    est = ctPLS(10, algorithm="covariance")
+    est.fit([X[:50_000]], Y[:50_000], max_iter=3)
+    est.transform([X])
+    torch.cuda.synchronize()
     print("ok")
 
 
