@@ -71,8 +71,16 @@ PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm
     }
     g.tile_rows = (int)tr;
     const size_t slots = kSlots * row_slot_doubles(g, masked) * sizeof(double);
-    const long long stage = (long long)row_stage_bytes(g) + (long long)tr * aux_doubles * 8;
-    g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
+    // The staged side inputs are tiny beside a tile (96 bytes per 32 KB stage for 4096 fp32 columns): they must not
+    // cost a whole stage of the ring when the tiles alone fill the budget exactly -- up to 2 KB in total ride on top.
+    const long long aux_stage = (long long)tr * aux_doubles * 8;
+    long long stage = (long long)row_stage_bytes(g);
+    long long n_st = std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
+    if (n_st * aux_stage > 2048) {
+        stage += aux_stage;
+        n_st = std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
+    }
+    g.stages = (int)n_st;
     const long long n_tiles = (n_rows + tr - 1) / tr;
     const long long want = std::max(1, (sm_count * tune_env("TPLS_CTAS_PER_SM", 2)) / g.n_slabs);
     g.grid_x = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
