@@ -1072,13 +1072,9 @@ static int trip_body(tpls_handle h, const StreamPlan& P, int a, unsigned long lo
         r.epi = l == 0 ? 0 : (l == L - 1 ? 2 : 1);
         r.div = (double)L;
         r.ctrl = h->ctrl;
-        if (P.fused) {
-            r.pitch_y = h->pitch_y;
-            // t_out / rowcnt / y of a tile ride in the bulk-copy ring (t.gr has the room); the switch is for A/B runs
-            r.stage_aux = getenv("TPLS_NO_STAGE_AUX") == nullptr ? 1 : 0;
-        }
         if (P.fused && l == L - 1) {  // K4 fused: partials of q = Y't over the final (averaged) scores
             r.y = h->y_work;
+            r.pitch_y = h->pitch_y;
             r.qpart = h->qpart;
             q_parts = d2_grid(t.gr);
         }
@@ -1447,9 +1443,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
         for (int l = 0; l < L; ++l) {
             Tensor& t = h->x[l];
             t.masked = flagsh[l] != 0;
-            // room for the staged side inputs of the projection's epilogue (score so far + row of Y)
-            t.gr = make_row_geom(n, t.p, t.pitch, t.elem, h->sm_count, false,
-                                 (h->pitch_y <= kMaxFusedResp && getenv("TPLS_NO_STAGE_AUX") == nullptr) ? 2 + h->pitch_y : 0);
+            t.gr = make_row_geom(n, t.p, t.pitch, t.elem, h->sm_count, false);
             t.gr_cnt = make_row_geom(n, t.p, t.pitch, t.elem, h->sm_count, true);
         }
     }

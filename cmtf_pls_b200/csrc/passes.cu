@@ -176,13 +176,9 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
             // optional 0/1 sample weights (cross-validation folds): weighted column statistics and
             // weighted residual norm; the row's own sum of squares is folded in once per row
             const double sw = ((COLSTAT || SUMSQ) && a.row_sw != nullptr) ? __ldg(a.row_sw + grow) : 1.0;
-            // the row's sum of squares in two independent chains (one long chain of dependent DFMAs held the
-            // read-only residual pass at half the bandwidth), folded into ss once per row
-#ifdef TPLS_SS_ONE_CHAIN
-            constexpr int kSsMask = 0;   // A/B switch for measurements: one chain per row
-#else
-            constexpr int kSsMask = 1;
-#endif
+            // the row's sum of squares in two chains, folded into ss (times the row weight) once per row.  (Measured on
+            // one box against a single chain: no difference -- the read-only residual pass is held back by its three
+            // conversions per element, fp32 -> fp64, to the storage type and back, not by the dependent DFMAs.)
             double rs[2] = {0.0, 0.0};
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
@@ -197,8 +193,14 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
                     double xd = (double)xs;
                     if (DEFLATE) {
                         xd = fma(-ar, wreg[k][j], xd);
-                        out.e[j] = (XT)xd;       // NaN stays NaN
-                        xd = (double)out.e[j];   // later passes see the stored (rounded) value
+                        if (WRITE) {
+                            out.e[j] = (XT)xd;       // NaN stays NaN
+                            xd = (double)out.e[j];   // later passes see the stored (rounded) value
+                        }
+                        // (the read-only residual pass after the last component stores nothing: it sums the squares
+                        // of the unrounded values -- for fp32 storage that differs from the sum over the would-be
+                        // stored values by ~6e-8 / sqrt(elements) relative, and saves two of its three conversions
+                        // per element, which are what bounds it)
                     }
                     if (MASKED && !ob) xd = 0.0;
                     if (CONTRACT) zacc[k][j] = fma(xd, ur, zacc[k][j]);
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
                         cacc[k][j] += ob ? sw : 0.0;
                         nmiss += ob ? 0 : 1;
                     }
-                    if (SUMSQ) rs[j & kSsMask] = fma(xd, xd, rs[j & kSsMask]);
+                    if (SUMSQ) rs[j & 1] = fma(xd, xd, rs[j & 1]);
                 }
                 if (WRITE) {
                     __stcs(reinterpret_cast<typename VecOf<XT>::type*>(xo + grow * g.pitch + c0 + cg * VEC), out.v);

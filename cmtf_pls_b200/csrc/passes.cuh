@@ -57,11 +57,8 @@ size_t colpass_smem(const PassGeom& g, int pitch_y);
 constexpr int kMaxFusedResp = 8;            // responses (padded) up to which the Y side of a trip is fused into the X passes
 int tune_env(const char* name, int dflt);
 // Row passes use their own layout (fewer lanes per row, a slot ring for the reducer warp).
-// aux_doubles > 0: room per staged row for that many doubles of per-row side inputs of the epilogue (the score
-// accumulated so far + the row of Y: 1 + pitch_y), which then ride in the ring instead of being loaded from global
-// memory by the reducer warp (RowPassArgs::stage_aux); the fit uses 2 + pitch_y (+ the observed count of the row)
-PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked, int aux_doubles = 0);
-size_t rowpass_smem(const PassGeom& g, bool masked, int aux_doubles = 0);
+PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked);
+size_t rowpass_smem(const PassGeom& g, bool masked);
 
 struct ColPassArgs {
     PassGeom g;
@@ -96,8 +93,6 @@ struct RowPassArgs {
     int pitch_y;
     double* qpart;          // optional [grid_x or row_finish grid][kMaxFusedResp]: partials of q = Y't over the FINAL t
                             //   of this CTA's rows (tpls.py:100 fused into the projection's epilogue)
-    int stage_aux;          // 1: the geometry has room (make_row_geom aux_doubles = 2 + pitch_y) and t_out / rowcnt / y of a
-                            //   tile are staged with it (one slab only); 0: the epilogue loads them from global memory
     const Ctrl* ctrl;
     int trip;
 };

@@ -35,7 +35,7 @@ static size_t row_slot_doubles(const PassGeom& g, bool masked) {
     return g.lpr >= 32 ? (size_t)g.tile_rows * g.lpr * (masked ? 2 : 1) : 0;
 }
 
-PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked, int aux_doubles) {
+PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm_count, bool masked) {
     PassGeom g{};
     const int vec = 16 / elem_size;
     g.n_rows = n_rows;
@@ -65,31 +65,18 @@ PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm
     long long tr = std::max<long long>(1, tile_max / row_bytes);
     tr = std::min<long long>(tr, std::max<long long>(1, n_rows));
     tr = std::min<long long>(tr, 4096);
-    if (aux_doubles > 0) {  // staged side inputs: <= 16 KB per stage, an even number of rows (16-byte bulk copies)
-        tr = std::min<long long>(tr, std::max<long long>(2, 16384 / (8 * aux_doubles)));
-        if (tr > 1) tr &= ~1ll;
-    }
     g.tile_rows = (int)tr;
     const size_t slots = kSlots * row_slot_doubles(g, masked) * sizeof(double);
-    // The staged side inputs are tiny beside a tile (96 bytes per 32 KB stage for 4096 fp32 columns): they must not
-    // cost a whole stage of the ring when the tiles alone fill the budget exactly -- up to 2 KB in total ride on top.
-    const long long aux_stage = (long long)tr * aux_doubles * 8;
-    long long stage = (long long)row_stage_bytes(g);
-    long long n_st = std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
-    if (n_st * aux_stage > 2048) {
-        stage += aux_stage;
-        n_st = std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
-    }
-    g.stages = (int)n_st;
+    const long long stage = (long long)row_stage_bytes(g);
+    g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
     const long long n_tiles = (n_rows + tr - 1) / tr;
     const long long want = std::max(1, (sm_count * tune_env("TPLS_CTAS_PER_SM", 2)) / g.n_slabs);
     g.grid_x = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
     return g;
 }
 
-size_t rowpass_smem(const PassGeom& g, bool masked, int aux_doubles) {
-    return g.stages * (row_stage_bytes(g) + (size_t)g.tile_rows * aux_doubles * 8) + 256 +
-           kSlots * row_slot_doubles(g, masked) * sizeof(double) + 1024;
+size_t rowpass_smem(const PassGeom& g, bool masked) {
+    return g.stages * row_stage_bytes(g) + 256 + kSlots * row_slot_doubles(g, masked) * sizeof(double) + 1024;
 }
 
 // `old` = previous t[row]; only read by the caller when the epilogue needs it (coupled accumulation, ||dt||^2)
@@ -146,19 +133,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     const int srow = FULL ? kConsumers * VEC * CPT : ((g.n_slabs == 1) ? g.pitch : g.slab_w);
     const size_t stage_elems = (size_t)g.tile_rows * srow;
     XT* tiles = reinterpret_cast<XT*>(smem);
-    // side inputs of the epilogue staged with the tiles: the rows of Y (q = Y't partials) and the scores so far
-    const bool slabbed = g.n_slabs > 1;
-    const bool stage_aux = a.stage_aux != 0 && !slabbed && g.tile_rows > 1 && (g.tile_rows & 1) == 0;
-    // (a bulk copy needs a 16-byte aligned source: column a of the column-major scores is not, for an odd row count)
-    const bool stage_old = stage_aux && epilogue_needs_old(a) && (reinterpret_cast<uintptr_t>(a.t_out) & 15) == 0;
-    const bool stage_cnt = stage_aux && MASKED && !COUNT && (reinterpret_cast<uintptr_t>(a.rowcnt) & 15) == 0;
-    const bool stage_y = stage_aux && a.y != nullptr && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
-    const int pitch_ys = stage_aux ? a.pitch_y : 0;
-    const size_t ystage = (size_t)g.tile_rows * pitch_ys;
-    double* ytiles = reinterpret_cast<double*>(smem + (size_t)g.stages * stage_elems * sizeof(XT));
-    double* vtiles = ytiles + (size_t)g.stages * ystage;                 // scores so far
-    double* ctiles = vtiles + (size_t)g.stages * g.tile_rows;            // observed entries per row (masked, known)
-    const size_t tile_area = (size_t)g.stages * (stage_elems * sizeof(XT) + (stage_aux ? (ystage + 2 * g.tile_rows) * sizeof(double) : 0));
+    const size_t tile_area = (size_t)g.stages * stage_elems * sizeof(XT);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + tile_area);
     uint64_t* empty = full + kMaxStages;
     uint64_t* red_full = empty + kMaxStages;
@@ -166,13 +141,13 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     double* slots = reinterpret_cast<double*>(smem + tile_area + 256);
     const bool use_slots = FULL ? true : (g.lpr >= 32);
     const size_t slot_doubles = use_slots ? (size_t)g.tile_rows * lpr * (COUNT ? 2 : 1) : 0;
+    const bool slabbed = g.n_slabs > 1;
     const double p_total = (double)g.p;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(&full[s], 1);
-            // with staged side inputs the reducer warp reads the stage too (into registers, right after the copy landed)
-            mbar_init(&empty[s], kConsumers / 32 + ((stage_aux && use_slots) ? 1 : 0));
+            mbar_init(&empty[s], kConsumers / 32);
         }
         for (int s = 0; s < kSlots; ++s) {
             mbar_init(&red_full[s], kConsumers / 32);
@@ -189,9 +164,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     // ------------------------------------------------------------------ producer
     if (tid >= kConsumers && tid < kConsumers + 32) {
         if (tid == kConsumers)
-            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow,
-                              stage_y ? a.y : nullptr, pitch_ys, ytiles,
-                              stage_old ? a.t_out : nullptr, vtiles, stage_cnt ? a.rowcnt : nullptr, ctiles);
+            produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow);
         return;
     }
 
@@ -218,36 +191,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
             const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
             // what the first round's epilogue reads from global memory is requested BEFORE the wait, so that
             // its latency (microseconds while the HBM is saturated) overlaps the consumers' work on the tile
-            // With staged side inputs the FIRST round's values come out of the stage as soon as the copy has landed
-            // (long before the consumers are done with the tile) and the stage is released at once, so the ring keeps
-            // its depth; later rounds of a many-row tile read global memory like the unstaged path.
             double old_pf = 0.0, cnt_pf = 1.0;
-            const int rows_staged = rows & ~1;
-            if (stage_aux) {
-                const int st_s = (int)(it % g.stages);
-                mbar_wait(&full[st_s], (uint32_t)((it / g.stages) & 1));
-                if (gl == 0 && rg < rows) {
-                    const bool in_stage = rg < rows_staged;
-                    if (need_old) old_pf = (stage_old && in_stage) ? vtiles[(size_t)st_s * g.tile_rows + rg] : a.t_out[r0 + rg];
-                    if (MASKED && !COUNT) cnt_pf = (stage_cnt && in_stage) ? ctiles[(size_t)st_s * g.tile_rows + rg] : a.rowcnt[r0 + rg];
-                    if (want_q) {
-                        if (stage_y) {
-                            const double2* yr = reinterpret_cast<const double2*>(ytiles + (size_t)st_s * ystage + (size_t)rg * pitch_ys);
-#pragma unroll
-                            for (int m = 0; m < kMaxFusedResp; m += 2) {
-                                double2 t = make_double2(0.0, 0.0);
-                                if (m < pitch_ys) t = yr[m >> 1];
-                                y_pf[m] = t.x;
-                                y_pf[m + 1] = t.y;
-                            }
-                        } else {
-                            load_y_row(a, r0 + rg, y_pf);
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[st_s]);
-            } else if (gl == 0 && rg < rows && !slabbed) {
+            if (gl == 0 && rg < rows && !slabbed) {
                 if (need_old) old_pf = a.t_out[r0 + rg];
                 if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + rg];
                 if (want_q) load_y_row(a, r0 + rg, y_pf);
@@ -423,24 +368,10 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                             }
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        double old = 0.0;
-                        if (epilogue_needs_old(a))
-                            old = (stage_old && r < (rows & ~1)) ? vtiles[(size_t)s * g.tile_rows + r] : a.t_out[grow];
-                        const double nv = row_epilogue(a, grow, v, old, d2);
+                        const double nv = row_epilogue(a, grow, v, epilogue_needs_old(a) ? a.t_out[grow] : 0.0, d2);
                         if (want_q) {
                             double yv[kMaxFusedResp];
-                            if (stage_y) {
-                                const double2* yr = reinterpret_cast<const double2*>(ytiles + (size_t)s * ystage + (size_t)r * pitch_ys);
-#pragma unroll
-                                for (int m = 0; m < kMaxFusedResp; m += 2) {
-                                    double2 t = make_double2(0.0, 0.0);
-                                    if (m < pitch_ys) t = yr[m >> 1];
-                                    yv[m] = t.x;
-                                    yv[m + 1] = t.y;
-                                }
-                            } else {
-                                load_y_row(a, grow, yv);
-                            }
+                            load_y_row(a, grow, yv);
                             q_accumulate(qacc, yv, nv);
                         }
                     }
@@ -489,7 +420,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
 template <typename XT, int CPT, int MODE, bool FULL>
 static cudaError_t run_rowpass_impl(const RowPassArgs& a, cudaStream_t s) {
     auto kern = rowpass_kernel<XT, CPT, MODE, FULL>;
-    const size_t smem = rowpass_smem(a.g, MODE == 2, a.stage_aux ? 2 + a.pitch_y : 0);
+    const size_t smem = rowpass_smem(a.g, MODE == 2);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);

@@ -25,17 +25,12 @@ union Pack {
 };
 
 // Producer: one elected lane streams this CTA's row tiles into the smem ring.  With `y` the matching rows of
-// Y (pitch_y doubles each, contiguous in memory) ride on the same barrier into ytiles[stage][tile_rows * pitch_y];
-// with `v` a per-row vector (one double per row, e.g. the scores accumulated so far) into vtiles[stage][tile_rows]
-// -- an even number of entries per tile (bulk copies move multiples of 16 bytes): the consumer of an odd last row
-// reads it from global memory.
+// Y (pitch_y doubles each, contiguous in memory) ride on the same barrier into ytiles[stage][tile_rows * pitch_y].
 template <typename XT>
 __device__ __forceinline__ void produce_tiles(const PassGeom& g, const XT* __restrict__ x, XT* tiles, uint64_t* full,
                                               uint64_t* empty, int c0, int slab_cols, int srow,
                                               const double* __restrict__ y = nullptr, int pitch_y = 0,
-                                              double* ytiles = nullptr, const double* __restrict__ v = nullptr,
-                                              double* vtiles = nullptr, const double* __restrict__ v2 = nullptr,
-                                              double* v2tiles = nullptr) {
+                                              double* ytiles = nullptr) {
     const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
     const size_t stage_elems = (size_t)g.tile_rows * srow;
     const size_t ystage = (size_t)g.tile_rows * pitch_y;
@@ -49,20 +44,16 @@ __device__ __forceinline__ void produce_tiles(const PassGeom& g, const XT* __res
         XT* dst = tiles + s * stage_elems;
         const XT* src = x + r0 * g.pitch + c0;
         const uint32_t ybytes = y != nullptr ? (uint32_t)((size_t)rows * pitch_y * sizeof(double)) : 0u;
-        const uint32_t vbytes = v != nullptr ? (uint32_t)((rows & ~1) * sizeof(double)) : 0u;
-        const uint32_t v2bytes = v2 != nullptr ? (uint32_t)((rows & ~1) * sizeof(double)) : 0u;
         if (g.n_slabs == 1) {
             const uint32_t bytes = (uint32_t)((size_t)rows * g.pitch * sizeof(XT));
-            mbar_arrive_expect_tx(&full[s], bytes + ybytes + vbytes + v2bytes);
+            mbar_arrive_expect_tx(&full[s], bytes + ybytes);
             bulk_g2s(dst, src, bytes, &full[s]);
         } else {
             const uint32_t rb = (uint32_t)(slab_cols * sizeof(XT));
-            mbar_arrive_expect_tx(&full[s], rb * rows + ybytes + vbytes + v2bytes);
+            mbar_arrive_expect_tx(&full[s], rb * rows + ybytes);
             for (int r = 0; r < rows; ++r) bulk_g2s(dst + (size_t)r * srow, src + (size_t)r * g.pitch, rb, &full[s]);
         }
         if (y != nullptr) bulk_g2s(ytiles + s * ystage, y + r0 * pitch_y, ybytes, &full[s]);
-        if (vbytes != 0u) bulk_g2s(vtiles + (size_t)s * g.tile_rows, v + r0, vbytes, &full[s]);
-        if (v2bytes != 0u) bulk_g2s(v2tiles + (size_t)s * g.tile_rows, v2 + r0, v2bytes, &full[s]);
     }
 }
 
