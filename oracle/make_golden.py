@@ -189,6 +189,14 @@ def main():
     Y = gen.random((20, 5))
     single("t4_maxiter_20x6x5x4_m5_r2", X, Y, 2, max_iter=4)
 
+    # 6-way and 7-way X (5- and 6-way Z through the HOSVD start + ALS sweeps): own generator, so that the cases
+    # above regenerate bit-identically
+    X, Y, _ = import_synthetic((24, 4, 3, 3, 2, 2), 3, 3, error=0.3, seed=61)
+    single("t6_24x4x3x3x2x2_m3_r2", X, Y, 2)
+    X, Y, _ = import_synthetic((20, 3, 3, 2, 2, 2, 2), 2, 3, error=0.3, seed=71)
+    Xn, Yn, _ = import_synthetic((5, 3, 3, 2, 2, 2, 2), 2, 3, error=0.3, seed=72)
+    single("t7_20x3x3x2x2x2x2_m2_r2", X, Y, 2, Xn, Yn)
+
 
 if __name__ == "__main__":
     main()
