@@ -1,11 +1,9 @@
 #!/bin/bash
 # ncu evidence for profiles/ (one B200, run under gpurun), round 2.  Each ncu pass runs only after the same command
 # exited 0 without it.  The fit is enqueued kernel by kernel (TPLS_NO_GRAPH=1: the same kernels as the graph-launched
-# fit, but plain launches that ncu lists one by one).
+# fit, but plain launches that ncu lists one by one).  The reports are summarised ON THE BOX (tools/ncu_summary.py, the
+# raw and source pages as CSV) and deleted: gpurun brings back at most 64 MiB.
 #   gpurun --timeout 1500 -- 'bash tools/ncu_capture_r02.sh'
-# then, here:  python tools/ncu_summary.py launches gpurun_out/r02ncu/launches.csv profiles/r02_ncu_launch_list_summary.csv "$CMD"
-#              python tools/ncu_summary.py full gpurun_out/r02ncu/prof_fit.ncu-rep profiles/r02_ncu_full_top_kernels.csv "$CMD"
-#              python tools/ncu_summary.py full gpurun_out/r02ncu/prof_ops.ncu-rep profiles/r02_ncu_full_op_variants.csv "python tools/ncu_ops.py"
 set -u
 O=gpurun_out/r02ncu
 mkdir -p $O
@@ -17,19 +15,22 @@ MINE='colpass_kernel|rowpass_kernel|covpass_kernel|cov_loop_kernel|rank1_kernel|
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$MINE" -c 1700 --csv \
     --log-file $O/launches.csv $CMD > $O/ncu_launches.log 2>&1
 echo "launch list rc=$?"
+python tools/ncu_summary.py launches $O/launches.csv $O/launch_list_summary.csv "TPLS_NO_GRAPH=1 $CMD"
+full() {  # name, kernel regex, launches to skip, launches to capture, command...
+    local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
+    ncu --set full --clock-control none --import-source on -k regex:"$rx" --launch-skip $skip -c $cnt -f -o $O/prof_$name "$@" > $O/ncu_$name.log 2>&1
+    echo "full set ($name) rc=$?"
+    python tools/ncu_summary.py full $O/prof_$name.ncu-rep $O/full_$name.csv "$*"
+    ncu -i $O/prof_$name.ncu-rep --page source --csv > $O/source_$name.csv 2> /dev/null
+    rm -f $O/prof_$name.ncu-rep
+}
 $CMD > $O/plain2.log 2>&1 || { echo "plain run 2 failed"; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:'colpass_kernel|rowpass_kernel|rank1_kernel' \
-    --launch-skip 40 -c 12 -f -o $O/prof_fit $CMD > $O/ncu_full.log 2>&1
-echo "full set (fit) rc=$?"
-# (TPLS_NO_GRAPH stays set: the covariance fit of ncu_ops.py is enqueued kernel by kernel too)
+# colpass launches of a fit: column statistics (X, X, Y), centre Y, fused centring (X, X), then the contractions
+full colpass 'colpass_kernel' 4 4 $CMD
+full rowpass 'rowpass_kernel' 2 2 $CMD
+full rank1 'rank1_kernel' 2 1 $CMD
 python tools/ncu_ops.py > $O/ops_plain.log 2>&1 || { echo "ops plain run failed"; tail -5 $O/ops_plain.log; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:'colpass_kernel|rowpass_kernel' \
-    -c 7 -f -o $O/prof_ops python tools/ncu_ops.py > $O/ncu_ops.log 2>&1
-echo "full set (ops) rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'multiproj_kernel' \
-    -c 1 -f -o $O/prof_multiproj python tools/ncu_ops.py > $O/ncu_multiproj.log 2>&1
-echo "full set (multiproj) rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'covpass_kernel' \
-    --launch-skip 1 -c 1 -f -o $O/prof_covpass python tools/ncu_ops.py > $O/ncu_covpass.log 2>&1
-echo "full set (covpass) rc=$?"
-ls -la $O
+full ops 'colpass_kernel|rowpass_kernel' 0 7 python tools/ncu_ops.py
+full multiproj 'multiproj_kernel' 0 1 python tools/ncu_ops.py
+full covpass 'covpass_kernel' 1 1 python tools/ncu_ops.py
+du -sh $O; ls -la $O
