@@ -484,7 +484,7 @@ def run_ours(args):
     kernel_ms = sum(v["ms"] for v in prof.values())
     traffic = None
     try:  # DRAM bytes per launch from the committed ncu capture, scaled to this launch's algorithmic bytes
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             tj = json.load(f)
         kk = tj["rowpass_kernel" if dom == "project" else "colpass_kernel_contract"]
         traffic = (kk["dram_read_bytes"] + kk["dram_write_bytes"]) / tj["algorithmic_bytes_per_launch"] * (d["bytes"] / max(1, d["launches"]))
@@ -496,7 +496,7 @@ def run_ours(args):
         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": traffic,
         "peak_source": peak_src,
         "note": "read-only stream measured against a COPY (read+write) peak, so a fraction slightly above 1 is expected; "
-                "traffic = ncu dram bytes per launch (profiles/r01_ncu_traffic.json) scaled to this launch size",
+                "traffic = ncu dram bytes per launch (profiles/r02_ncu_traffic.json) scaled to this launch size",
         "bytes_per_launch": d["bytes"] / max(1, d["launches"]), "ms_per_launch": d["ms"] / max(1, d["launches"]),
         "share_of_step": d["ms"] / (ms_profiled if world == 1 else kernel_ms),
         "measured": "CUDA events around every launch of %d profiled (host-enqueued) fits run right after the timed "
