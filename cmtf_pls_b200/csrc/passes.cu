@@ -321,10 +321,15 @@ cudaError_t launch_reduce_cols(const ReduceArgs& a, cudaStream_t s) {
 __global__ void __launch_bounds__(256) fold_sets_kernel(const __grid_constant__ FoldArgs a) {
     pdl_prologue();
     if (trip_is_dead(a.ctrl, 0)) return;
-    __shared__ double fold[8][33];
+    __shared__ double fold[8][37];  // 8 x 37 >= 32 x 9: doubles as the [32][9] area of fold_narrow
     const int cl = threadIdx.x & 31, q = threadIdx.x >> 5;
     int c_base = 0;
     const FoldSet& S = a.sets[fold_locate(a.sets, a.n_sets, blockIdx.x, &c_base)];
+    if (S.n_cols <= 8) {  // narrow set: 32 part-groups per column
+        const double t = fold_narrow(S, reinterpret_cast<double(*)[9]>(&fold[0][0]));
+        if ((threadIdx.x >> 3) == 0 && (int)(threadIdx.x & 7) < S.n_cols) a.out[S.off + (threadIdx.x & 7)] = t;
+        return;
+    }
     const int c = c_base + cl;
     fold[q][cl] = fold_share(S, c, q);
     __syncthreads();

@@ -1,5 +1,6 @@
 // Small kernels -- see small.cuh.
 #include "small.cuh"
+#include "stream_common.cuh"
 
 #include <cstdlib>
 
@@ -94,36 +95,23 @@ __global__ void __launch_bounds__(256) reduce_q_stop_kernel(const double* part, 
                                                             double* q_prev, Ctrl* ctrl, const LoopEnd e) {
     pdl_prologue();
     if (trip_is_dead(ctrl, 0)) return;
-    __shared__ double fold[8][33];
-    const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-    if (c < pitch) {
-        int b = q;
-        for (; b + 24 < n_parts; b += 32) {
-            t0 += part[(size_t)(b + 0) * stride + c];
-            t1 += part[(size_t)(b + 8) * stride + c];
-            t2 += part[(size_t)(b + 16) * stride + c];
-            t3 += part[(size_t)(b + 24) * stride + c];
-        }
-        for (; b < n_parts; b += 8) t0 += part[(size_t)b * stride + c];
-    }
-    fold[q][c] = (t0 + t1) + (t2 + t3);
-    __syncthreads();
-    if (q == 0 && c < pitch) {
-        double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t += fold[k][c];
-        fold[0][c] = t;
-        qraw[c] = t;
+    // pitch <= 8 columns: 8 columns x 32 part-groups (the association order of fold_narrow)
+    __shared__ double fold32[32][9];
+    __shared__ double qsum[8];
+    FoldSet S{part, n_parts, stride, pitch, 0};
+    const double t = fold_narrow(S, fold32);
+    if ((threadIdx.x >> 3) == 0 && (int)(threadIdx.x & 7) < pitch) {
+        qsum[threadIdx.x & 7] = t;
+        qraw[threadIdx.x & 7] = t;
     }
     __syncthreads();
-    if (threadIdx.x == 0) normalize_q_stop_body(fold[0], m, pitch, qcol, qvec, gram, q_prev, ctrl, e);
+    if (threadIdx.x == 0) normalize_q_stop_body(qsum, m, pitch, qcol, qvec, gram, q_prev, ctrl, e);
 }
 
 cudaError_t launch_reduce_q_stop(const double* part, int n_parts, int stride, double* qraw, int m, int pitch, double* qcol,
                                  double* qvec, const double* gram, double* q_prev, Ctrl* ctrl, const LoopEnd& e,
                                  cudaStream_t s) {
-    if (pitch > 32 || m > 8) return cudaErrorInvalidValue;
+    if (pitch > 8 || m > 8) return cudaErrorInvalidValue;
     launch_k(reduce_q_stop_kernel, dim3(1), dim3(256), 0, s, part, n_parts, stride, qraw, m, pitch, qcol, qvec, gram, q_prev, ctrl, e);
     return cudaGetLastError();
 }

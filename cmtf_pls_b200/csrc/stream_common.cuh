@@ -57,21 +57,47 @@ __device__ __forceinline__ void produce_tiles(const PassGeom& g, const XT* __res
     }
 }
 
-// One 32-column chunk of a second-stage fold (reduce_cols order): 256 threads = 32 columns x 8 part-groups, each
+// One 32-column chunk of a second-stage fold: 256 threads = 32 columns x 8 part-groups, each
 // thread folds every 8th partial of its column in four independent chains.  Returns this thread's share.
 __device__ __forceinline__ double fold_share(const FoldSet& S, int c, int q) {
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    // eight independent chains: ~300 partials per column are 37 loads per thread, i.e. five dependent L2 round trips
+    // (with four chains it was ten, and this fold sits on the critical path of every trip)
+    double t[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (c < S.n_cols) {
         int b = q;
-        for (; b + 24 < S.n_parts; b += 32) {
-            t0 += S.part[(size_t)(b + 0) * S.stride + c];
-            t1 += S.part[(size_t)(b + 8) * S.stride + c];
-            t2 += S.part[(size_t)(b + 16) * S.stride + c];
-            t3 += S.part[(size_t)(b + 24) * S.stride + c];
+        for (; b + 56 < S.n_parts; b += 64) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] += S.part[(size_t)(b + 8 * k) * S.stride + c];
         }
-        for (; b < S.n_parts; b += 8) t0 += S.part[(size_t)b * S.stride + c];
+        for (int k = 0; b < S.n_parts; b += 8, ++k) t[k & 7] += S.part[(size_t)b * S.stride + c];
     }
-    return (t0 + t1) + (t2 + t3);
+    return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+}
+
+// The same for a NARROW set (at most 8 columns, e.g. the partials of q = Y't): 256 threads = 8 columns x 32
+// part-groups, so that the ~300 partials of a column are folded by 32 threads instead of 8 (a fold by 8 threads is
+// ten dependent L2 round trips, ~10 us on the critical path of every trip).  fold32 is [32][9] doubles of shared
+// memory; returns the column's sum in the threads with grp == 0 (valid for col < n_cols).
+__device__ __forceinline__ double fold_narrow(const FoldSet& S, double (*fold32)[9]) {
+    const int col = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    double t0 = 0.0, t1 = 0.0;
+    if (col < S.n_cols) {
+        int b = grp;
+        for (; b + 32 < S.n_parts; b += 64) {
+            t0 += S.part[(size_t)b * S.stride + col];
+            t1 += S.part[(size_t)(b + 32) * S.stride + col];
+        }
+        if (b < S.n_parts) t0 += S.part[(size_t)b * S.stride + col];
+    }
+    __syncthreads();
+    fold32[grp][col] = t0 + t1;
+    __syncthreads();
+    double t = 0.0;
+    if (grp == 0) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += fold32[k][col];
+    }
+    return t;
 }
 
 // which set does chunk `chunk` belong to (chunks are numbered set by set) and which is its first column
