@@ -207,6 +207,18 @@ def cpu_threads():
     return int(n), len(os.sched_getaffinity(0))
 
 
+def cpu_extrapolation(seconds, rate_gbs, trips_full=None):
+    """a full-size CPU figure can only be a linear-in-N EXTRAPOLATION of the bounded sample and must
+    be labelled as such (the reference would need hours and > 100 GB of host RAM for 1M rows)."""
+    out = {"label": "EXTRAPOLATION, linear in N, from the bounded sample -- not a measurement",
+           "same_fit_at_1M_rows_s": seconds * N_TOTAL / CPU_SAMPLE_ROWS,
+           "basis": f"{CPU_SAMPLE_R}-component fit of {CPU_SAMPLE_ROWS} rows took {seconds:.2f} s"}
+    if trips_full is not None and rate_gbs > 0:
+        out["full_workload_s"] = alg_bytes(N_TOTAL, trips_full, R) / (rate_gbs * 1e9)
+        out["full_workload"] = f"{R} components, {trips_full} inner trips (the GPU fit's count), at the sample's B_alg rate"
+    return out
+
+
 def cpu_baseline_block(value, cores, affinity):
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": (f"oracle/tpls_oracle.fit (numpy restatement of cmtf_pls ctPLS.fit incl. its dense R2X/R2Y "
@@ -236,7 +248,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[3] shape (coupled pair x64x64 fp32, M=4), bounded CPU sample",
                    "rows": CPU_SAMPLE_ROWS, "components": CPU_SAMPLE_R, "latent": LATENT, "error": ERROR, "trips": trips},
-        "cpu_baseline": cpu_baseline_block(val, cores, aff),
+        "cpu_baseline": dict(cpu_baseline_block(val, cores, aff), extrapolation=cpu_extrapolation(t_tot / args.steps, val)),
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -513,6 +525,7 @@ def run_ours(args):
         cpu = cpu_baseline_block(b / dt / 1e9, cores, aff)
         cpu["seconds"] = dt
         cpu["trips"] = tr
+        cpu["extrapolation"] = cpu_extrapolation(dt, b / dt / 1e9, trips)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
