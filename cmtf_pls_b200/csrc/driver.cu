@@ -1464,7 +1464,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     // Everything from here to the residual norms is ONE sequence of launches with no host decision in it: captured
     // into a CUDA graph (and kept for the next fit with the same key) unless the fit is profiled, some collective
     // has to go through NCCL, or TPLS_NO_GRAPH is set.
-    bool use_graph = !h->profile && getenv("TPLS_NO_GRAPH") == nullptr;
+    bool use_graph = !h->profile && !h->graph_broken && getenv("TPLS_NO_GRAPH") == nullptr;
     if (h->world > 1) {
         const size_t biggest = std::max(h->zcat_len, cov_mode ? h->cov_len : (size_t)0);
         if (!xchg_fits(h, biggest)) use_graph = false;
@@ -1512,16 +1512,28 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             h->stream = st;
             cudaGraph_t g = nullptr;
             cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
-            if (rc) {
-                if (g) cudaGraphDestroy(g);
-                return rc;
+            if (rc == 0 && e != cudaSuccess) rc = fail(h, "tpls_fit: capturing the fit -> %s", cudaGetErrorString(e));
+            if (rc == 0) {
+                h->graph = g;
+                g = nullptr;
+                e = cudaGraphInstantiate(&h->graph_exec, h->graph, 0);
+                if (e != cudaSuccess) rc = fail(h, "tpls_fit: cudaGraphInstantiate -> %s", cudaGetErrorString(e));
             }
-            if (e != cudaSuccess) return fail(h, "tpls_fit: capturing the fit -> %s", cudaGetErrorString(e));
-            h->graph = g;
-            e = cudaGraphInstantiate(&h->graph_exec, g, 0);
-            if (e != cudaSuccess) {
+            if (rc != 0) {
+                if (g) cudaGraphDestroy(g);
                 drop_graph(h);
-                return fail(h, "tpls_fit: cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+                cudaGetLastError();
+                // Nothing has run yet.  A single-GPU fit falls back to host-enqueued trips (and stays there); on
+                // several GPUs every rank must drive its loop the same way (a host-driven rank enqueues a fixed number
+                // of bodies past the stop, a graph does not), so there the failure is reported.
+                if (h->world > 1) return rc;
+                h->graph_broken = true;
+                h->stats = pre;
+                for (auto& b : h->body) b = tpls_ctx::BodyCount{};
+                h->fit_mode = 0;
+                use_graph = false;
+                TRY(enqueue_main());
+                goto loops_done;
             }
             h->graph_key = key;
             // static launches of the captured fit (the loop bodies were captured once each)
@@ -1541,6 +1553,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
     } else {
         TRY(enqueue_main());
     }
+loops_done:
 
     // ---- R2X / R2Y from the residual norms ----
     // through NCCL on purpose: it cannot complete before every peer has finished all earlier exchanges,

@@ -138,6 +138,7 @@ struct tpls_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     unsigned long long graph_key = 0;
     bool capturing = false;
+    bool graph_broken = false;  // capturing / instantiating failed once on this handle: host-enqueued trips from then on
     // launch accounting of the trip body of every component (launches / collectives / streamed bytes of ONE body,
     // bytes of the trailing contraction that the last body skips, bodies the host enqueued)
     struct BodyCount {
