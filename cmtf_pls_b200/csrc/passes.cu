@@ -163,32 +163,14 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
             if (DEFLATE && a.row_a != nullptr) ar = __ldg(a.row_a + grow);
             if (CONTRACT) {
                 if (use_y) {
-                    // u[row] = y[row, :] . q, unrolled for the (even, <= 8) pitch of Y: a runtime loop cost ~35
-                    // instructions per row and thread (ncu: +41 % instructions over the plain contraction)
+                    // (a compile-time unrolled variant with two chains was measured against this loop on one box:
+                    //  1 % slower, although it executes ~25 % fewer instructions -- the pass waits on the copy barrier)
                     const double2* yr = reinterpret_cast<const double2*>(yp + (size_t)r * pitch_y);
-                    const double2* qr = reinterpret_cast<const double2*>(qs);
-                    double u1 = 0.0;
-                    {
-                        const double2 yv = yr[0], qv = qr[0];
-                        ur = yv.x * qv.x;
-                        u1 = yv.y * qv.y;
+                    for (int m = 0; m < pitch_y; m += 2) {
+                        const double2 yv = yr[m >> 1];
+                        ur = fma(yv.x, qs[m], ur);
+                        ur = fma(yv.y, qs[m + 1], ur);
                     }
-                    if (pitch_y > 2) {
-                        const double2 yv = yr[1], qv = qr[1];
-                        ur = fma(yv.x, qv.x, ur);
-                        u1 = fma(yv.y, qv.y, u1);
-                    }
-                    if (pitch_y > 4) {
-                        const double2 yv = yr[2], qv = qr[2];
-                        ur = fma(yv.x, qv.x, ur);
-                        u1 = fma(yv.y, qv.y, u1);
-                    }
-                    if (pitch_y > 6) {
-                        const double2 yv = yr[3], qv = qr[3];
-                        ur = fma(yv.x, qv.x, ur);
-                        u1 = fma(yv.y, qv.y, u1);
-                    }
-                    ur += u1;
                 } else {
                     ur = __ldg(a.row_u + grow);
                 }
