@@ -6,12 +6,15 @@ for fp32 storage, on loadings, scores, Q, coef_, R2X, R2Y after per-component
 sign alignment; measured per factor column as ||a-b|| / ||b||.
 """
 
+import os
+
 import numpy as np
 import pytest
 
 from _util import golden_cases, load_golden, aligned_errors, col_err
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 FP64_TOL = 1e-8
 FP32_TOL = 1e-4
@@ -395,3 +398,34 @@ def test_fit_runs_as_one_graph_and_reports_its_launches():
     assert est.n_iter_.tolist() == first[0] and np.array_equal(est.factor_T, first[1])
     ref = orc.fit([x.copy() for x in Xs], Y.copy(), 3, r2_mode="residual")
     assert est.n_iter_.tolist() == ref["trips"].tolist()
+
+
+@pytest.mark.parametrize("env", [{"TPLS_NO_GRAPH": "1"}, {"TPLS_PDL": "0"}, {"TPLS_NO_GRAPH": "1", "TPLS_PDL": "0"}])
+def test_host_enqueued_and_plain_launch_paths_give_the_same_fit(env, tmp_path):
+    """The graph-launched fit (default), the host-enqueued trips (profiling / NCCL fallback) and launches without the
+    PDL attribute run the same kernels: bit-identical results.  The switches are read once per process, so the
+    variants run in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    from cmtf_pls_b200 import ctPLS
+    g = load_golden("ct_90x32x16_90x24_m4_r5")
+    est = ctPLS(5)
+    est.fit([x.copy() for x in g["Xs"]], g["Y"].copy())
+    out = str(tmp_path / "variant.npz")
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        "from _util import load_golden\n"
+        "from cmtf_pls_b200 import ctPLS\n"
+        "g = load_golden('ct_90x32x16_90x24_m4_r5')\n"
+        "est = ctPLS(5)\n"
+        "est.fit([x.copy() for x in g['Xs']], g['Y'].copy())\n"
+        f"np.savez({out!r}, T=est.factor_T, coef=est.coef_, trips=est.n_iter_, graph=np.array(est.stats_['graph_launches']))\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    v = np.load(out)
+    assert v["trips"].tolist() == est.n_iter_.tolist() == g["trips"].tolist()
+    assert int(v["graph"]) == (0 if "TPLS_NO_GRAPH" in env else 1)
+    assert np.array_equal(v["T"], est.factor_T) and np.array_equal(v["coef"], est.coef_)

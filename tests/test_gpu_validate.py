@@ -65,3 +65,22 @@ def test_cv_fold_with_all_nans_in_held_out_rows_stays_finite():
         q, cv = q2y_sweep(X, Y, 3, folds=folds, return_scores=True, algorithm=alg)
         assert np.all(np.isfinite(q)) and np.all(np.isfinite(cv))
         assert np.max(np.abs(q - q_ref)) < 1e-8, alg
+
+
+def test_covariance_loop_with_three_coupled_tensors_matches_oracle():
+    """The covariance-mode inner loop runs one CTA per coupled tensor in a thread-block cluster (the per-tensor parts
+    of Y't meet through distributed shared memory): three tensors of different order, against the oracle."""
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import ctPLS
+    Xs, Y, _ = orc.synthetic((120, 16, 8), 4, 5, error=0.4, seed=17, extra_dims=[(120, 6, 5, 4), (120, 20)])
+    ref = orc.fit([x.copy() for x in Xs], Y.copy(), 4, r2_mode="residual")
+    for alg in ("covariance", "stream"):
+        est = ctPLS(4, algorithm=alg)
+        est.fit([x.copy() for x in Xs], Y.copy())
+        assert bool(est.stats_["covariance_mode"]) == (alg == "covariance")
+        assert est.n_iter_.tolist() == ref["trips"].tolist(), alg
+        s = np.sign(np.sum(est.factor_T * ref["T"], axis=0))
+        assert np.max(np.abs(est.factor_T * s - ref["T"])) / np.max(np.abs(ref["T"])) < 1e-8, alg
+        assert np.max(np.abs(est.R2Y - ref["R2Y"])) < 1e-8, alg
+        for l in range(3):
+            assert np.max(np.abs(est.R2Xs[l] - ref["R2X"][l])) < 1e-8, (alg, l)
