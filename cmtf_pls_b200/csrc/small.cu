@@ -116,22 +116,6 @@ cudaError_t launch_reduce_q_stop(const double* part, int n_parts, int stride, do
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) sum_small_kernel(const double* parts, int n, double* out, const Ctrl* ctrl,
-                                                        int trip) {
-    pdl_prologue();
-    if (trip_is_dead(ctrl, trip)) return;
-    __shared__ double red[40];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += parts[i];
-    s = block_sum(s, red);
-    if (threadIdx.x == 0) out[0] = s;
-}
-
-cudaError_t launch_sum_small(const double* parts, int n, double* out, const Ctrl* ctrl, int trip, cudaStream_t s) {
-    launch_k(sum_small_kernel, dim3(1), dim3(256), 0, s, parts, n, out, ctrl, trip);
-    return cudaGetLastError();
-}
-
 __global__ void __launch_bounds__(256) stop_kernel(Ctrl* ctrl, const double* parts, int n, const LoopEnd e) {
     pdl_prologue();
     if (trip_is_dead(ctrl, 0)) return;
@@ -348,37 +332,6 @@ __global__ void count_rescale_kernel(double* z, const double* cnt, double n_tota
 
 cudaError_t launch_count_rescale(double* z, const double* cnt, double n_total, int p, cudaStream_t s) {
     launch_k(count_rescale_kernel, dim3((p + 255) / 256), dim3(256), 0, s, z, cnt, n_total, p);
-    return cudaGetLastError();
-}
-
-__global__ void rows_complete_kernel(const double* rowcnt, long long n, double p, int* flag) {
-    pdl_prologue();
-    bool bad = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        bad |= !(rowcnt[i] == p);
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
-}
-
-cudaError_t launch_rows_complete(const double* rowcnt, long long n, double p, int* flag, cudaStream_t s) {
-    const int blocks = (int)std::max<long long>(1, std::min<long long>(592, (n + 255) / 256));
-    launch_k(rows_complete_kernel, dim3(blocks), dim3(256), 0, s, rowcnt, n, p, flag);
-    return cudaGetLastError();
-}
-
-__global__ void score_recurrence_kernel(double* S, long long n, int R, const double* c, const double* G) {
-    pdl_prologue();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        for (int a = 0; a < R; ++a) {
-            double t = S[(size_t)a * n + i] - c[a];
-            for (int b = 0; b < a; ++b) t = fma(-S[(size_t)b * n + i], G[b * R + a], t);
-            S[(size_t)a * n + i] = t;
-        }
-    }
-}
-
-cudaError_t launch_score_recurrence(double* S, long long n, int R, const double* c, const double* G, cudaStream_t s) {
-    const int blocks = (int)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
-    launch_k(score_recurrence_kernel, dim3(blocks), dim3(256), 0, s, S, n, R, c, G);
     return cudaGetLastError();
 }
 

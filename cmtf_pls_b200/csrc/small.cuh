@@ -79,9 +79,6 @@ cudaError_t launch_reduce_q_stop(const double* part, int n_parts, int stride, do
                                  double* qvec, const double* gram, double* q_prev, Ctrl* ctrl, const LoopEnd& e,
                                  cudaStream_t s);
 
-// out[0] = sum parts[0..n)
-cudaError_t launch_sum_small(const double* parts, int n, double* out, const Ctrl* ctrl, int trip, cudaStream_t s);
-
 // stop test of tpls.py:103 on d2 = sum parts (more than kMaxFusedResp responses: explicit ||u_old - u_new||^2)
 cudaError_t launch_stop(Ctrl* ctrl, const double* parts, int n, const LoopEnd& e, cudaStream_t s);
 cudaError_t launch_reset_ctrl(Ctrl* ctrl, cudaStream_t s);
@@ -120,12 +117,6 @@ cudaError_t launch_gram_rows(const double* y, long long n, int pitch, int m, dou
 
 // z[c] = cnt[c] > 0 ? z[c] / cnt[c] * n_total : 0     (missingvals.py:18)
 cudaError_t launch_count_rescale(double* z, const double* cnt, double n_total, int p, cudaStream_t s);
-
-// flag |= 1 when some row has fewer than p observed entries
-cudaError_t launch_rows_complete(const double* rowcnt, long long n, double p, int* flag, cudaStream_t s);
-
-// in place on the column-major scores S (n x R): t_a = r_a - c[a] - sum_{b<a} t_b * G[b*R + a]
-cudaError_t launch_score_recurrence(double* S, long long n, int R, const double* c, const double* G, cudaStream_t s);
 
 // dst[i] = (double)src[i], src in the storage type
 cudaError_t launch_widen(int dtype, const void* src, double* dst, int n, cudaStream_t s);

@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cmtf_pls_b200", "libtpls_b200.so")
-COLS = ["UBLKCP", "SYNCS", "LDS", "STS", "F2F", "DFMA", "DMUL+DADD", "SHFL", "BAR", "LD/LDG", "ST/STG", "LDL/STL"]
+COLS = ["UBLKCP", "SYNCS", "LDS", "STS", "F2F", "DFMA", "DMMA", "DMUL+DADD", "SHFL", "BAR", "LD/LDG", "ST/STG", "LDL/STL"]
 
 
 def main():
@@ -36,6 +36,8 @@ def main():
             c["UBLKCP"] += 1
         elif base == "SYNCS":
             c["SYNCS"] += 1
+        elif base == "DMMA":
+            c["DMMA"] += 1
         elif base == "LDS":
             c["LDS"] += 1
         elif base == "STS":
