@@ -93,13 +93,12 @@ __global__ void __launch_bounds__(kThreads, 2) covpass_kernel(const __grid_const
         if (threadIdx.x == kConsumers) {
             // producer: the X tile (contiguous, or one row segment per row) and the matching rows of Y
             const XT* x = reinterpret_cast<const XT*>(a.x_in);
-            long long it = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int s = (int)(it % g.stages);
-                const uint32_t ph = (uint32_t)((it / g.stages) & 1);
-                if (it >= g.stages) mbar_wait(&empty[s], ph ^ 1u);
+            RingPos rp;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, rp.advance(g.stages)) {
+                const int s = rp.idx;
+                if (rp.wrapped) mbar_wait(&empty[s], rp.phase ^ 1u);
                 const long long r0 = tile * g.tile_rows;
-                const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+                const int rows = tile_rows_of(g, tile, n_tiles);
                 XT* dst = tiles + s * stage_elems;
                 const XT* src = x + r0 * g.pitch + c0;
                 const uint32_t ybytes = (uint32_t)((size_t)rows * a.pitch_y * sizeof(double));
@@ -136,13 +135,12 @@ __global__ void __launch_bounds__(kThreads, 2) covpass_kernel(const __grid_const
     XT* xo = reinterpret_cast<XT*>(a.x_out);
     const double p_total = (double)g.p;
 
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = (int)(it % g.stages);
-        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+    RingPos rp;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, rp.advance(g.stages)) {
+        const int s = rp.idx;
         const long long r0 = tile * g.tile_rows;
-        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
-        mbar_wait(&full[s], ph);
+        const int rows = tile_rows_of(g, tile, n_tiles);
+        mbar_wait(&full[s], rp.phase);
         const XT* tp = tiles + s * stage_elems;
         const double* yp = ytiles + s * ystage;
         if (cvalid) {

@@ -119,15 +119,27 @@ cudaEvent_t prof_event(tpls_handle h) {
 // microseconds each, so they are made when the profile is asked for, not inside the fit).
 void prof_collect(tpls_handle h) {
     h->prof_sum = tpls_profile{};
+    // TPLS_PROFILE_TRACE=<file>: one line "class ms bytes" per profiled launch, in launch order (tools/trace_classes.py)
+    const char* trace_path = getenv("TPLS_PROFILE_TRACE");
+    FILE* trace = (trace_path != nullptr && *trace_path) ? fopen(trace_path, "a") : nullptr;
     for (auto& r : h->prof) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.a, r.b);
+        if (trace != nullptr) fprintf(trace, "%d %.6f %.0f\n", r.cls, ms, r.bytes);
+        // A streaming launch that "moved" its bytes faster than 20 TB/s did not run: the host-enqueued loop works one
+        // trip ahead of the stop flag, so the last trip of a component is followed by kernels that return at once
+        // (trip_is_dead).  They must not count as launches or bytes of their class -- in round 1 and early round 2
+        // they did, which overstated the per-class rates by the share of dead launches (one trip in ~17).
+        const bool dead = r.bytes > 0.0 && r.bytes > 20e12 * (double)ms * 1e-3;
         h->prof_sum.ms[r.cls] += ms;
-        h->prof_sum.launches[r.cls] += 1;
-        h->prof_sum.bytes[r.cls] += r.bytes;
+        if (!dead) {
+            h->prof_sum.launches[r.cls] += 1;
+            h->prof_sum.bytes[r.cls] += r.bytes;
+        }
         h->ev_pool.push_back(r.a);
         h->ev_pool.push_back(r.b);
     }
+    if (trace != nullptr) fclose(trace);
     h->prof.clear();
 }
 
@@ -226,6 +238,10 @@ int col_pass(tpls_handle h, int dtype, bool masked, int flags, ColPassArgs& a, i
 // mode: 0 dense, 1 masked with known row counts (a.rowcnt), 2 masked and counting (fills a.rowcnt)
 int row_pass(tpls_handle h, int dtype, int mode, RowPassArgs& a, int cls) {
     const double bytes = (double)a.g.n_rows * a.g.pitch * a.g.elem_size;
+    {
+        int ex = 0;
+        a.inv_div = (a.div > 0.0 && std::frexp(a.div, &ex) == 0.5) ? 1.0 / a.div : 0.0;  // exact only for powers of two
+    }
     ProfScope ps(h, cls, bytes);
     CK(launch_rowpass(dtype, mode, a, h->stream));
     h->stats.kernel_launches++;

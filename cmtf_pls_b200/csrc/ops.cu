@@ -40,6 +40,18 @@ int tpls_op_contract(tpls_handle h, const void* x, int dtype, int64_t n, int64_t
     const int elem = dtype == TPLS_F32 ? 4 : 8;
     PassGeom g = make_geom(n, (int)p, (int)p, elem, h->sm_count);
     double *zpart = nullptr, *cntpart = nullptr, *cnt = nullptr;
+#ifdef TPLS_PROBE
+    // TPLS_DBG & 64: the contraction as the fit runs it -- u[row] = Y[row,:] . q from rows of Y staged beside the X tiles
+    double *fake_y = nullptr, *fake_q = nullptr;
+    const bool y_variant = (tpls::tune_env("TPLS_DBG", 0) & 64) != 0;
+    if (y_variant) {
+        g = make_geom(n, (int)p, (int)p, elem, h->sm_count, 32);
+        CK(cudaMalloc((void**)&fake_y, sizeof(double) * n * 4));
+        CK(cudaMalloc((void**)&fake_q, sizeof(double) * 8));
+        CK(cudaMemset(fake_y, 0, sizeof(double) * n * 4));
+        CK(cudaMemset(fake_q, 0, sizeof(double) * 8));
+    }
+#endif
     CK(cudaMalloc((void**)&zpart, sizeof(double) * g.grid_x * p));
     CK(cudaMalloc((void**)&cntpart, sizeof(double) * g.grid_x * p));
     CK(cudaMalloc((void**)&cnt, sizeof(double) * p));
@@ -60,6 +72,13 @@ int tpls_op_contract(tpls_handle h, const void* x, int dtype, int64_t n, int64_t
             c.x_in = x;
             c.row_u = u;
             c.zpart = zpart;
+#ifdef TPLS_PROBE
+            if (y_variant) {
+                c.y = fake_y;
+                c.q = fake_q;
+                c.pitch_y = 4;
+            }
+#endif
             TRY(col_pass(h, dtype, masked != 0, PF_CONTRACT, c));
             return reduce_cols(h, zpart, z_out, (int)p, (int)p, g.grid_x, nullptr, nullptr, 0, nullptr, 0);
         });
@@ -72,6 +91,10 @@ int tpls_op_contract(tpls_handle h, const void* x, int dtype, int64_t n, int64_t
     cudaFree(zpart);
     cudaFree(cntpart);
     cudaFree(cnt);
+#ifdef TPLS_PROBE
+    cudaFree(fake_y);
+    cudaFree(fake_q);
+#endif
     return rc;
 }
 

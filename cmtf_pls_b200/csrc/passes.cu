@@ -55,6 +55,9 @@ PassGeom make_geom(long long n_rows, int p, int pitch, int elem_size, int sm_cou
     const long long n_tiles = (n_rows + tr - 1) / tr;
     const long long want = std::max(1, (sm_count * tune_env("TPLS_CTAS_PER_SM", 2)) / g.n_slabs);
     g.grid_x = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
+#ifdef TPLS_PROBE
+    g.dbg = tune_env("TPLS_DBG", 0);
+#endif
     return g;
 }
 
@@ -147,14 +150,17 @@ __global__ void __launch_bounds__(kThreads, 2) colpass_kernel(const __grid_const
     int nmiss = 0;  // COLSTAT: unobserved entries seen by this thread, whatever the row weights
 
     XT* xo = reinterpret_cast<XT*>(a.x_out);
+    const TileWalk tw = tile_walk(g);
     const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = (int)(it % g.stages);
-        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+    RingPos rp;
+    for (long long tile = tw.first; tile < tw.end; tile += tw.step, rp.advance(g.stages)) {
+        const int s = rp.idx;
         const long long r0 = tile * g.tile_rows;
-        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
-        mbar_wait(&full[s], ph);
+        int rows = tile_rows_of(g, tile, n_tiles);
+        mbar_wait(&full[s], rp.phase);
+#ifdef TPLS_PROBE
+        if (g.dbg & 16) rows = 0;  // data movement only
+#endif
         const XT* tp = tiles + s * stage_elems;
         const double* yp = ytiles + s * ystage;
         for (int r = rl; r < rows; r += rpt) {
@@ -417,7 +423,10 @@ cudaError_t launch_row_finish(const RowFinishArgs& a, int* grid_out, cudaStream_
 template <typename XT, int CPT, bool MASKED, int FLAGS, bool FULL>
 static cudaError_t run_colpass_impl(const ColPassArgs& a, cudaStream_t s) {
     auto kern = colpass_kernel<XT, CPT, MASKED, FLAGS, FULL>;
-    const size_t smem = colpass_smem(a.g, ((FLAGS & PF_CONTRACT) && a.y != nullptr) ? a.pitch_y : 0);
+    size_t smem = colpass_smem(a.g, ((FLAGS & PF_CONTRACT) && a.y != nullptr) ? a.pitch_y : 0);
+#ifdef TPLS_PROBE
+    smem += (size_t)tune_env("TPLS_DBG_COLPAD_KB", 0) * 1024;  // unused tail: does the footprint alone matter?
+#endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);

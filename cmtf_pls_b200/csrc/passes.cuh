@@ -48,6 +48,7 @@ struct PassGeom {
     int stages;
     int grid_x;     // CTAs along the row-tile axis
     int elem_size;  // 4 or 8
+    int dbg;        // probe builds only (-DTPLS_PROBE, tools/probe_build.sh): experiment switches from TPLS_DBG; 0 otherwise
 };
 
 // Chooses slab width, thread layout, tile size and grid for a shard.  y_row_bytes > 0: contractions over this
@@ -88,6 +89,7 @@ struct RowPassArgs {
     double* rowcnt;         // masked: [n_rows] observed entries per row (read in mode 1, written in mode 2)
     int epi;                // 0: t = v   1: t += v   2: t = (t + v) / div
     double div;
+    double inv_div;         // 1 / div when that is exact (div a power of two: the product rounds like the quotient), else 0
     double* d2part;         // optional [grid_x]: sum over rows of (t_old - t_new)^2
     const double* y;        // optional (with qpart): responses [n_rows][pitch_y], pitch_y <= kMaxFusedResp
     int pitch_y;

@@ -20,6 +20,9 @@ namespace tpls {
 
 constexpr int kRowThreads = kConsumers + 64;
 constexpr int kSlots = 3;
+#ifndef TPLS_RP_RPI
+#define TPLS_RP_RPI 1   // row iterations whose loads are issued together when a thread owns more than 8 elements of a row
+#endif
 
 static int pow2_ceil_i(int v) {
     int p = 1;
@@ -66,12 +69,18 @@ PassGeom make_row_geom(long long n_rows, int p, int pitch, int elem_size, int sm
     tr = std::min<long long>(tr, std::max<long long>(1, n_rows));
     tr = std::min<long long>(tr, 4096);
     g.tile_rows = (int)tr;
+#ifdef TPLS_PROBE
+    g.dbg = tune_env("TPLS_DBG", 0);
+#endif
     const size_t slots = kSlots * row_slot_doubles(g, masked) * sizeof(double);
     const long long stage = (long long)row_stage_bytes(g);
     g.stages = (int)std::max<long long>(2, std::min<long long>(kMaxStages, ((long long)budget - (long long)slots) / stage));
     const long long n_tiles = (n_rows + tr - 1) / tr;
     const long long want = std::max(1, (sm_count * tune_env("TPLS_CTAS_PER_SM", 2)) / g.n_slabs);
     g.grid_x = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
+#ifdef TPLS_PROBE
+    g.dbg = tune_env("TPLS_DBG", 0);
+#endif
     return g;
 }
 
@@ -86,7 +95,10 @@ __device__ __forceinline__ double row_epilogue(const RowPassArgs& a, long long g
     double* tp = a.t_out + grow;
     double nv = v;
     if (a.epi == 1) nv = old + v;
-    if (a.epi == 2) nv = (old + v) / a.div;
+    if (a.epi == 2) nv = a.inv_div != 0.0 ? (old + v) * a.inv_div : (old + v) / a.div;
+#ifdef TPLS_PROBE
+    if (!(a.g.dbg & 1) || nv == 1.2345e301)
+#endif
     *tp = nv;
     if (a.d2part != nullptr) {
         const double d = old - nv;
@@ -157,20 +169,33 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     }
     __syncthreads();
 
+    const TileWalk tw = tile_walk(g);
     const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
     const int tid = threadIdx.x;
+#ifdef TPLS_PROBE
+    const int dbg = g.dbg;  // 1: no store of t   2: reducer skips its fold   4: no slot ring   8: contiguous tile runs   16: no compute
+#else
+    constexpr int dbg = 0;
+#endif
     const int lane = tid & 31;
 
     // ------------------------------------------------------------------ producer
     if (tid >= kConsumers && tid < kConsumers + 32) {
-        if (tid == kConsumers)
+        if (tid == kConsumers) {
+#ifdef TPLS_PROBE
+            if (dbg & 32)  // a second, tiny bulk copy per tile (as the column pass has with the rows of Y): does it matter?
+                produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow,
+                                  reinterpret_cast<const double*>(a.x_in), 4, slots + (size_t)kSlots * slot_doubles);
+            else
+#endif
             produce_tiles<XT>(g, reinterpret_cast<const XT*>(a.x_in), tiles, full, empty, c0, slab_cols, srow);
+        }
         return;
     }
 
     // ------------------------------------------------------------------ reducer
     if (tid >= kConsumers + 32) {
-        if (!use_slots) return;
+        if (!use_slots || (dbg & 4)) return;
         // G lanes cooperate on one row; 32/G rows per round
         int G = 32;
         while (G > 1 && (32 / G) * 2 <= g.tile_rows) G >>= 1;  // as many rows per round as the tile has
@@ -183,17 +208,21 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         double qacc[kMaxFusedResp], y_pf[kMaxFusedResp];
 #pragma unroll
         for (int m = 0; m < kMaxFusedResp; ++m) qacc[m] = y_pf[m] = 0.0;
-        long long it = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int sl = (int)(it % kSlots);
-            const uint32_t ph = (uint32_t)((it / kSlots) & 1);
+        RingPos sp_pos;
+        for (long long tile = tw.first; tile < tw.end; tile += tw.step, sp_pos.advance(kSlots)) {
+            const int sl = sp_pos.idx;
+            const uint32_t ph = sp_pos.phase;
             const long long r0 = tile * g.tile_rows;
-            const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+            int rows = tile_rows_of(g, tile, n_tiles);
+            if (dbg & (2 | 16)) rows = 0;
             // what the first round's epilogue reads from global memory is requested BEFORE the wait, so that
             // its latency (microseconds while the HBM is saturated) overlaps the consumers' work on the tile
             double old_pf = 0.0, cnt_pf = 1.0;
             if (gl == 0 && rg < rows && !slabbed) {
-                if (need_old) old_pf = a.t_out[r0 + rg];
+                // (t is read before it is written even when the epilogue does not use the old value: measured on
+                //  several B200s the first projection of a trip, whose stores missed in L2, took 2.50 ms per 16.4 GB
+                //  and 2.23 ms with this load in front of the store; on other boxes it made no difference)
+                asm volatile("ld.global.f64 %0, [%1];" : "=d"(old_pf) : "l"(a.t_out + r0 + rg));
                 if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + rg];
                 if (want_q) load_y_row(a, r0 + rg, y_pf);
             }
@@ -290,89 +319,118 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
 #pragma unroll
     for (int m = 0; m < kMaxFusedResp; ++m) qacc[m] = 0.0;
 
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = (int)(it % g.stages);
-        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+    const bool ring = use_slots && !(dbg & 4);
+    RingPos st_pos, sl_pos;
+    for (long long tile = tw.first; tile < tw.end; tile += tw.step, st_pos.advance(g.stages), sl_pos.advance(kSlots)) {
+        const int s = st_pos.idx;
         const long long r0 = tile * g.tile_rows;
-        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
-        const int sl = (int)(it % kSlots);
+        int rows = tile_rows_of(g, tile, n_tiles);
+        if (dbg & 16) rows = 0;
+        const int sl = sl_pos.idx;
         double* sp = slots + (size_t)sl * slot_doubles;
         double* cp = sp + (size_t)g.tile_rows * lpr;
-        if (use_slots && it >= kSlots) mbar_wait(&red_empty[sl], (uint32_t)(((it / kSlots) - 1) & 1));
-        mbar_wait(&full[s], ph);
+        // the slot must have been folded by the reducer before it is written again.  (Waiting for it only right before
+        // the first partial of the tile is stored was measured too: 1769 against 1775-1784 ms per fit, within the noise.)
+        if (ring && sl_pos.wrapped) mbar_wait(&red_empty[sl], sl_pos.phase ^ 1u);
+        mbar_wait(&full[s], st_pos.phase);
         const XT* tp = tiles + s * stage_elems;
-        // every lane of a row group walks the same number of rounds so that the shuffles stay converged
-        for (int rb = 0; rb < rows; rb += rpt) {
-            const int r = rb + rl;
-            const bool live = FULL ? true : (r < rows);
-            double v = 0.0, cnt = 0.0;
-            int icnt = 0;
-            if (live) {
-                // one accumulator per (column group, element): CPT * VEC independent chains instead of
-                // one chain of CPT * VEC dependent fp64 FMAs
-                double acc[CPT][VEC];
+        // every lane of a row group walks the same number of rounds so that the shuffles stay converged.
+        // The stage goes back to the producer as soon as the LAST rows of the tile sit in registers, before their
+        // arithmetic: what a consumer holds a stage for is then loads only, as in the column pass.  RPI row iterations
+        // are loaded together (two when a thread owns at most 8 elements of a row; for 16 elements two were measured
+        // slower inside the fit: 1814 against 1775 ms).
+        constexpr int RPI = (CPT * VEC <= 8) ? 2 : TPLS_RP_RPI;
+        bool released = false;
+        for (int rb = 0; rb < rows; rb += rpt * RPI) {
+            Pack<XT> in[RPI][CPT];
+            bool live[RPI];
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) {
+            for (int i = 0; i < RPI; ++i) {
+                const int r = rb + i * rpt + rl;
+                live[i] = r < rows;
+                if (live[i]) {
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) acc[k][j] = 0.0;
-                    if (!FULL && !cvalid[k]) continue;
-                    const int cg = cl + k * lpr;
-                    Pack<XT> in;
-                    in.v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const XT xs = in.e[j];
-                        if (MASKED) {
-                            const bool ob = (xs == xs);
-                            const XT xc = ob ? xs : (XT)0;  // select in the storage type, convert once
-                            acc[k][j] = (double)xc * wreg[k][j];
-                            if (COUNT) icnt += ob ? 1 : 0;
-                        } else {
-                            acc[k][j] = (double)xs * wreg[k][j];
-                        }
+                    for (int k = 0; k < CPT; ++k) {
+                        if (!FULL && !cvalid[k]) continue;
+                        const int cg = cl + k * lpr;
+                        in[i][k].v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
                     }
                 }
-                // fixed-shape tree
-#pragma unroll
-                for (int k = 0; k < CPT; ++k) {
-                    double t = acc[k][0];
-#pragma unroll
-                    for (int j = 1; j < VEC; ++j) t += acc[k][j];
-                    v += t;
-                }
             }
-            if (COUNT) cnt = (double)icnt;
-            if (use_slots) {
-                if (live) {
-                    sp[(size_t)r * lpr + cl] = v;
-                    if (COUNT) cp[(size_t)r * lpr + cl] = cnt;
-                }
-            } else {
-                for (int m = lpr >> 1; m >= 1; m >>= 1) {
-                    v += shfl_xor_d(v, m);
-                    if (COUNT) cnt += shfl_xor_d(cnt, m);
-                }
-                if (live && cl == 0) {
-                    const long long grow = r0 + r;
-                    if (slabbed) {
-                        a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
-                        if (COUNT) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
-                    } else {
-                        if (MASKED) {
-                            if (COUNT) {
-                                cnt -= pads;
-                                if (a.rowcnt != nullptr) a.rowcnt[grow] = cnt;
+            if (rb + rpt * RPI >= rows) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                released = true;
+            }
+#pragma unroll
+            for (int i = 0; i < RPI; ++i) {
+                const int r = rb + i * rpt + rl;
+                if (RPI > 1 && rb + i * rpt >= rows) break;  // (uniform over the warp)
+                double v = 0.0, cnt = 0.0;
+                int icnt = 0;
+                if (live[i]) {
+                    // one accumulator per (column group, element): CPT * VEC independent chains instead of
+                    // one chain of CPT * VEC dependent fp64 FMAs
+                    double acc[CPT][VEC];
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) acc[k][j] = 0.0;
+                        if (!FULL && !cvalid[k]) continue;
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) {
+                            const XT xs = in[i][k].e[j];
+                            if (MASKED) {
+                                const bool ob = (xs == xs);
+                                const XT xc = ob ? xs : (XT)0;  // select in the storage type, convert once
+                                acc[k][j] = (double)xc * wreg[k][j];
+                                if (COUNT) icnt += ob ? 1 : 0;
                             } else {
-                                cnt = a.rowcnt[grow];
+                                acc[k][j] = (double)xs * wreg[k][j];
                             }
-                            v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        const double nv = row_epilogue(a, grow, v, epilogue_needs_old(a) ? a.t_out[grow] : 0.0, d2);
-                        if (want_q) {
-                            double yv[kMaxFusedResp];
-                            load_y_row(a, grow, yv);
-                            q_accumulate(qacc, yv, nv);
+                    }
+                    // fixed-shape tree
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) {
+                        double t = acc[k][0];
+#pragma unroll
+                        for (int j = 1; j < VEC; ++j) t += acc[k][j];
+                        v += t;
+                    }
+                }
+                if (COUNT) cnt = (double)icnt;
+                if (use_slots) {
+                    if (live[i] && (ring || v == 1.2345e301)) {
+                        sp[(size_t)r * lpr + cl] = v;
+                        if (COUNT) cp[(size_t)r * lpr + cl] = cnt;
+                    }
+                } else {
+                    for (int m = lpr >> 1; m >= 1; m >>= 1) {
+                        v += shfl_xor_d(v, m);
+                        if (COUNT) cnt += shfl_xor_d(cnt, m);
+                    }
+                    if (live[i] && cl == 0) {
+                        const long long grow = r0 + r;
+                        if (slabbed) {
+                            a.tpart[(size_t)blockIdx.y * g.n_rows + grow] = v;
+                            if (COUNT) a.cpart[(size_t)blockIdx.y * g.n_rows + grow] = cnt;
+                        } else {
+                            if (MASKED) {
+                                if (COUNT) {
+                                    cnt -= pads;
+                                    if (a.rowcnt != nullptr) a.rowcnt[grow] = cnt;
+                                } else {
+                                    cnt = a.rowcnt[grow];
+                                }
+                                v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
+                            }
+                            const double nv = row_epilogue(a, grow, v, epilogue_needs_old(a) ? a.t_out[grow] : 0.0, d2);
+                            if (want_q) {
+                                double yv[kMaxFusedResp];
+                                load_y_row(a, grow, yv);
+                                q_accumulate(qacc, yv, nv);
+                            }
                         }
                     }
                 }
@@ -380,8 +438,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
         }
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&empty[s]);
-            if (use_slots) mbar_arrive(&red_full[sl]);
+            if (!released) mbar_arrive(&empty[s]);
+            if (ring) mbar_arrive(&red_full[sl]);
         }
     }
 
@@ -424,7 +482,11 @@ static cudaError_t run_rowpass_impl(const RowPassArgs& a, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.g.grid_x, a.g.n_slabs);
-    launch_k(kern, dim3(grid), dim3(kRowThreads), smem, s, a);
+    int threads = kRowThreads;
+#ifdef TPLS_PROBE
+    if (a.g.dbg & 4) threads -= 32;  // no slot ring: no reducer warp either
+#endif
+    launch_k(kern, dim3(grid), dim3(threads), smem, s, a);
     return cudaGetLastError();
 }
 

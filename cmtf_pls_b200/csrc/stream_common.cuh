@@ -24,6 +24,46 @@ union Pack {
     XT e[VecOf<XT>::N];
 };
 
+// Which tiles a CTA walks: tile = first, first + step, ... < end.  Normal builds interleave the CTAs (tile = blockIdx.x + k *
+// gridDim.x); probe builds (TPLS_DBG & 8) can give every CTA one contiguous run of tiles instead.
+struct TileWalk {
+    long long first, end, step;
+};
+__device__ __forceinline__ TileWalk tile_walk(const PassGeom& g) {
+    const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
+    TileWalk w{(long long)blockIdx.x, n_tiles, (long long)gridDim.x};
+#ifdef TPLS_PROBE
+    if (g.dbg & 8) {
+        const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
+        w.first = blockIdx.x * per;
+        w.end = min(n_tiles, w.first + per);
+        w.step = 1;
+    }
+#endif
+    return w;
+}
+
+// Position in a ring of n mbarrier-guarded buffers, advanced without the 64-bit division and modulo that
+// (iteration % n, iteration / n) cost once per tile and warp (they were a third of a consumer's instructions on 2-row tiles).
+struct RingPos {
+    int idx;         // buffer of the current iteration
+    uint32_t phase;  // parity of the number of completed trips around the ring
+    bool wrapped;    // at least one trip around the ring is complete (the buffer has been used before)
+    __device__ __forceinline__ RingPos() : idx(0), phase(0u), wrapped(false) {}
+    __device__ __forceinline__ void advance(int n) {
+        if (++idx == n) {
+            idx = 0;
+            phase ^= 1u;
+            wrapped = true;
+        }
+    }
+};
+
+// rows of tile `tile` (the last tile of a shard may be short)
+__device__ __forceinline__ int tile_rows_of(const PassGeom& g, long long tile, long long n_tiles) {
+    return tile == n_tiles - 1 ? (int)(g.n_rows - tile * g.tile_rows) : g.tile_rows;
+}
+
 // Producer: one elected lane streams this CTA's row tiles into the smem ring.  With `y` the matching rows of
 // Y (pitch_y doubles each, contiguous in memory) ride on the same barrier into ytiles[stage][tile_rows * pitch_y].
 template <typename XT>
@@ -31,16 +71,16 @@ __device__ __forceinline__ void produce_tiles(const PassGeom& g, const XT* __res
                                               uint64_t* empty, int c0, int slab_cols, int srow,
                                               const double* __restrict__ y = nullptr, int pitch_y = 0,
                                               double* ytiles = nullptr) {
+    const TileWalk tw = tile_walk(g);
     const long long n_tiles = (g.n_rows + g.tile_rows - 1) / g.tile_rows;
     const size_t stage_elems = (size_t)g.tile_rows * srow;
     const size_t ystage = (size_t)g.tile_rows * pitch_y;
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = (int)(it % g.stages);
-        const uint32_t ph = (uint32_t)((it / g.stages) & 1);
-        if (it >= g.stages) mbar_wait(&empty[s], ph ^ 1u);
+    RingPos rp;
+    for (long long tile = tw.first; tile < tw.end; tile += tw.step, rp.advance(g.stages)) {
+        const int s = rp.idx;
+        if (rp.wrapped) mbar_wait(&empty[s], rp.phase ^ 1u);
         const long long r0 = tile * g.tile_rows;
-        const int rows = (int)min((long long)g.tile_rows, g.n_rows - r0);
+        const int rows = tile_rows_of(g, tile, n_tiles);
         XT* dst = tiles + s * stage_elems;
         const XT* src = x + r0 * g.pitch + c0;
         const uint32_t ybytes = y != nullptr ? (uint32_t)((size_t)rows * pitch_y * sizeof(double)) : 0u;
