@@ -47,6 +47,7 @@ class Stats(C.Structure):
         ("xchg_count", C.c_int64),
         ("xchg_ms", C.c_double),
         ("xchg_wait_ms", C.c_double),
+        ("resident_loops", C.c_int64),
     ]
 
 

@@ -679,6 +679,9 @@ static int layout_fit(tpls_handle h, int L, int R) {
     TRY(dev_alloc(h, (void**)&h->grampart, sizeof(double) * 148 * 64, tr));
     TRY(dev_alloc(h, (void**)&h->q_prev, sizeof(double) * 8, tr));
     TRY(dev_alloc(h, (void**)&h->qpart, sizeof(double) * 2048 * kMaxFusedResp, tr));
+    TRY(dev_alloc(h, (void**)&h->res_bar, sizeof(unsigned int) * 4, tr));  // (the slab is zeroed when it is laid out)
+    h->res_stamps = nullptr;
+    if (tune_env("TPLS_RESIDENT_STAMPS", 0)) TRY(dev_alloc(h, (void**)&h->res_stamps, sizeof(long long) * 16, tr));
     TRY(dev_alloc(h, (void**)&h->e0vec, sizeof(double) * kMaxFusedResp, tr));
     TRY(dev_alloc(h, (void**)&h->nloc, sizeof(double) * 2, tr));
     TRY(dev_alloc(h, (void**)&h->conv_dev, sizeof(int) * R, tr));
@@ -690,7 +693,8 @@ static int layout_fit(tpls_handle h, int L, int R) {
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
         const size_t gp = (size_t)t.g.grid_x * t.pitch;
-        TRY(dev_alloc(h, (void**)&t.zpart, sizeof(double) * gp, tr));
+        // (the resident trip loop writes one row of partials per CTA, one CTA per SM)
+        TRY(dev_alloc(h, (void**)&t.zpart, sizeof(double) * (size_t)std::max(t.g.grid_x, h->sm_count) * t.pitch, tr));
         TRY(dev_alloc(h, (void**)&t.cntpart, sizeof(double) * gp, tr));
         TRY(dev_alloc(h, (void**)&t.sspart, sizeof(double) * t.g.grid_x * t.g.n_slabs, tr));
         TRY(dev_alloc(h, (void**)&t.mean_d, sizeof(double) * t.pitch, tr));
@@ -1187,8 +1191,83 @@ static int trip_body(tpls_handle h, const StreamPlan& P, int a, unsigned long lo
     return 0;
 }
 
+// Can the inner trips of a component run in the resident loop kernel (rank1.cuh)?  One GPU, the Y side fused, rows
+// narrow enough for its thread layout, and a working set that stays in L2 (TPLS_RESIDENT_MB, default 80; the
+// streaming kernels win beyond that).  TPLS_RESIDENT=0 turns it off, =1 forces it whatever the size.  Profiled fits
+// keep the streaming kernels (their per-class timing is what the profile is for) unless forced.
+static int resident_ctas(tpls_handle h, const StreamPlan& P) {
+    const int force = tune_env("TPLS_RESIDENT", -1);
+    if (force == 0 || h->world > 1 || !P.fused || P.L > h->sm_count) return 0;
+    if (h->profile && force != 1) return 0;
+    double bytes = (double)h->n * h->pitch_y * 8.0;
+    for (int l = 0; l < P.L; ++l) {
+        const Tensor& t = h->x[l];
+        if (t.pitch / (16 / t.elem) > kRank1Threads * kResidentKc) return 0;
+        bytes += (double)h->n * t.pitch * t.elem;
+    }
+    if (force != 1 && bytes > 1048576.0 * tune_env("TPLS_RESIDENT_MB", 80)) return 0;
+    if (P.r1_use_smem && P.r1_smem > 200 * 1024) return 0;
+    const long long want = (h->n + 15) / 16;  // at least 16 samples per CTA
+    return (int)std::max<long long>(P.L, std::min<long long>(h->sm_count, want));
+}
+
+static int run_resident(tpls_handle h, const StreamPlan& P, int a, int n_ctas) {
+    ResidentArgs ra{};
+    ra.n_tensors = P.L;
+    ra.n_rows = h->n;
+    ra.y = h->y_work;
+    ra.pitch_y = h->pitch_y;
+    ra.m = h->m;
+    ra.t_out = h->T + (size_t)a * h->n;
+    ra.qpart = h->qpart;
+    ra.qcol = h->Q + (size_t)a * h->m;
+    ra.qvec = h->qvec;
+    ra.q_prev = h->q_prev;
+    ra.gram = h->arena + h->off_gram_y;
+    ra.ctrl = h->ctrl;
+    ra.tol = P.tol;
+    ra.max_iter = P.max_iter;
+    ra.normalize_on_break = (P.flags & TPLS_FIT_NORMALIZE_ON_BREAK) ? 1 : 0;
+    ra.r1_in_smem = P.r1_use_smem ? 1 : 0;
+    ra.bar = h->res_bar;
+    ra.stamps = h->res_stamps;
+    double bytes = 0.0;
+    for (int l = 0; l < P.L; ++l) {
+        Tensor& t = h->x[l];
+        ResidentTensor& X = ra.x[l];
+        X.x = t.work;
+        X.dtype = t.dtype;
+        X.p = t.p;
+        X.pitch = t.pitch;
+        X.masked = t.masked ? 1 : 0;
+        X.rowcnt = t.rowcnt;
+        X.zpart = t.zpart;
+        X.parts0 = t.g.grid_x;
+        X.z = h->arena + t.off_z;
+        X.wkron = t.wkron + (size_t)a * t.pitch;
+        fill_rank1_task(h, t, a, ra.r1[l], P.r1_use_smem);
+        bytes += (double)h->n * t.pitch * t.elem;
+    }
+    tpls_ctx::BodyCount& bc = h->body[a];
+    bc = tpls_ctx::BodyCount{};
+    {
+        ProfScope ps(h, TPLS_K_OTHER, 0.0);
+        CK(launch_resident_loop(ra, n_ctas, P.r1_use_smem ? P.r1_smem : 0, h->stream));
+    }
+    h->stats.kernel_launches++;
+    h->stats.resident_loops++;
+    // per trip: one projection and one contraction over every tensor; the last trip has no contraction
+    h->stats.streamed_bytes += 2.0 * bytes;
+    bc.streamed = 2.0 * bytes;
+    bc.tail_streamed = bytes;
+    bc.enqueued = 1;
+    bc.resident = true;
+    return 0;
+}
+
 // runs the trip body until the stop flag is up: a WHILE node while capturing, host-driven otherwise
 static int run_loop(tpls_handle h, const StreamPlan& P, int a) {
+    if (const int n_ctas = resident_ctas(h, P)) return run_resident(h, P, a, n_ctas);
     tpls_ctx::BodyCount& bc = h->body[a];
     bc = tpls_ctx::BodyCount{};
     const tpls_stats before = h->stats;
@@ -1346,6 +1425,8 @@ static unsigned long long graph_key_of(tpls_handle h, int L, int R, double tol, 
     KEY(h->y_src); KEY(h->y_work); KEY(h->row_w); KEY(h->slab); KEY(h->slab_need);
     const bool pdl = pdl_enabled();
     KEY(pdl);
+    const int res_switch = tune_env("TPLS_RESIDENT", -1), res_mb = tune_env("TPLS_RESIDENT_MB", 80);  // resident_ctas()
+    KEY(res_switch); KEY(res_mb);
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
         KEY(t.src); KEY(t.work); KEY(t.dtype); KEY(t.ndim); KEY(t.masked);
@@ -1563,6 +1644,7 @@ int tpls_fit(tpls_handle h, int n_tensors, int n_components, double tol, int max
             h->stats.kernel_launches = pre.kernel_launches + h->g_static.kernel_launches;
             h->stats.collectives = pre.collectives + h->g_static.collectives;
             h->stats.streamed_bytes = pre.streamed_bytes + h->g_static.streamed_bytes;
+            h->stats.resident_loops = h->g_static.resident_loops;
         }
         CK(cudaGraphLaunch(h->graph_exec, st));
         h->stats.graph_launches = 1;
@@ -1609,12 +1691,23 @@ loops_done:
     long long total = 0;
     for (int a = 0; a < R; ++a) total += h->trips[a];
     h->stats.total_trips = total;
+    if (h->res_stamps != nullptr && h->stats.resident_loops > 0) {
+        long long hs[16];
+        CK(cudaMemcpy(hs, h->res_stamps, sizeof hs, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(h->res_stamps, 0, sizeof hs));
+        const double tr = (double)std::max<long long>(1, hs[9]);
+        fprintf(stderr,
+                "resident loop, us per trip (CTA 0, %lld trips): fold %.2f  rank-1 %.2f  projection %.2f  q/stop %.2f  "
+                "contraction %.2f | barriers %.2f %.2f %.2f %.2f\n",
+                hs[9], hs[0] / tr * 1e-3, hs[1] / tr * 1e-3, hs[2] / tr * 1e-3, hs[3] / tr * 1e-3, hs[4] / tr * 1e-3,
+                hs[5] / tr * 1e-3, hs[6] / tr * 1e-3, hs[7] / tr * 1e-3, hs[8] / tr * 1e-3);
+    }
     // launches / collectives / streamed bytes of the loops: one body was counted per component
     if (!cov_mode) {
         int per_trip = 0;
         for (int a = 0; a < R; ++a) {
             const tpls_ctx::BodyCount& b = h->body[a];
-            const long long runs = use_graph ? h->trips[a] : b.enqueued;
+            const long long runs = b.resident ? 1 : (use_graph ? h->trips[a] : b.enqueued);
             h->stats.kernel_launches += b.launches * (runs - 1);
             h->stats.collectives += b.collectives * (runs - 1);
             h->stats.streamed_bytes += b.streamed * (h->trips[a] - 1) - b.tail_streamed;

@@ -128,6 +128,8 @@ struct tpls_ctx {
     size_t off_cov = 0, cov_len = 0, off_gram_y = 0;
     double *grampart = nullptr, *q_prev = nullptr;
     double *qpart = nullptr, *e0vec = nullptr, *nloc = nullptr;
+    unsigned int* res_bar = nullptr;  // grid barrier of the resident trip loop (rank1.cuh)
+    long long* res_stamps = nullptr;  // its per-phase diagnostics (TPLS_RESIDENT_STAMPS=1), else nullptr
     size_t off_nmiss = 0;
     int* conv_dev = nullptr;
     std::vector<int> converged;
@@ -144,6 +146,7 @@ struct tpls_ctx {
     struct BodyCount {
         long long launches = 0, collectives = 0, enqueued = 0;
         double streamed = 0, tail_streamed = 0;
+        bool resident = false;  // the component's trips ran in one resident-loop launch
     };
     BodyCount body[32], g_body[32];
     tpls_stats g_static{};  // launches / collectives / bytes of one pass through the captured graph

@@ -22,6 +22,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace tpls {
 
@@ -856,6 +857,416 @@ __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid
     cluster.sync();  // no CTA may exit while a peer can still store into its shared memory
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Resident trip loop (rank1.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr size_t kResidentScratch = 20 * 1024;  // bytes of dynamic shared memory the non-rank-1 phases use
+
+// Grid-wide barrier of co-resident CTAs (one per SM): arrivals counter + generation word in global memory.
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int gen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+        __threadfence();
+        if (atomicAdd(bar, 1u) == n_ctas - 1) {
+            bar[0] = 0u;
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1u) : "memory");
+        } else {
+            unsigned int g2;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 1) : "memory");
+            } while (g2 == gen);
+        }
+    }
+    __syncthreads();
+}
+
+template <typename XT>
+struct RVec;
+template <>
+struct RVec<float> {
+    using type = float4;
+    static constexpr int N = 4;
+};
+template <>
+struct RVec<double> {
+    using type = double2;
+    static constexpr int N = 2;
+};
+template <typename XT>
+union RPack {
+    typename RVec<XT>::type v;
+    XT e[RVec<XT>::N];
+};
+
+// NR rows of X times kron(w) at once: the lanes of a warp stride over the 16-byte column groups and keep 2 * NR loads
+// in flight (the data sits in L2: a load costs its latency, not its bytes); results in every lane.  Rows past the
+// end of the CTA's block repeat the last valid row (their results are ignored by the caller).
+template <typename XT, int NR>
+__device__ __forceinline__ void resident_row_dots(const XT* __restrict__ x, const long long (&rows)[NR], int pitch,
+                                                  const double* __restrict__ wk, bool masked, int lane, double (&out)[NR]) {
+    constexpr int VEC = RVec<XT>::N;
+    using V = typename RVec<XT>::type;
+    double acc[NR][2];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i][0] = acc[i][1] = 0.0;
+    int c = lane * VEC;
+    for (; c + 32 * VEC < pitch; c += 2 * 32 * VEC) {
+        RPack<XT> in[NR][2];
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) in[i][h].v = __ldcg(reinterpret_cast<const V*>(x + rows[i] * pitch + c + h * 32 * VEC));
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const double w = __ldg(wk + c + h * 32 * VEC + j);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    XT xs = in[i][h].e[j];
+                    if (masked && !(xs == xs)) xs = (XT)0;
+                    acc[i][j & 1] = fma((double)xs, w, acc[i][j & 1]);
+                }
+            }
+    }
+    for (; c < pitch; c += 32 * VEC) {
+        RPack<XT> in[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) in[i].v = __ldcg(reinterpret_cast<const V*>(x + rows[i] * pitch + c));
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const double w = __ldg(wk + c + j);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                XT xs = in[i].e[j];
+                if (masked && !(xs == xs)) xs = (XT)0;
+                acc[i][j & 1] = fma((double)xs, w, acc[i][j & 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) out[i] = acc[i][0] + acc[i][1];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1)
+#pragma unroll
+        for (int i = 0; i < NR; ++i) out[i] += __shfl_xor_sync(0xffffffffu, out[i], m);
+}
+
+// Z partials of this CTA's rows for one tensor: zpart_row[c] = sum_r x[r, c] * u[r], u[r] = Y[r,:] . q
+template <typename XT, int KC>
+__device__ __forceinline__ void resident_contract_kc(const ResidentTensor& X, const double* __restrict__ y, int pitch_y, int m,
+                                                  const double* q_s, long long r_lo, long long r_hi, double* zrow, double* scr) {
+    constexpr int VEC = RVec<XT>::N;
+    const XT* x = reinterpret_cast<const XT*>(X.x);
+    const int n_cg = X.pitch / VEC;
+    int lpr = 1;
+    while (lpr < n_cg && lpr < NTH) lpr <<= 1;
+    const int rpt = NTH / lpr;
+    const int cl = threadIdx.x & (lpr - 1), rl = threadIdx.x / lpr;
+    const bool masked = X.masked != 0;
+    double zacc[KC][VEC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) zacc[k][j] = 0.0;
+    using V = typename RVec<XT>::type;
+    constexpr int RU = KC <= 2 ? 8 : 4;  // rows in flight per thread: the loads of a group are issued before any of them is used
+    long long r = r_lo + rl;
+    for (; r + (long long)(RU - 1) * rpt < r_hi; r += (long long)RU * rpt) {
+        double u[RU];
+#pragma unroll
+        for (int i = 0; i < RU; ++i) {
+            u[i] = 0.0;
+            for (int q = 0; q < m; ++q) u[i] = fma(__ldg(y + (r + (long long)i * rpt) * pitch_y + q), q_s[q], u[i]);
+        }
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const int cg = cl + k * lpr;
+            if (cg < n_cg) {
+                RPack<XT> in[RU];
+#pragma unroll
+                for (int i = 0; i < RU; ++i)
+                    in[i].v = __ldcg(reinterpret_cast<const V*>(x + (r + (long long)i * rpt) * X.pitch + cg * VEC));
+#pragma unroll
+                for (int i = 0; i < RU; ++i)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        XT xs = in[i].e[j];
+                        if (masked && !(xs == xs)) xs = (XT)0;
+                        zacc[k][j] = fma((double)xs, u[i], zacc[k][j]);
+                    }
+            }
+        }
+    }
+    for (; r < r_hi; r += rpt) {
+        double u = 0.0;
+        for (int q = 0; q < m; ++q) u = fma(__ldg(y + r * pitch_y + q), q_s[q], u);
+        const XT* xr = x + r * X.pitch;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const int cg = cl + k * lpr;
+            if (cg < n_cg) {
+                RPack<XT> in;
+                in.v = __ldcg(reinterpret_cast<const V*>(xr + cg * VEC));
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    XT xs = in.e[j];
+                    if (masked && !(xs == xs)) xs = (XT)0;
+                    zacc[k][j] = fma((double)xs, u, zacc[k][j]);
+                }
+            }
+        }
+    }
+    if (rpt == 1) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const int cg = cl + k * lpr;
+            if (cg < n_cg) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) zrow[cg * VEC + j] = zacc[k][j];
+            }
+        }
+    } else {
+        // fewer than NTH column groups: several row lanes per column group (then one group per thread), folded in order
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) scr[(size_t)threadIdx.x * VEC + j] = zacc[0][j];
+        __syncthreads();
+        if (rl == 0 && cl < n_cg) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                double t = 0.0;
+                for (int q = 0; q < rpt; ++q) t += scr[((size_t)q * lpr + cl) * VEC + j];
+                zrow[cl * VEC + j] = t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename XT>
+__device__ __forceinline__ void resident_contract(const ResidentTensor& X, const double* __restrict__ y, int pitch_y, int m,
+                                                  const double* q_s, long long r_lo, long long r_hi, double* zrow, double* scr) {
+    const int n_cg = X.pitch / RVec<XT>::N;
+    if (n_cg <= NTH)
+        resident_contract_kc<XT, 1>(X, y, pitch_y, m, q_s, r_lo, r_hi, zrow, scr);
+    else if (n_cg <= 2 * NTH)
+        resident_contract_kc<XT, 2>(X, y, pitch_y, m, q_s, r_lo, r_hi, zrow, scr);
+    else
+        resident_contract_kc<XT, kResidentKc>(X, y, pitch_y, m, q_s, r_lo, r_hi, zrow, scr);
+}
+
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const __grid_constant__ ResidentArgs a) {
+    pdl_prologue();
+    // diagnostics: thread 0 of CTA 0 adds the time since the previous mark to slot i
+    long long t_mark = 0;
+    const bool stamping = a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamping) t_mark = global_ns();
+#define RES_MARK(i)                              \
+    if (stamping) {                              \
+        const long long t_now = global_ns();     \
+        a.stamps[i] += t_now - t_mark;           \
+        t_mark = t_now;                          \
+    }
+    extern __shared__ __align__(16) double dyn[];
+    __shared__ double q_s[8], qp_s[8], qraw_s[8], qw_s[NWARP][8];
+    __shared__ int stop_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int L = a.n_tensors, M = a.m;
+    const long long per = (a.n_rows + G - 1) / G;
+    const long long r_lo = min(a.n_rows, (long long)b * per), r_hi = min(a.n_rows, r_lo + per);
+    double* scr = dyn;  // phases other than the rank-1 step: <= kResidentScratch bytes
+    if (tid < 8) qp_s[tid] = tid < M ? a.q_prev[tid] : 0.0;
+    if (tid == 0) stop_s = 0;
+    __syncthreads();
+    int trip = 0;
+    double d2_last = 0.0;
+    int done_trip = -1;
+    for (;;) {
+        // ---- Z = fold of the per-CTA partials (trip 0: the fused centring / deflation pass wrote them) ----
+        {
+            int chunk = b;
+            for (int l = 0; l < L; ++l) {
+                const ResidentTensor& X = a.x[l];
+                const int nch = (X.pitch + 31) >> 5;
+                const int n_parts = trip == 0 ? X.parts0 : G;
+                for (; chunk < nch; chunk += G) {
+                    const int c = chunk * 32 + lane;   // 32 columns x 16 part-groups
+                    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                    if (c < X.pitch) {
+                        int pb = warp;
+                        for (; pb + 3 * NWARP < n_parts; pb += 4 * NWARP) {
+                            const double v0 = __ldcg(X.zpart + (size_t)pb * X.pitch + c);
+                            const double v1 = __ldcg(X.zpart + (size_t)(pb + NWARP) * X.pitch + c);
+                            const double v2 = __ldcg(X.zpart + (size_t)(pb + 2 * NWARP) * X.pitch + c);
+                            const double v3 = __ldcg(X.zpart + (size_t)(pb + 3 * NWARP) * X.pitch + c);
+                            t0 += v0;
+                            t1 += v1;
+                            t2 += v2;
+                            t3 += v3;
+                        }
+                        for (; pb < n_parts; pb += NWARP) t0 += __ldcg(X.zpart + (size_t)pb * X.pitch + c);
+                    }
+                    __syncthreads();
+                    scr[warp * 33 + lane] = (t0 + t1) + (t2 + t3);
+                    __syncthreads();
+                    if (warp == 0 && c < X.pitch) {
+                        double t = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NWARP; ++k) t += scr[k * 33 + lane];
+                        X.z[c] = t;
+                    }
+                }
+                chunk -= nch;
+            }
+        }
+        RES_MARK(0);
+        grid_sync(a.bar, G);
+        RES_MARK(5);
+        // ---- rank-1 step: the first L CTAs, one tensor each (tpls.py:84-90, cmtf.py:98-104) ----
+        if (b < L) {
+            if (SMEM)
+                rank1_task(a.r1[b], a.tol, a.normalize_on_break, dyn);
+            else
+                rank1_task(a.r1[b], a.tol, a.normalize_on_break, a.r1[b].scratch);
+        }
+        RES_MARK(1);
+        grid_sync(a.bar, G);
+        RES_MARK(6);
+        // ---- projection of this CTA's rows (a warp per row), coupled average, partials of q = Y't ----
+        {
+            double qacc = 0.0;  // lane i < pitch_y: response i
+            const double inv_l = 1.0 / (double)L;
+            const bool pow2 = (L & (L - 1)) == 0;
+            constexpr int NR = 2;  // rows per warp at once
+            for (long long r0 = r_lo + warp; r0 < r_hi; r0 += NR * NWARP) {
+                long long rows[NR];
+                double t[NR];
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    rows[i] = min(r0 + (long long)i * NWARP, r_hi - 1);
+                    t[i] = 0.0;
+                }
+                for (int l = 0; l < L; ++l) {
+                    const ResidentTensor& X = a.x[l];
+                    double v[NR];
+                    if (X.dtype == 0)
+                        resident_row_dots<float, NR>(reinterpret_cast<const float*>(X.x), rows, X.pitch, X.wkron, X.masked != 0, lane, v);
+                    else
+                        resident_row_dots<double, NR>(reinterpret_cast<const double*>(X.x), rows, X.pitch, X.wkron, X.masked != 0, lane, v);
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        if (X.masked) v[i] = v[i] / __ldg(X.rowcnt + rows[i]) * (double)X.p;  // missingvals.py:37
+                        t[i] = l == 0 ? v[i] : t[i] + v[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const long long r = r0 + (long long)i * NWARP;
+                    if (r >= r_hi) break;
+                    double ti = t[i];
+                    if (L > 1) ti = pow2 ? ti * inv_l : ti / (double)L;
+                    if (lane == 0) a.t_out[r] = ti;
+                    if (lane < a.pitch_y) qacc = fma(__ldg(a.y + r * a.pitch_y + lane), ti, qacc);
+                }
+            }
+            if (lane < 8) qw_s[warp][lane] = lane < a.pitch_y ? qacc : 0.0;
+            __syncthreads();
+            if (tid < 8) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) t += qw_s[w][tid];
+                a.qpart[(size_t)b * 8 + tid] = t;
+            }
+        }
+        RES_MARK(2);
+        grid_sync(a.bar, G);
+        RES_MARK(7);
+        // ---- q = Y't / ||.||, stop test dq^T (Y'Y) dq (tpls.py:100-107): every CTA folds the same partials in the
+        //      same order and takes the same decision; CTA 0 publishes it ----
+        {
+            const int col = tid & 7, grp = tid >> 3;  // 8 responses x 64 part-groups
+            double t = 0.0;
+            for (int pb = grp; pb < G; pb += NTH / 8) t += __ldcg(a.qpart + (size_t)pb * 8 + col);
+            scr[grp * 9 + col] = t;
+            __syncthreads();
+            if (tid < 8) {
+                double s = 0.0;
+                for (int k = 0; k < NTH / 8; ++k) s += scr[k * 9 + tid];
+                qraw_s[tid] = s;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double nrm = 0.0;
+                for (int i = 0; i < M; ++i) nrm = fma(qraw_s[i], qraw_s[i], nrm);
+                nrm = sqrt(nrm);
+                double dq[8];
+                for (int i = 0; i < 8; ++i) {
+                    const double qi = i < M ? qraw_s[i] / nrm : 0.0;
+                    dq[i] = qp_s[i] - qi;
+                    q_s[i] = qi;
+                    qp_s[i] = qi;
+                }
+                double d2 = 0.0;
+                for (int i = 0; i < M; ++i)
+                    for (int j = 0; j < M; ++j) d2 = fma(dq[i] * a.gram[i * M + j], dq[j], d2);
+                d2_last = d2;
+                bool stop = false;
+                if (trip >= 1 && sqrt(fabs(d2)) < a.tol) {
+                    done_trip = trip;
+                    stop = true;
+                }
+                if (trip + 1 >= a.max_iter) stop = true;
+                stop_s = stop ? 1 : 0;
+            }
+            __syncthreads();
+        }
+        ++trip;
+        RES_MARK(3);
+        if (stop_s) break;
+        // ---- contraction for the next trip: u = Y q row by row (tpls.py:102 fused into :83) ----
+        for (int l = 0; l < L; ++l) {
+            const ResidentTensor& X = a.x[l];
+            double* zrow = X.zpart + (size_t)b * X.pitch;
+            if (X.dtype == 0)
+                resident_contract<float>(X, a.y, a.pitch_y, M, q_s, r_lo, r_hi, zrow, scr);
+            else
+                resident_contract<double>(X, a.y, a.pitch_y, M, q_s, r_lo, r_hi, zrow, scr);
+        }
+        RES_MARK(4);
+        grid_sync(a.bar, G);
+        RES_MARK(8);
+    }
+    if (stamping) a.stamps[9] += trip;
+#undef RES_MARK
+    if (b == 0) {
+        if (tid < a.pitch_y) a.qvec[tid] = tid < M ? q_s[tid] : 0.0;
+        if (tid < M) {
+            a.qcol[tid] = q_s[tid];
+            a.q_prev[tid] = q_s[tid];
+        }
+        if (tid == 0) {
+            a.ctrl->done_trip = done_trip;
+            a.ctrl->trips_taken = trip;
+            a.ctrl->last_d2 = d2_last;
+            a.ctrl->trip = trip;
+            a.ctrl->stop = 1;
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_smem, cudaStream_t s) {
@@ -880,6 +1291,40 @@ cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_sm
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = (pdl_enabled() && !pdl_take_hold()) ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+size_t resident_min_smem() { return kResidentScratch; }
+
+cudaError_t launch_resident_loop(const ResidentArgs& a, int n_ctas, size_t r1_smem_bytes, cudaStream_t s) {
+    if (a.n_tensors < 1 || a.n_tensors > kMaxTensors || a.m > 8 || a.pitch_y > 8 || n_ctas < a.n_tensors) return cudaErrorInvalidValue;
+    const bool in_smem = a.r1_in_smem != 0 && r1_smem_bytes > 0;
+    auto kern = in_smem ? resident_loop_kernel<true> : resident_loop_kernel<false>;
+    const size_t smem = std::max(in_smem ? r1_smem_bytes : (size_t)0, kResidentScratch);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // A cooperative launch: the CTAs spin on each other at the grid barriers, so all of them must be resident at once
+    // (the driver checks it and schedules them together; a plain launch would also fit -- one CTA per SM -- unless
+    // another stream holds SMs).  TPLS_RESIDENT_COOP=0 launches it as an ordinary kernel.
+    static const bool coop = [] {
+        const char* v = getenv("TPLS_RESIDENT_COOP");
+        return v == nullptr || *v != '0';
+    }();
+    if (!coop) {
+        launch_k(kern, dim3(n_ctas), dim3(kRank1Threads), smem, s, a);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_ctas);
+    cfg.blockDim = dim3(kRank1Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    pdl_take_hold();
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 

@@ -64,6 +64,55 @@ struct CovLoopArgs {
 };
 cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_smem, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------------------------
+// Resident trip loop ("one persistent kernel per trip for L2-resident problems"): ALL inner trips
+// of one component (tpls.py:79-107, cmtf.py:90-128) in ONE launch of one CTA per SM.  The phases of a trip --
+// fold of the Z partials, rank-1 step, projection + partials of q = Y't, stop test, contraction for the next trip --
+// are separated by grid-wide barriers instead of kernel boundaries (four per trip, ~1.5 us each).  Every CTA owns a
+// contiguous block of samples and reads X with plain 16-byte loads: meant for working sets that stay in the 126 MB
+// L2, where a trip of the streaming kernels (7 launches) is bound by launch ramps rather than bytes.  One GPU, fused
+// Y side (<= 8 responses); larger problems, several ranks and profiled fits keep the streaming kernels.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kResidentKc = 8;  // 16-byte column groups per thread in the contraction (<= 8 * 512 groups per row)
+
+struct ResidentTensor {
+    const void* x;          // working copy [n_rows][pitch] in the storage type
+    int dtype;              // 0 = float32, 1 = float64
+    int p, pitch;
+    int masked;             // NaNs present: zero them, rescale projections by p / rowcnt[row] (missingvals.py:23-38)
+    const double* rowcnt;   // masked: observed entries per row
+    double* zpart;          // [max(parts0, CTAs)][pitch] per-CTA partials of Z
+    int parts0;             // rows of zpart that hold trip 0's partials (written by the fused centring/deflation pass)
+    double* z;              // folded Z [pitch] (what the rank-1 task reads)
+    const double* wkron;    // kron of this component's weight vectors [pitch] (what the rank-1 task writes)
+};
+
+struct ResidentArgs {
+    ResidentTensor x[kMaxTensors];
+    Rank1Task r1[kMaxTensors];
+    int n_tensors;
+    long long n_rows;
+    const double* y;        // centred / deflated responses [n_rows][pitch_y]
+    int pitch_y, m;
+    double* t_out;          // scores of this component [n_rows]
+    double* qpart;          // [CTAs][8] partials of q = Y't
+    double* qcol;           // out: unit q of the last trip [m]
+    double* qvec;           // out: the same, zero-padded [pitch_y]
+    double* q_prev;         // in/out [m] (what the stop test of the streaming loop keeps between launches)
+    const double* gram;     // Y'Y [m][m]
+    Ctrl* ctrl;
+    double tol;
+    int max_iter;
+    int normalize_on_break;
+    int r1_in_smem;         // rank-1 workspace in dynamic shared memory (else the tasks' global scratch)
+    unsigned int* bar;      // grid barrier: {arrivals, generation}, zero-initialised once
+    long long* stamps;      // optional diagnostics (TPLS_RESIDENT_STAMPS=1): ns CTA 0 spent per phase, summed over the trips
+                            //   [0] fold [1] rank-1 [2] projection [3] q / stop [4] contraction [5..8] the four barriers [9] trips
+};
+// smem_bytes: rank-1 workspace (0 when it lives in global memory); the launcher adds what the other phases need
+cudaError_t launch_resident_loop(const ResidentArgs& a, int n_ctas, size_t r1_smem_bytes, cudaStream_t s);
+size_t resident_min_smem();
+
 // doubles of workspace a task needs, and the Gram order it implies
 size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out,
                                int* tab_cols_out);

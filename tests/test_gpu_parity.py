@@ -378,16 +378,17 @@ def test_stop_test_met_on_the_last_allowed_trip_counts_as_converged():
     assert int(est3.n_iter_[0]) == k - 1 and not bool(est3.converged_[0])
 
 
-def test_fit_runs_as_one_graph_and_reports_its_launches():
+def test_fit_runs_as_one_graph_and_reports_its_launches(monkeypatch):
     """The streaming fit is ONE CUDA-graph launch (a WHILE node per component); 3 + 2 L kernels per inner trip."""
     import os
     from oracle import tpls_oracle as orc
     from cmtf_pls_b200 import ctPLS
+    monkeypatch.setenv("TPLS_RESIDENT", "0")         # the streaming kernels, whatever the size (read at every fit)
     Xs, Y, _ = orc.synthetic((400, 16, 8), 3, 4, error=0.4, seed=3, extra_dims=[(400, 20)])
     est = ctPLS(3)
     est.fit(Xs, Y)
     st = est.stats_
-    assert st["launches_per_trip"] == 3 + 2 * 2
+    assert st["launches_per_trip"] == 3 + 2 * 2 and st["resident_loops"] == 0
     if os.environ.get("TPLS_NO_GRAPH") is None:
         assert st["graph_launches"] == 1
     first = (est.n_iter_.tolist(), est.factor_T.copy())
@@ -398,6 +399,36 @@ def test_fit_runs_as_one_graph_and_reports_its_launches():
     assert est.n_iter_.tolist() == first[0] and np.array_equal(est.factor_T, first[1])
     ref = orc.fit([x.copy() for x in Xs], Y.copy(), 3, r2_mode="residual")
     assert est.n_iter_.tolist() == ref["trips"].tolist()
+
+
+@pytest.mark.parametrize("case", ["ct_90x32x16_90x24_m4_r5", "t3_miss_70x12x8_m4_r4", "t4_60x8x6x4_m3_r4", "t3_f32_80x16x8_m4_r4"])
+def test_resident_trip_loop_matches_the_streaming_kernels(case, monkeypatch):
+    """Working sets that stay in L2 run ALL inner trips of a component in one persistent launch (one CTA per SM, grid
+    barriers between the phases of a trip; rank1.cuh `ResidentArgs`).  Same trips, same model as the streaming kernels
+    (different summation order: 1e-10), one launch per component; profiled fits keep the streaming kernels."""
+    from cmtf_pls_b200 import ctPLS
+    g = load_golden(case)
+    R = int(g["n_components"])
+    fits = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("TPLS_RESIDENT", mode)
+        est = ctPLS(R)
+        est.fit([x.copy() for x in g["Xs"]], g["Y"].copy())
+        fits[mode] = est
+        assert est.stats_["resident_loops"] == (R if mode == "1" else 0)
+        assert est.n_iter_.tolist() == g["trips"].tolist()
+    a, b = fits["1"], fits["0"]
+    assert a.stats_["kernel_launches"] < b.stats_["kernel_launches"]
+    assert np.max(np.abs(a.factor_T - b.factor_T)) < 1e-10 * max(1.0, np.max(np.abs(b.factor_T)))
+    assert np.max(np.abs(a.coef_ - b.coef_)) < 1e-10 and np.max(np.abs(a.R2Y - b.R2Y)) < 1e-12
+    for l in range(len(g["Xs"])):
+        assert np.max(np.abs(a.R2Xs[l] - b.R2Xs[l])) < 1e-12
+    monkeypatch.delenv("TPLS_RESIDENT")
+    est = ctPLS(R)
+    est.fit([x.copy() for x in g["Xs"]], g["Y"].copy())          # small enough: resident by default
+    assert est.stats_["resident_loops"] == R
+    est.fit([x.copy() for x in g["Xs"]], g["Y"].copy(), profile=True)
+    assert est.stats_["resident_loops"] == 0 and est.n_iter_.tolist() == g["trips"].tolist()
 
 
 @pytest.mark.parametrize("env", [{"TPLS_NO_GRAPH": "1"}, {"TPLS_PDL": "0"}, {"TPLS_NO_GRAPH": "1", "TPLS_PDL": "0"}])
