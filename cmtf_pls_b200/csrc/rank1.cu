@@ -863,16 +863,17 @@ __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid
 // ---------------------------------------------------------------------------------------------------------------
 constexpr size_t kResidentScratch = 20 * 1024;  // bytes of dynamic shared memory the non-rank-1 phases use
 
-// Grid-wide barrier of co-resident CTAs (one per SM): arrivals counter + generation word in global memory.
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int n_ctas) {
+// Grid-wide barrier of co-resident CTAs (one per SM): arrivals counter + generation word in global memory.  The
+// generation is tracked in a register (read once at kernel start; every CTA takes part in every barrier), so an
+// arrival is ONE atomic with release/acquire semantics and the wait one polled word -- no load of the generation and
+// no separate fence ahead of the atomic.  The last arriver resets the counter before it publishes the next generation.
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int n_ctas, unsigned int& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int gen;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-        __threadfence();
-        if (atomicAdd(bar, 1u) == n_ctas - 1) {
-            bar[0] = 0u;
-            __threadfence();
+        unsigned int old;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+        if (old == n_ctas - 1) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1u) : "memory");
         } else {
             unsigned int g2;
@@ -881,6 +882,7 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int n_ctas
             } while (g2 == gen);
         }
     }
+    ++gen;
     __syncthreads();
 }
 
@@ -903,11 +905,13 @@ union RPack {
 };
 
 // NR rows of X times kron(w) at once: the lanes of a warp stride over the 16-byte column groups and keep 2 * NR loads
-// in flight (the data sits in L2: a load costs its latency, not its bytes); results in every lane.  Rows past the
-// end of the CTA's block repeat the last valid row (their results are ignored by the caller).
+// in flight (a load costs its latency, not its bytes); results in every lane.  xr[i] points at a row in the
+// shared-memory cache or in global memory (generic loads); rows past the end of the CTA's block repeat the last valid
+// row (their results are ignored by the caller).  kron(w) was written by another CTA earlier in this launch: plain
+// loads (ordered by the grid barrier), never the non-coherent path.
 template <typename XT, int NR>
-__device__ __forceinline__ void resident_row_dots(const XT* __restrict__ x, const long long (&rows)[NR], int pitch,
-                                                  const double* __restrict__ wk, bool masked, int lane, double (&out)[NR]) {
+__device__ __forceinline__ void resident_row_dots(const XT* const (&xr)[NR], int pitch, const double* wk, bool masked, int lane,
+                                                  double (&out)[NR]) {
     constexpr int VEC = RVec<XT>::N;
     using V = typename RVec<XT>::type;
     double acc[NR][2];
@@ -919,12 +923,12 @@ __device__ __forceinline__ void resident_row_dots(const XT* __restrict__ x, cons
 #pragma unroll
         for (int i = 0; i < NR; ++i)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) in[i][h].v = __ldcg(reinterpret_cast<const V*>(x + rows[i] * pitch + c + h * 32 * VEC));
+            for (int h = 0; h < 2; ++h) in[i][h].v = *reinterpret_cast<const V*>(xr[i] + c + h * 32 * VEC);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const double w = __ldg(wk + c + h * 32 * VEC + j);
+                const double w = wk[c + h * 32 * VEC + j];
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
                     XT xs = in[i][h].e[j];
@@ -936,10 +940,10 @@ __device__ __forceinline__ void resident_row_dots(const XT* __restrict__ x, cons
     for (; c < pitch; c += 32 * VEC) {
         RPack<XT> in[NR];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) in[i].v = __ldcg(reinterpret_cast<const V*>(x + rows[i] * pitch + c));
+        for (int i = 0; i < NR; ++i) in[i].v = *reinterpret_cast<const V*>(xr[i] + c);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            const double w = __ldg(wk + c + j);
+            const double w = wk[c + j];
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 XT xs = in[i].e[j];
@@ -956,12 +960,42 @@ __device__ __forceinline__ void resident_row_dots(const XT* __restrict__ x, cons
         for (int i = 0; i < NR; ++i) out[i] += __shfl_xor_sync(0xffffffffu, out[i], m);
 }
 
+// Where the rows of a CTA's block live: the first n_cached of them in shared memory, the rest in global memory.
+// Rows are addressed by their index inside the block (32-bit arithmetic).
+template <typename XT>
+struct RowSrc {
+    const XT* gbase;   // row 0 of the block in global memory
+    const XT* cbase;   // row 0 of the block in the shared-memory cache
+    int n_cached, pitch;
+    __device__ __forceinline__ const XT* row(int k) const {
+        return (k < n_cached ? cbase : gbase) + (size_t)((unsigned)k * (unsigned)pitch);
+    }
+};
+
+constexpr int kResidentUChunk = 1024;  // rows of u = Y q kept in shared memory at a time
+
+// u[k] = Y[k,:] . q for the rows [c_lo, c_hi) of the block, once per CTA (every thread of the contraction would
+// otherwise form the u of each of its rows itself: m loads per row against one 16-byte load of X)
+__device__ __forceinline__ void resident_u_chunk(double* u_s, const RowSrc<double>& ysrc, int m, const double* q_s, int c_lo, int c_hi) {
+    __syncthreads();
+    for (int k = c_lo + (int)threadIdx.x; k < c_hi; k += NTH) {
+        const double* yr = ysrc.row(k);
+        double ui = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < m) ui = fma(yr[q], q_s[q], ui);
+        u_s[k - c_lo] = ui;
+    }
+    __syncthreads();
+}
+
 // Z partials of this CTA's rows for one tensor: zpart_row[c] = sum_r x[r, c] * u[r], u[r] = Y[r,:] . q
+// One loop, no tail: a thread's RU rows are loaded together, rows past the end of the block repeat its last row with
+// u = 0 (a serial tail cost one L2 round trip per leftover row).
 template <typename XT, int KC>
-__device__ __forceinline__ void resident_contract_kc(const ResidentTensor& X, const double* __restrict__ y, int pitch_y, int m,
-                                                  const double* q_s, long long r_lo, long long r_hi, double* zrow, double* scr) {
+__device__ __forceinline__ void resident_contract_kc(const ResidentTensor& X, const RowSrc<XT>& src, const RowSrc<double>& ysrc, int m,
+                                                     const double* q_s, int nblk, double* u_s, int& u_lo, double* zrow, double* scr) {
     constexpr int VEC = RVec<XT>::N;
-    const XT* x = reinterpret_cast<const XT*>(X.x);
     const int n_cg = X.pitch / VEC;
     int lpr = 1;
     while (lpr < n_cg && lpr < NTH) lpr <<= 1;
@@ -975,48 +1009,37 @@ __device__ __forceinline__ void resident_contract_kc(const ResidentTensor& X, co
         for (int j = 0; j < VEC; ++j) zacc[k][j] = 0.0;
     using V = typename RVec<XT>::type;
     constexpr int RU = KC <= 2 ? 8 : 4;  // rows in flight per thread: the loads of a group are issued before any of them is used
-    long long r = r_lo + rl;
-    for (; r + (long long)(RU - 1) * rpt < r_hi; r += (long long)RU * rpt) {
-        double u[RU];
-#pragma unroll
-        for (int i = 0; i < RU; ++i) {
-            u[i] = 0.0;
-            for (int q = 0; q < m; ++q) u[i] = fma(__ldg(y + (r + (long long)i * rpt) * pitch_y + q), q_s[q], u[i]);
+    for (int c_lo = 0; c_lo < nblk; c_lo += kResidentUChunk) {
+        const int c_hi = min(nblk, c_lo + kResidentUChunk);
+        if (u_lo != c_lo) {
+            resident_u_chunk(u_s, ysrc, m, q_s, c_lo, c_hi);
+            u_lo = c_lo;
         }
+        for (int r = c_lo + rl; r < c_hi; r += RU * rpt) {
+            double u[RU];
+            const XT* xr[RU];
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            const int cg = cl + k * lpr;
-            if (cg < n_cg) {
-                RPack<XT> in[RU];
-#pragma unroll
-                for (int i = 0; i < RU; ++i)
-                    in[i].v = __ldcg(reinterpret_cast<const V*>(x + (r + (long long)i * rpt) * X.pitch + cg * VEC));
-#pragma unroll
-                for (int i = 0; i < RU; ++i)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        XT xs = in[i].e[j];
-                        if (masked && !(xs == xs)) xs = (XT)0;
-                        zacc[k][j] = fma((double)xs, u[i], zacc[k][j]);
-                    }
+            for (int i = 0; i < RU; ++i) {
+                const int ri = r + i * rpt;
+                const bool in = ri < c_hi;
+                xr[i] = src.row(in ? ri : c_hi - 1);
+                u[i] = in ? u_s[ri - c_lo] : 0.0;
             }
-        }
-    }
-    for (; r < r_hi; r += rpt) {
-        double u = 0.0;
-        for (int q = 0; q < m; ++q) u = fma(__ldg(y + r * pitch_y + q), q_s[q], u);
-        const XT* xr = x + r * X.pitch;
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            const int cg = cl + k * lpr;
-            if (cg < n_cg) {
-                RPack<XT> in;
-                in.v = __ldcg(reinterpret_cast<const V*>(xr + cg * VEC));
+            for (int k = 0; k < KC; ++k) {
+                const int cg = cl + k * lpr;
+                if (cg < n_cg) {
+                    RPack<XT> in[RU];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    XT xs = in.e[j];
-                    if (masked && !(xs == xs)) xs = (XT)0;
-                    zacc[k][j] = fma((double)xs, u, zacc[k][j]);
+                    for (int i = 0; i < RU; ++i) in[i].v = *reinterpret_cast<const V*>(xr[i] + cg * VEC);
+#pragma unroll
+                    for (int i = 0; i < RU; ++i)
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) {
+                            XT xs = in[i].e[j];
+                            if (masked && !(xs == xs)) xs = (XT)0;
+                            zacc[k][j] = fma((double)xs, u[i], zacc[k][j]);
+                        }
                 }
             }
         }
@@ -1049,15 +1072,15 @@ __device__ __forceinline__ void resident_contract_kc(const ResidentTensor& X, co
 }
 
 template <typename XT>
-__device__ __forceinline__ void resident_contract(const ResidentTensor& X, const double* __restrict__ y, int pitch_y, int m,
-                                                  const double* q_s, long long r_lo, long long r_hi, double* zrow, double* scr) {
+__device__ __forceinline__ void resident_contract(const ResidentTensor& X, const RowSrc<XT>& src, const RowSrc<double>& ysrc, int m,
+                                                  const double* q_s, int nblk, double* u_s, int& u_lo, double* zrow, double* scr) {
     const int n_cg = X.pitch / RVec<XT>::N;
     if (n_cg <= NTH)
-        resident_contract_kc<XT, 1>(X, y, pitch_y, m, q_s, r_lo, r_hi, zrow, scr);
+        resident_contract_kc<XT, 1>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
     else if (n_cg <= 2 * NTH)
-        resident_contract_kc<XT, 2>(X, y, pitch_y, m, q_s, r_lo, r_hi, zrow, scr);
+        resident_contract_kc<XT, 2>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
     else
-        resident_contract_kc<XT, kResidentKc>(X, y, pitch_y, m, q_s, r_lo, r_hi, zrow, scr);
+        resident_contract_kc<XT, kResidentKc>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
 }
 
 __device__ __forceinline__ long long global_ns() {
@@ -1080,17 +1103,49 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
         t_mark = t_now;                          \
     }
     extern __shared__ __align__(16) double dyn[];
-    __shared__ double q_s[8], qp_s[8], qraw_s[8], qw_s[NWARP][8];
+    __shared__ double q_s[8], qp_s[8], qw_s[NWARP][8];
     __shared__ int stop_s;
+    __shared__ __align__(8) uint64_t cache_bar;
+    __shared__ double u_s[kResidentUChunk];
+    __shared__ double dq_s[8], gram_s[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)gridDim.x, b = (int)blockIdx.x;
     const int L = a.n_tensors, M = a.m;
     const long long per = (a.n_rows + G - 1) / G;
     const long long r_lo = min(a.n_rows, (long long)b * per), r_hi = min(a.n_rows, r_lo + per);
     double* scr = dyn;  // phases other than the rank-1 step: <= kResidentScratch bytes
+    // rows [r_lo, r_lo + n_cached) of every tensor and of Y live in shared memory from the first projection on
+    unsigned char* const cache = reinterpret_cast<unsigned char*>(dyn) + a.cache_off;
+    const int n_cached = (int)max(0ll, min((long long)a.cache_rows, r_hi - r_lo));
+    size_t y_cache_off = 0;  // tensor l starts cache_rows * (bytes per row of the tensors before it) into the cache; Y is last
+    for (int l = 0; l < L; ++l) y_cache_off += (size_t)a.cache_rows * a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
+    unsigned int bar_gen = 0;
     if (tid < 8) qp_s[tid] = tid < M ? a.q_prev[tid] : 0.0;
-    if (tid == 0) stop_s = 0;
+    if (tid >= 32 && tid < 32 + M * M) gram_s[tid - 32] = a.gram[tid - 32];
+    if (tid == 0) {
+        stop_s = 0;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(bar_gen) : "l"(a.bar + 1) : "memory");
+        mbar_init(&cache_bar, 1);
+        fence_mbar_init();
+    }
     __syncthreads();
+    if (tid == 0 && n_cached > 0) {
+        // one thread hands the copies to the bulk-copy engine; they land while the first fold and rank-1 step run
+        unsigned int total = (unsigned int)n_cached * (unsigned int)(a.pitch_y * 8);
+        for (int l = 0; l < L; ++l) total += (unsigned int)n_cached * (unsigned int)(a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8));
+        mbar_arrive_expect_tx(&cache_bar, total);
+        size_t off = 0;
+        for (int l = 0; l <= L; ++l) {
+            const size_t row_b = l < L ? (size_t)a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8) : (size_t)a.pitch_y * 8;
+            const unsigned char* g = reinterpret_cast<const unsigned char*>(l < L ? a.x[l].x : (const void*)a.y) + (size_t)r_lo * row_b;
+            const size_t bytes = (size_t)n_cached * row_b;
+            for (size_t o = 0; o < bytes; o += 32768)
+                bulk_g2s(cache + off + o, g + o, (uint32_t)min((size_t)32768, bytes - o), &cache_bar);
+            off += (size_t)a.cache_rows * row_b;
+        }
+    }
+    const int nblk = (int)(r_hi - r_lo);  // rows of this CTA's block
+    const RowSrc<double> ysrc{a.y + (size_t)r_lo * a.pitch_y, reinterpret_cast<const double*>(cache + y_cache_off), n_cached, a.pitch_y};
     int trip = 0;
     double d2_last = 0.0;
     int done_trip = -1;
@@ -1133,7 +1188,7 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
             }
         }
         RES_MARK(0);
-        grid_sync(a.bar, G);
+        grid_sync(a.bar, G, bar_gen);
         RES_MARK(5);
         // ---- rank-1 step: the first L CTAs, one tensor each (tpls.py:84-90, cmtf.py:98-104) ----
         if (b < L) {
@@ -1143,43 +1198,58 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
                 rank1_task(a.r1[b], a.tol, a.normalize_on_break, a.r1[b].scratch);
         }
         RES_MARK(1);
-        grid_sync(a.bar, G);
+        grid_sync(a.bar, G, bar_gen);
         RES_MARK(6);
         // ---- projection of this CTA's rows (a warp per row), coupled average, partials of q = Y't ----
+        if (trip == 0 && n_cached > 0) mbar_wait(&cache_bar, 0);  // the cached rows have landed
         {
             double qacc = 0.0;  // lane i < pitch_y: response i
             const double inv_l = 1.0 / (double)L;
             const bool pow2 = (L & (L - 1)) == 0;
-            constexpr int NR = 2;  // rows per warp at once
-            for (long long r0 = r_lo + warp; r0 < r_hi; r0 += NR * NWARP) {
-                long long rows[NR];
+            constexpr int NR = 4;  // rows per warp at once
+            for (int k0 = warp; k0 < nblk; k0 += NR * NWARP) {
+                int ks[NR];
                 double t[NR];
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
-                    rows[i] = min(r0 + (long long)i * NWARP, r_hi - 1);
+                    ks[i] = min(k0 + i * NWARP, nblk - 1);
                     t[i] = 0.0;
                 }
+                size_t coff = 0;
                 for (int l = 0; l < L; ++l) {
                     const ResidentTensor& X = a.x[l];
                     double v[NR];
-                    if (X.dtype == 0)
-                        resident_row_dots<float, NR>(reinterpret_cast<const float*>(X.x), rows, X.pitch, X.wkron, X.masked != 0, lane, v);
-                    else
-                        resident_row_dots<double, NR>(reinterpret_cast<const double*>(X.x), rows, X.pitch, X.wkron, X.masked != 0, lane, v);
+                    if (X.dtype == 0) {
+                        const RowSrc<float> src{reinterpret_cast<const float*>(X.x) + (size_t)r_lo * X.pitch,
+                                                reinterpret_cast<const float*>(cache + coff), n_cached, X.pitch};
+                        const float* xr[NR];
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) xr[i] = src.row(ks[i]);
+                        resident_row_dots<float, NR>(xr, X.pitch, X.wkron, X.masked != 0, lane, v);
+                        coff += (size_t)a.cache_rows * X.pitch * 4;
+                    } else {
+                        const RowSrc<double> src{reinterpret_cast<const double*>(X.x) + (size_t)r_lo * X.pitch,
+                                                 reinterpret_cast<const double*>(cache + coff), n_cached, X.pitch};
+                        const double* xr[NR];
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) xr[i] = src.row(ks[i]);
+                        resident_row_dots<double, NR>(xr, X.pitch, X.wkron, X.masked != 0, lane, v);
+                        coff += (size_t)a.cache_rows * X.pitch * 8;
+                    }
 #pragma unroll
                     for (int i = 0; i < NR; ++i) {
-                        if (X.masked) v[i] = v[i] / __ldg(X.rowcnt + rows[i]) * (double)X.p;  // missingvals.py:37
+                        if (X.masked) v[i] = v[i] / __ldg(X.rowcnt + r_lo + ks[i]) * (double)X.p;  // missingvals.py:37
                         t[i] = l == 0 ? v[i] : t[i] + v[i];
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
-                    const long long r = r0 + (long long)i * NWARP;
-                    if (r >= r_hi) break;
+                    const int k = k0 + i * NWARP;
+                    if (k >= nblk) break;
                     double ti = t[i];
                     if (L > 1) ti = pow2 ? ti * inv_l : ti / (double)L;
-                    if (lane == 0) a.t_out[r] = ti;
-                    if (lane < a.pitch_y) qacc = fma(__ldg(a.y + r * a.pitch_y + lane), ti, qacc);
+                    if (lane == 0) a.t_out[r_lo + k] = ti;
+                    if (lane < a.pitch_y) qacc = fma(ysrc.row(k)[lane], ti, qacc);
                 }
             }
             if (lane < 8) qw_s[warp][lane] = lane < a.pitch_y ? qacc : 0.0;
@@ -1192,44 +1262,57 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
             }
         }
         RES_MARK(2);
-        grid_sync(a.bar, G);
+        grid_sync(a.bar, G, bar_gen);
         RES_MARK(7);
         // ---- q = Y't / ||.||, stop test dq^T (Y'Y) dq (tpls.py:100-107): every CTA folds the same partials in the
         //      same order and takes the same decision; CTA 0 publishes it ----
         {
-            const int col = tid & 7, grp = tid >> 3;  // 8 responses x 64 part-groups
-            double t = 0.0;
-            for (int pb = grp; pb < G; pb += NTH / 8) t += __ldcg(a.qpart + (size_t)pb * 8 + col);
-            scr[grp * 9 + col] = t;
+            const int col = tid & 7, grp = tid >> 3;  // 8 responses x 64 part-groups (4 per warp)
+            double t0 = 0.0, t1 = 0.0;
+            int pb = grp;
+            for (; pb + NTH / 8 < G; pb += 2 * (NTH / 8)) {
+                const double v0 = __ldcg(a.qpart + (size_t)pb * 8 + col);
+                const double v1 = __ldcg(a.qpart + (size_t)(pb + NTH / 8) * 8 + col);
+                t0 += v0;
+                t1 += v1;
+            }
+            if (pb < G) t0 += __ldcg(a.qpart + (size_t)pb * 8 + col);
+            double t = t0 + t1;
+            t += shfl_xor_d(t, 8);
+            t += shfl_xor_d(t, 16);
+            if (lane < 8) qw_s[warp][lane] = t;
             __syncthreads();
             if (tid < 8) {
+                // eight lanes in step: every lane folds its response, forms the same norm, divides its own entry
                 double s = 0.0;
-                for (int k = 0; k < NTH / 8; ++k) s += scr[k * 9 + tid];
-                qraw_s[tid] = s;
-            }
-            __syncthreads();
-            if (tid == 0) {
+#pragma unroll
+                for (int k = 0; k < NWARP; ++k) s += qw_s[k][tid];
+                if (tid >= M) s = 0.0;
                 double nrm = 0.0;
-                for (int i = 0; i < M; ++i) nrm = fma(qraw_s[i], qraw_s[i], nrm);
-                nrm = sqrt(nrm);
-                double dq[8];
+#pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const double qi = i < M ? qraw_s[i] / nrm : 0.0;
-                    dq[i] = qp_s[i] - qi;
-                    q_s[i] = qi;
-                    qp_s[i] = qi;
+                    const double si = __shfl_sync(0xffu, s, i);
+                    nrm = fma(si, si, nrm);
                 }
-                double d2 = 0.0;
-                for (int i = 0; i < M; ++i)
-                    for (int j = 0; j < M; ++j) d2 = fma(dq[i] * a.gram[i * M + j], dq[j], d2);
-                d2_last = d2;
-                bool stop = false;
-                if (trip >= 1 && sqrt(fabs(d2)) < a.tol) {
-                    done_trip = trip;
-                    stop = true;
+                nrm = sqrt(nrm);
+                const double qi = tid < M ? s / nrm : 0.0;
+                dq_s[tid] = qp_s[tid] - qi;
+                q_s[tid] = qi;
+                qp_s[tid] = qi;
+                __syncwarp(0xffu);
+                if (tid == 0) {
+                    double d2 = 0.0;
+                    for (int i = 0; i < M; ++i)
+                        for (int j = 0; j < M; ++j) d2 = fma(dq_s[i] * gram_s[i * M + j], dq_s[j], d2);
+                    d2_last = d2;
+                    bool stop = false;
+                    if (trip >= 1 && sqrt(fabs(d2)) < a.tol) {
+                        done_trip = trip;
+                        stop = true;
+                    }
+                    if (trip + 1 >= a.max_iter) stop = true;
+                    stop_s = stop ? 1 : 0;
                 }
-                if (trip + 1 >= a.max_iter) stop = true;
-                stop_s = stop ? 1 : 0;
             }
             __syncthreads();
         }
@@ -1237,16 +1320,27 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
         RES_MARK(3);
         if (stop_s) break;
         // ---- contraction for the next trip: u = Y q row by row (tpls.py:102 fused into :83) ----
-        for (int l = 0; l < L; ++l) {
-            const ResidentTensor& X = a.x[l];
-            double* zrow = X.zpart + (size_t)b * X.pitch;
-            if (X.dtype == 0)
-                resident_contract<float>(X, a.y, a.pitch_y, M, q_s, r_lo, r_hi, zrow, scr);
-            else
-                resident_contract<double>(X, a.y, a.pitch_y, M, q_s, r_lo, r_hi, zrow, scr);
+        {
+            size_t coff = 0;
+            int u_lo = -1;  // first row of the block whose u sits in u_s
+            for (int l = 0; l < L; ++l) {
+                const ResidentTensor& X = a.x[l];
+                double* zrow = X.zpart + (size_t)b * X.pitch;
+                if (X.dtype == 0) {
+                    const RowSrc<float> src{reinterpret_cast<const float*>(X.x) + (size_t)r_lo * X.pitch,
+                                            reinterpret_cast<const float*>(cache + coff), n_cached, X.pitch};
+                    resident_contract<float>(X, src, ysrc, M, q_s, nblk, u_s, u_lo, zrow, scr);
+                    coff += (size_t)a.cache_rows * X.pitch * 4;
+                } else {
+                    const RowSrc<double> src{reinterpret_cast<const double*>(X.x) + (size_t)r_lo * X.pitch,
+                                             reinterpret_cast<const double*>(cache + coff), n_cached, X.pitch};
+                    resident_contract<double>(X, src, ysrc, M, q_s, nblk, u_s, u_lo, zrow, scr);
+                    coff += (size_t)a.cache_rows * X.pitch * 8;
+                }
+            }
         }
         RES_MARK(4);
-        grid_sync(a.bar, G);
+        grid_sync(a.bar, G, bar_gen);
         RES_MARK(8);
     }
     if (stamping) a.stamps[9] += trip;
@@ -1296,11 +1390,41 @@ cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_sm
 
 size_t resident_min_smem() { return kResidentScratch; }
 
-cudaError_t launch_resident_loop(const ResidentArgs& a, int n_ctas, size_t r1_smem_bytes, cudaStream_t s) {
+cudaError_t launch_resident_loop(const ResidentArgs& a_in, int n_ctas, size_t r1_smem_bytes, cudaStream_t s) {
+    ResidentArgs a = a_in;
     if (a.n_tensors < 1 || a.n_tensors > kMaxTensors || a.m > 8 || a.pitch_y > 8 || n_ctas < a.n_tensors) return cudaErrorInvalidValue;
     const bool in_smem = a.r1_in_smem != 0 && r1_smem_bytes > 0;
     auto kern = in_smem ? resident_loop_kernel<true> : resident_loop_kernel<false>;
-    const size_t smem = std::max(in_smem ? r1_smem_bytes : (size_t)0, kResidentScratch);
+    // dynamic shared memory: [rank-1 workspace or the scratch of the other phases | row cache]
+    const size_t front = (std::max(in_smem ? r1_smem_bytes : (size_t)0, kResidentScratch) + 127) & ~(size_t)127;
+    static const size_t dyn_max[2] = {
+        [] {
+            cudaFuncAttributes fa{};
+            int dev = 0, optin = 0;
+            if (cudaFuncGetAttributes(&fa, resident_loop_kernel<false>) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+                cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+                return (size_t)0;
+            return (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : (size_t)0;
+        }(),
+        [] {
+            cudaFuncAttributes fa{};
+            int dev = 0, optin = 0;
+            if (cudaFuncGetAttributes(&fa, resident_loop_kernel<true>) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+                cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+                return (size_t)0;
+            return (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : (size_t)0;
+        }()};
+    static const bool cache_on = [] {
+        const char* v = getenv("TPLS_RESIDENT_CACHE");  // =0: every pass reads its rows from L2 (A/B switch)
+        return v == nullptr || *v != '0';
+    }();
+    size_t row_bytes = (size_t)a.pitch_y * 8;
+    for (int l = 0; l < a.n_tensors; ++l) row_bytes += (size_t)a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
+    const long long per = (a.n_rows + n_ctas - 1) / n_ctas;
+    const size_t room = dyn_max[in_smem ? 1 : 0] > front ? dyn_max[in_smem ? 1 : 0] - front : 0;
+    a.cache_rows = cache_on ? (int)std::min<long long>(per, (long long)(room / row_bytes)) : 0;
+    a.cache_off = (unsigned)front;
+    const size_t smem = front + (size_t)a.cache_rows * row_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // A cooperative launch: the CTAs spin on each other at the grid barriers, so all of them must be resident at once

@@ -69,9 +69,12 @@ cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_sm
 // of one component (tpls.py:79-107, cmtf.py:90-128) in ONE launch of one CTA per SM.  The phases of a trip --
 // fold of the Z partials, rank-1 step, projection + partials of q = Y't, stop test, contraction for the next trip --
 // are separated by grid-wide barriers instead of kernel boundaries (four per trip, ~1.5 us each).  Every CTA owns a
-// contiguous block of samples and reads X with plain 16-byte loads: meant for working sets that stay in the 126 MB
-// L2, where a trip of the streaming kernels (7 launches) is bound by launch ramps rather than bytes.  One GPU, fused
-// Y side (<= 8 responses); larger problems, several ranks and profiled fits keep the streaming kernels.
+// contiguous block of samples; X does not change during the trips of a component, so the first rows of the block
+// (as many as fit in the ~200 KB of shared memory the rank-1 workspace leaves, with their rows of Y) are copied into
+// shared memory ONCE per launch by bulk async copies that land behind the first fold and rank-1 step; the rest of the
+// block is read from L2 with 16-byte loads in both passes of every trip.  Meant for working sets that stay in the
+// 126 MB L2, where a trip of the streaming kernels (7 launches) is bound by launch ramps rather than bytes.  One GPU,
+// fused Y side (<= 8 responses); larger problems, several ranks and profiled fits keep the streaming kernels.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kResidentKc = 8;  // 16-byte column groups per thread in the contraction (<= 8 * 512 groups per row)
 
@@ -106,6 +109,8 @@ struct ResidentArgs {
     int normalize_on_break;
     int r1_in_smem;         // rank-1 workspace in dynamic shared memory (else the tasks' global scratch)
     unsigned int* bar;      // grid barrier: {arrivals, generation}, zero-initialised once
+    int cache_rows;         // set by the launcher: rows of every CTA's block (X of all tensors and Y) that are copied into
+    unsigned cache_off;     //   shared memory once per launch, and the byte offset of that cache in dynamic shared memory
     long long* stamps;      // optional diagnostics (TPLS_RESIDENT_STAMPS=1): ns CTA 0 spent per phase, summed over the trips
                             //   [0] fold [1] rank-1 [2] projection [3] q / stop [4] contraction [5..8] the four barriers [9] trips
 };

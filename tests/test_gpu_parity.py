@@ -431,6 +431,33 @@ def test_resident_trip_loop_matches_the_streaming_kernels(case, monkeypatch):
     assert est.stats_["resident_loops"] == 0 and est.n_iter_.tolist() == g["trips"].tolist()
 
 
+@pytest.mark.parametrize("dtype,nan_frac", [(np.float64, 0.0), (np.float32, 0.15)])
+def test_resident_trip_loop_with_a_partly_cached_block(dtype, nan_frac, monkeypatch):
+    """Blocks of rows too large for shared memory: the first rows of every CTA's block are read from its shared-memory
+    cache, the rest from L2, in both passes of a trip (rank1.cuh).  Same trips and the same model as the streaming
+    kernels, complete and masked, coupled with a narrow second tensor."""
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import ctPLS
+    Xs, Y, _ = orc.synthetic((6000, 32, 32), 3, 4, error=0.5, seed=11, extra_dims=[(6000, 20)])
+    Xs = [x.astype(dtype) for x in Xs]
+    if nan_frac:
+        rng = np.random.default_rng(5)
+        for x in Xs:
+            x[rng.random(x.shape) < nan_frac] = np.nan
+    fits = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("TPLS_RESIDENT", mode)
+        est = ctPLS(3)
+        est.fit([x.copy() for x in Xs], Y.copy())
+        fits[mode] = est
+        assert est.stats_["resident_loops"] == (3 if mode == "1" else 0)
+    a, b = fits["1"], fits["0"]
+    tol = 1e-10 if dtype == np.float64 else 1e-9     # fp64 arithmetic on the same stored values either way
+    assert a.n_iter_.tolist() == b.n_iter_.tolist()
+    assert np.max(np.abs(a.factor_T - b.factor_T)) < tol * max(1.0, np.max(np.abs(b.factor_T)))
+    assert np.max(np.abs(a.coef_ - b.coef_)) < tol and np.max(np.abs(a.R2Y - b.R2Y)) < 1e-10
+
+
 @pytest.mark.parametrize("env", [{"TPLS_NO_GRAPH": "1"}, {"TPLS_PDL": "0"}, {"TPLS_NO_GRAPH": "1", "TPLS_PDL": "0"}])
 def test_host_enqueued_and_plain_launch_paths_give_the_same_fit(env, tmp_path):
     """The graph-launched fit (default), the host-enqueued trips (profiling / NCCL fallback) and launches without the
