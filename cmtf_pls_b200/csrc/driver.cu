@@ -1701,6 +1701,12 @@ loops_done:
                 "contraction %.2f | barriers %.2f %.2f %.2f %.2f\n",
                 hs[9], hs[0] / tr * 1e-3, hs[1] / tr * 1e-3, hs[2] / tr * 1e-3, hs[3] / tr * 1e-3, hs[4] / tr * 1e-3,
                 hs[5] / tr * 1e-3, hs[6] / tr * 1e-3, hs[7] / tr * 1e-3, hs[8] / tr * 1e-3);
+        long long fs[32];
+        if (resident_fine_stamps(fs))
+            fprintf(stderr,
+                    "   cycles per trip: projection [t0 first round %.0f, later %.0f | t1+ first %.0f, later %.0f | epilogues %.0f | "
+                    "fold+store %.0f]  contraction [u %.0f  rows %.0f  write %.0f]\n",
+                    fs[0] / tr, fs[1] / tr, fs[2] / tr, fs[3] / tr, fs[4] / tr, fs[5] / tr, fs[8] / tr, fs[9] / tr, fs[10] / tr);
     }
     // launches / collectives / streamed bytes of the loops: one body was counted per component
     if (!cov_mode) {

@@ -626,20 +626,30 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         double* tmp = B + n2;
         // rows of Mt are the columns of the mode-ks unfolding: Z^T for ks == 0, Z for ks == 1
         const double* Mt = ks == 0 ? mt2 : zs;
-        syrk_dmma<false>(G, ldg, Mt, ks == 0 ? ld0 : ld1, no, up8(n), 1.0, cta);
         double* const f0 = fac;        // the two factor vectors, back to back
         double* const f1 = fac + d0;
-        lead_eig(G, A, B, ks == 0 ? f0 : f1, tmp, n, ldg, cta, /*polish=*/1, /*want_lambda=*/false);
-        TPLS_STAMP(2);
-        if (ks == 0) {
-            matvec8(tmp, mt2, ld0, f0, d1, d0, cta);
-            normalize_into(f1, tmp, d1, cta);
+        // Tiny matrices (Gram order <= 8: one 8x8 tile; vectors of <= 32 entries) run on ONE warp: every step below
+        // is a short dependent chain, and with the whole CTA each of the ~35 steps paid a 16-warp barrier and a
+        // 16-entry fold for work that fits one lane each (8 x 6: 13.0 -> 11.6 us; from order 16 on the 8-lane
+        // matrix-vector passes and the tiles one after the other cost more than the barriers: 32 x 16 12.5 -> 15 us).
+        const bool one_warp = up8(n) <= 8 && no <= 32;
+        Grp w0{(int)threadIdx.x, 32, 1, red + 4 * NWARP, ired + 2 * NWARP, 0, T.stamps};
+        Grp& g = one_warp ? w0 : cta;
+        if (!one_warp || threadIdx.x < 32) {
+            syrk_dmma<false>(G, ldg, Mt, ks == 0 ? ld0 : ld1, no, up8(n), 1.0, g);
+            lead_eig(G, A, B, ks == 0 ? f0 : f1, tmp, n, ldg, g, /*polish=*/1, /*want_lambda=*/false);
+            TPLS_STAMP(2);
+            if (ks == 0) {
+                matvec8(tmp, mt2, ld0, f0, d1, d0, g);
+                normalize_into(f1, tmp, d1, g);
+            }
+            flip_to_positive_peak(f1, d1, g);
+            matvec8(tmp, zs, ld1, f1, d0, d1, g);
+            normalize_into(f0, tmp, d0, g);
+            matvec8(tmp, mt2, ld0, f0, d1, d0, g);
+            normalize_into(f1, tmp, d1, g);
         }
-        flip_to_positive_peak(f1, d1, cta);
-        matvec8(tmp, zs, ld1, f1, d0, d1, cta);
-        normalize_into(f0, tmp, d0, cta);
-        matvec8(tmp, mt2, ld0, f0, d1, d0, cta);
-        normalize_into(f1, tmp, d1, cta);
+        if (one_warp) __syncthreads();
         sweeps = 2;
         TPLS_STAMP(3);
     } else {
@@ -904,61 +914,84 @@ union RPack {
     XT e[RVec<XT>::N];
 };
 
-// NR rows of X times kron(w) at once: the lanes of a warp stride over the 16-byte column groups and keep 2 * NR loads
-// in flight (a load costs its latency, not its bytes); results in every lane.  xr[i] points at a row in the
-// shared-memory cache or in global memory (generic loads); rows past the end of the CTA's block repeat the last valid
-// row (their results are ignored by the caller).  kron(w) was written by another CTA earlier in this launch: plain
-// loads (ordered by the grid barrier), never the non-coherent path.
-template <typename XT, int NR>
-__device__ __forceinline__ void resident_row_dots(const XT* const (&xr)[NR], int pitch, const double* wk, bool masked, int lane,
-                                                  double (&out)[NR]) {
+// NR rows of X times kron(w) at once: the lanes of a warp stride over the 16-byte column groups and keep H * NR
+// loads in flight (a load costs its latency, not its bytes); out[i] = this LANE's share of row i's dot product (the
+// caller folds the lanes once per row, after all coupled tensors).  xr[i] points at a row in the shared-memory cache
+// or in global memory (generic loads).  kron(w) was written by another CTA earlier in this launch: plain loads
+// (ordered by the grid barrier), never the non-coherent path.
+template <typename XT, bool MASKED, int NR, int H>
+__device__ __forceinline__ void resident_row_dots(const XT* const (&xr)[NR], int pitch, const double* wk, int lane, double (&out)[NR]) {
     constexpr int VEC = RVec<XT>::N;
     using V = typename RVec<XT>::type;
     double acc[NR][2];
+    const XT* px[NR];  // this lane's position in every row: the pointers advance, the loads of a step use constant offsets
 #pragma unroll
-    for (int i = 0; i < NR; ++i) acc[i][0] = acc[i][1] = 0.0;
-    int c = lane * VEC;
-    for (; c + 32 * VEC < pitch; c += 2 * 32 * VEC) {
-        RPack<XT> in[NR][2];
+    for (int i = 0; i < NR; ++i) {
+        acc[i][0] = acc[i][1] = 0.0;
+        px[i] = xr[i] + lane * VEC;
+    }
+    const double* pw = wk + lane * VEC;
+    int left = pitch / VEC - lane;  // column groups from this lane's first one to the end of the row
+    for (; left > (H - 1) * 32; left -= H * 32) {
+        RPack<XT> in[NR][H];
 #pragma unroll
-        for (int i = 0; i < NR; ++i)
+        for (int h = 0; h < H; ++h)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) in[i][h].v = *reinterpret_cast<const V*>(xr[i] + c + h * 32 * VEC);
+            for (int i = 0; i < NR; ++i) in[i][h].v = *reinterpret_cast<const V*>(px[i] + h * 32 * VEC);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < H; ++h)
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const double w = wk[c + h * 32 * VEC + j];
+                const double w = pw[h * 32 * VEC + j];
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
                     XT xs = in[i][h].e[j];
-                    if (masked && !(xs == xs)) xs = (XT)0;
+                    if (MASKED && !(xs == xs)) xs = (XT)0;
                     acc[i][j & 1] = fma((double)xs, w, acc[i][j & 1]);
                 }
             }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) px[i] += H * 32 * VEC;
+        pw += H * 32 * VEC;
     }
-    for (; c < pitch; c += 32 * VEC) {
+    for (; left > 0; left -= 32) {
         RPack<XT> in[NR];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) in[i].v = *reinterpret_cast<const V*>(xr[i] + c);
+        for (int i = 0; i < NR; ++i) in[i].v = *reinterpret_cast<const V*>(px[i]);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            const double w = wk[c + j];
+            const double w = pw[j];
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 XT xs = in[i].e[j];
-                if (masked && !(xs == xs)) xs = (XT)0;
+                if (MASKED && !(xs == xs)) xs = (XT)0;
                 acc[i][j & 1] = fma((double)xs, w, acc[i][j & 1]);
             }
         }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) px[i] += 32 * VEC;
+        pw += 32 * VEC;
     }
 #pragma unroll
     for (int i = 0; i < NR; ++i) out[i] = acc[i][0] + acc[i][1];
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1)
-#pragma unroll
-        for (int i = 0; i < NR; ++i) out[i] += __shfl_xor_sync(0xffffffffu, out[i], m);
 }
+
+// Probe builds (-DTPLS_PROBE): clock64 deltas of thread 0 of CTA 0 inside the phases of the resident loop
+#ifdef TPLS_PROBE
+__device__ long long g_fine[32];
+#define FINE_DECL long long fine_t = clock64()
+#define FINE(i)                                                         \
+    do {                                                                \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                      \
+            const long long fine_now = clock64();                       \
+            g_fine[i] += fine_now - fine_t;                             \
+            fine_t = fine_now;                                          \
+        }                                                               \
+    } while (0)
+#else
+#define FINE_DECL
+#define FINE(i)
+#endif
 
 // Where the rows of a CTA's block live: the first n_cached of them in shared memory, the rest in global memory.
 // Rows are addressed by their index inside the block (32-bit arithmetic).
@@ -989,10 +1022,72 @@ __device__ __forceinline__ void resident_u_chunk(double* u_s, const RowSrc<doubl
     __syncthreads();
 }
 
+// n rows starting at `base` (all in shared memory or all in global memory), their u in `u`, into a thread's
+// accumulators.  Every row lane takes a CONTIGUOUS run of the rows: one pointer that advances, constant offsets for the
+// RU rows of a step (their loads are issued before any of them is used), u in consecutive shared-memory words.
+template <typename XT, bool MASKED, int KC, int RU>
+__device__ __forceinline__ void resident_contract_rows(const XT* base, const double* u, int n, int pitch, int n_cg, int lpr, int rpt,
+                                                       int cl, int rl, double (&zacc)[KC][RVec<XT>::N]) {
+    constexpr int VEC = RVec<XT>::N;
+    using V = typename RVec<XT>::type;
+    const int per = (n + rpt - 1) / rpt;
+    int r = rl * per;
+    const int r_end = min(n, r + per);
+    if (r >= r_end) return;
+    const XT* p = base + (size_t)((unsigned)r * (unsigned)pitch) + cl * VEC;
+    const double* up = u + r;
+    for (; r + RU <= r_end; r += RU) {
+        double uu[RU];
+#pragma unroll
+        for (int i = 0; i < RU; ++i) uu[i] = up[i];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (cl + k * lpr < n_cg) {
+                RPack<XT> in[RU];
+#pragma unroll
+                for (int i = 0; i < RU; ++i) in[i].v = *reinterpret_cast<const V*>(p + (size_t)i * pitch + k * lpr * VEC);
+#pragma unroll
+                for (int i = 0; i < RU; ++i)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        XT xs = in[i].e[j];
+                        if (MASKED && !(xs == xs)) xs = (XT)0;
+                        zacc[k][j] = fma((double)xs, uu[i], zacc[k][j]);
+                    }
+            }
+        }
+        p += (size_t)RU * pitch;
+        up += RU;
+    }
+    if (r < r_end) {  // the last, partial step of the run: rows past its end repeat its first row with u = 0
+        const int nv = r_end - r;
+        double uu[RU];
+#pragma unroll
+        for (int i = 0; i < RU; ++i) uu[i] = i < nv ? up[i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (cl + k * lpr < n_cg) {
+                RPack<XT> in[RU];
+#pragma unroll
+                for (int i = 0; i < RU; ++i)
+                    in[i].v = *reinterpret_cast<const V*>(p + (i < nv ? (size_t)i * pitch : (size_t)0) + k * lpr * VEC);
+#pragma unroll
+                for (int i = 0; i < RU; ++i)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        XT xs = in[i].e[j];
+                        if (MASKED && !(xs == xs)) xs = (XT)0;
+                        zacc[k][j] = fma((double)xs, uu[i], zacc[k][j]);
+                    }
+            }
+        }
+    }
+}
+
 // Z partials of this CTA's rows for one tensor: zpart_row[c] = sum_r x[r, c] * u[r], u[r] = Y[r,:] . q
-// One loop, no tail: a thread's RU rows are loaded together, rows past the end of the block repeat its last row with
-// u = 0 (a serial tail cost one L2 round trip per leftover row).
-template <typename XT, int KC>
+// Per chunk of u: the rows still in L2 first, with twice the rows of a thread in flight (their loads are the long
+// ones), then the rows in the shared-memory cache.
+template <typename XT, bool MASKED, int KC>
 __device__ __forceinline__ void resident_contract_kc(const ResidentTensor& X, const RowSrc<XT>& src, const RowSrc<double>& ysrc, int m,
                                                      const double* q_s, int nblk, double* u_s, int& u_lo, double* zrow, double* scr) {
     constexpr int VEC = RVec<XT>::N;
@@ -1001,49 +1096,28 @@ __device__ __forceinline__ void resident_contract_kc(const ResidentTensor& X, co
     while (lpr < n_cg && lpr < NTH) lpr <<= 1;
     const int rpt = NTH / lpr;
     const int cl = threadIdx.x & (lpr - 1), rl = threadIdx.x / lpr;
-    const bool masked = X.masked != 0;
     double zacc[KC][VEC];
 #pragma unroll
     for (int k = 0; k < KC; ++k)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) zacc[k][j] = 0.0;
-    using V = typename RVec<XT>::type;
     constexpr int RU = KC <= 2 ? 8 : 4;  // rows in flight per thread: the loads of a group are issued before any of them is used
+    FINE_DECL;
     for (int c_lo = 0; c_lo < nblk; c_lo += kResidentUChunk) {
         const int c_hi = min(nblk, c_lo + kResidentUChunk);
         if (u_lo != c_lo) {
             resident_u_chunk(u_s, ysrc, m, q_s, c_lo, c_hi);
             u_lo = c_lo;
         }
-        for (int r = c_lo + rl; r < c_hi; r += RU * rpt) {
-            double u[RU];
-            const XT* xr[RU];
-#pragma unroll
-            for (int i = 0; i < RU; ++i) {
-                const int ri = r + i * rpt;
-                const bool in = ri < c_hi;
-                xr[i] = src.row(in ? ri : c_hi - 1);
-                u[i] = in ? u_s[ri - c_lo] : 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const int cg = cl + k * lpr;
-                if (cg < n_cg) {
-                    RPack<XT> in[RU];
-#pragma unroll
-                    for (int i = 0; i < RU; ++i) in[i].v = *reinterpret_cast<const V*>(xr[i] + cg * VEC);
-#pragma unroll
-                    for (int i = 0; i < RU; ++i)
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            XT xs = in[i].e[j];
-                            if (masked && !(xs == xs)) xs = (XT)0;
-                            zacc[k][j] = fma((double)xs, u[i], zacc[k][j]);
-                        }
-                }
-            }
-        }
+        FINE(8);
+        const int split = min(c_hi, max(c_lo, src.n_cached));  // [c_lo, split) cached, [split, c_hi) in L2
+        resident_contract_rows<XT, MASKED, KC, (KC == 1 ? 2 * RU : RU)>(src.gbase + (size_t)((unsigned)split * (unsigned)src.pitch),
+                                                                        u_s + (split - c_lo), c_hi - split, src.pitch, n_cg, lpr, rpt,
+                                                                        cl, rl, zacc);
+        resident_contract_rows<XT, MASKED, KC, RU>(src.cbase + (size_t)((unsigned)c_lo * (unsigned)src.pitch), u_s, split - c_lo, src.pitch,
+                                                   n_cg, lpr, rpt, cl, rl, zacc);
     }
+    FINE(9);
     if (rpt == 1) {
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
@@ -1069,18 +1143,106 @@ __device__ __forceinline__ void resident_contract_kc(const ResidentTensor& X, co
         }
         __syncthreads();
     }
+    FINE(10);
+}
+
+template <typename XT, bool MASKED>
+__device__ __forceinline__ void resident_contract_m(const ResidentTensor& X, const RowSrc<XT>& src, const RowSrc<double>& ysrc, int m,
+                                                    const double* q_s, int nblk, double* u_s, int& u_lo, double* zrow, double* scr) {
+    const int n_cg = X.pitch / RVec<XT>::N;
+    if (n_cg <= NTH)
+        resident_contract_kc<XT, MASKED, 1>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
+    else if (n_cg <= 2 * NTH)
+        resident_contract_kc<XT, MASKED, 2>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
+    else
+        resident_contract_kc<XT, MASKED, kResidentKc>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
 }
 
 template <typename XT>
 __device__ __forceinline__ void resident_contract(const ResidentTensor& X, const RowSrc<XT>& src, const RowSrc<double>& ysrc, int m,
                                                   const double* q_s, int nblk, double* u_s, int& u_lo, double* zrow, double* scr) {
-    const int n_cg = X.pitch / RVec<XT>::N;
-    if (n_cg <= NTH)
-        resident_contract_kc<XT, 1>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
-    else if (n_cg <= 2 * NTH)
-        resident_contract_kc<XT, 2>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
+    if (X.masked)
+        resident_contract_m<XT, true>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
     else
-        resident_contract_kc<XT, kResidentKc>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
+        resident_contract_m<XT, false>(X, src, ysrc, m, q_s, nblk, u_s, u_lo, zrow, scr);
+}
+
+// Projection of the rows [lo, hi) of a CTA's block: the rows are dealt to the warps round-robin, NR rows of a warp at
+// a time with H column groups per row in flight.  Complete tensors add up per lane and are folded over the lanes once
+// per row; a masked tensor is folded on its own (its rescale p / observed is per row and tensor, missingvals.py:37).
+// Writes the scores, adds the rows' share of q = Y't to qacc (lane i < pitch_y: response i).
+template <int NR, int H>
+__device__ __forceinline__ void resident_project_rows(const ResidentArgs& a, int lo, int hi, long long r_lo, const unsigned char* cache,
+                                                      int n_cached, const double* w_s, const RowSrc<double>& ysrc, int warp, int lane,
+                                                      double& qacc) {
+    const int L = a.n_tensors;
+    const double inv_l = 1.0 / (double)L;
+    const bool pow2 = (L & (L - 1)) == 0;
+    for (int k0 = lo + warp; k0 < hi; k0 += NR * NWARP) {
+        int ks[NR];
+        double tl[NR], td[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int k = k0 + i * NWARP;
+            ks[i] = k < hi ? k : k0;  // rows past the end repeat the warp's first row (results dropped)
+            tl[i] = td[i] = 0.0;
+        }
+        size_t coff = 0;
+        int woff = 0;
+        for (int l = 0; l < L; ++l) {
+            const ResidentTensor& X = a.x[l];
+            const double* wk = w_s != nullptr ? w_s + woff : X.wkron;
+            double v[NR];
+            if (X.dtype == 0) {
+                const RowSrc<float> src{reinterpret_cast<const float*>(X.x) + (size_t)r_lo * X.pitch,
+                                        reinterpret_cast<const float*>(cache + coff), n_cached, X.pitch};
+                const float* xr[NR];
+#pragma unroll
+                for (int i = 0; i < NR; ++i) xr[i] = src.row(ks[i]);
+                if (X.masked)
+                    resident_row_dots<float, true, NR, H>(xr, X.pitch, wk, lane, v);
+                else
+                    resident_row_dots<float, false, NR, H>(xr, X.pitch, wk, lane, v);
+                coff += (size_t)a.cache_rows * X.pitch * 4;
+            } else {
+                const RowSrc<double> src{reinterpret_cast<const double*>(X.x) + (size_t)r_lo * X.pitch,
+                                         reinterpret_cast<const double*>(cache + coff), n_cached, X.pitch};
+                const double* xr[NR];
+#pragma unroll
+                for (int i = 0; i < NR; ++i) xr[i] = src.row(ks[i]);
+                if (X.masked)
+                    resident_row_dots<double, true, NR, H>(xr, X.pitch, wk, lane, v);
+                else
+                    resident_row_dots<double, false, NR, H>(xr, X.pitch, wk, lane, v);
+                coff += (size_t)a.cache_rows * X.pitch * 8;
+            }
+            woff += X.pitch;
+            if (X.masked) {
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1)
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) td[i] += v[i] / __ldg(X.rowcnt + r_lo + ks[i]) * (double)X.p;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NR; ++i) tl[i] += v[i];
+            }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1)
+#pragma unroll
+            for (int i = 0; i < NR; ++i) tl[i] += __shfl_xor_sync(0xffffffffu, tl[i], m);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int k = k0 + i * NWARP;
+            if (k >= hi) break;
+            double ti = tl[i] + td[i];
+            if (L > 1) ti = pow2 ? ti * inv_l : ti / (double)L;
+            if (lane == 0) a.t_out[r_lo + k] = ti;
+            if (lane < a.pitch_y) qacc = fma(ysrc.row(k)[lane], ti, qacc);
+        }
+    }
 }
 
 __device__ __forceinline__ long long global_ns() {
@@ -1119,6 +1281,8 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
     const int n_cached = (int)max(0ll, min((long long)a.cache_rows, r_hi - r_lo));
     size_t y_cache_off = 0;  // tensor l starts cache_rows * (bytes per row of the tensors before it) into the cache; Y is last
     for (int l = 0; l < L; ++l) y_cache_off += (size_t)a.cache_rows * a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
+    int w_total = 0;
+    for (int l = 0; l < L; ++l) w_total += a.x[l].pitch;
     unsigned int bar_gen = 0;
     if (tid < 8) qp_s[tid] = tid < M ? a.q_prev[tid] : 0.0;
     if (tid >= 32 && tid < 32 + M * M) gram_s[tid - 32] = a.gram[tid - 32];
@@ -1204,54 +1368,24 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
         if (trip == 0 && n_cached > 0) mbar_wait(&cache_bar, 0);  // the cached rows have landed
         {
             double qacc = 0.0;  // lane i < pitch_y: response i
-            const double inv_l = 1.0 / (double)L;
-            const bool pow2 = (L & (L - 1)) == 0;
-            constexpr int NR = 4;  // rows per warp at once
-            for (int k0 = warp; k0 < nblk; k0 += NR * NWARP) {
-                int ks[NR];
-                double t[NR];
-#pragma unroll
-                for (int i = 0; i < NR; ++i) {
-                    ks[i] = min(k0 + i * NWARP, nblk - 1);
-                    t[i] = 0.0;
-                }
-                size_t coff = 0;
+            const double* w_s = nullptr;
+            if (w_total <= (int)(kResidentScratch / sizeof(double))) {
+                // kron(w) of all tensors into shared memory: one L2 round trip for the CTA instead of one per warp and slice
+                int woff = 0;
                 for (int l = 0; l < L; ++l) {
-                    const ResidentTensor& X = a.x[l];
-                    double v[NR];
-                    if (X.dtype == 0) {
-                        const RowSrc<float> src{reinterpret_cast<const float*>(X.x) + (size_t)r_lo * X.pitch,
-                                                reinterpret_cast<const float*>(cache + coff), n_cached, X.pitch};
-                        const float* xr[NR];
-#pragma unroll
-                        for (int i = 0; i < NR; ++i) xr[i] = src.row(ks[i]);
-                        resident_row_dots<float, NR>(xr, X.pitch, X.wkron, X.masked != 0, lane, v);
-                        coff += (size_t)a.cache_rows * X.pitch * 4;
-                    } else {
-                        const RowSrc<double> src{reinterpret_cast<const double*>(X.x) + (size_t)r_lo * X.pitch,
-                                                 reinterpret_cast<const double*>(cache + coff), n_cached, X.pitch};
-                        const double* xr[NR];
-#pragma unroll
-                        for (int i = 0; i < NR; ++i) xr[i] = src.row(ks[i]);
-                        resident_row_dots<double, NR>(xr, X.pitch, X.wkron, X.masked != 0, lane, v);
-                        coff += (size_t)a.cache_rows * X.pitch * 8;
-                    }
-#pragma unroll
-                    for (int i = 0; i < NR; ++i) {
-                        if (X.masked) v[i] = v[i] / __ldg(X.rowcnt + r_lo + ks[i]) * (double)X.p;  // missingvals.py:37
-                        t[i] = l == 0 ? v[i] : t[i] + v[i];
-                    }
+                    const double* wk = a.x[l].wkron;
+                    for (int i = tid; i < a.x[l].pitch; i += NTH) scr[woff + i] = wk[i];
+                    woff += a.x[l].pitch;
                 }
-#pragma unroll
-                for (int i = 0; i < NR; ++i) {
-                    const int k = k0 + i * NWARP;
-                    if (k >= nblk) break;
-                    double ti = t[i];
-                    if (L > 1) ti = pow2 ? ti * inv_l : ti / (double)L;
-                    if (lane == 0) a.t_out[r_lo + k] = ti;
-                    if (lane < a.pitch_y) qacc = fma(ysrc.row(k)[lane], ti, qacc);
-                }
+                __syncthreads();
+                w_s = scr;
             }
+            FINE_DECL;
+            // rows still in L2 first and with whole rows in flight (their loads are the long ones), then the cached rows
+            resident_project_rows<2, 8>(a, n_cached, nblk, r_lo, cache, n_cached, w_s, ysrc, warp, lane, qacc);
+            FINE(0);
+            resident_project_rows<4, 2>(a, 0, n_cached, r_lo, cache, n_cached, w_s, ysrc, warp, lane, qacc);
+            FINE(1);
             if (lane < 8) qw_s[warp][lane] = lane < a.pitch_y ? qacc : 0.0;
             __syncthreads();
             if (tid < 8) {
@@ -1260,6 +1394,7 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
                 for (int w = 0; w < NWARP; ++w) t += qw_s[w][tid];
                 a.qpart[(size_t)b * 8 + tid] = t;
             }
+            FINE(5);
         }
         RES_MARK(2);
         grid_sync(a.bar, G, bar_gen);
@@ -1389,6 +1524,18 @@ cudaError_t launch_cov_loop(const CovLoopArgs& a, size_t smem_bytes, bool use_sm
 }
 
 size_t resident_min_smem() { return kResidentScratch; }
+
+int resident_fine_stamps(long long* out32) {
+#ifdef TPLS_PROBE
+    if (cudaMemcpyFromSymbol(out32, g_fine, sizeof(long long) * 32) != cudaSuccess) return 0;
+    long long z[32] = {};
+    cudaMemcpyToSymbol(g_fine, z, sizeof z);
+    return 1;
+#else
+    (void)out32;
+    return 0;
+#endif
+}
 
 cudaError_t launch_resident_loop(const ResidentArgs& a_in, int n_ctas, size_t r1_smem_bytes, cudaStream_t s) {
     ResidentArgs a = a_in;

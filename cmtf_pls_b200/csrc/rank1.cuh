@@ -117,6 +117,7 @@ struct ResidentArgs {
 // smem_bytes: rank-1 workspace (0 when it lives in global memory); the launcher adds what the other phases need
 cudaError_t launch_resident_loop(const ResidentArgs& a, int n_ctas, size_t r1_smem_bytes, cudaStream_t s);
 size_t resident_min_smem();
+int resident_fine_stamps(long long* out32);  // probe builds (-DTPLS_PROBE): cycles per sub-phase, summed; 0 otherwise
 
 // doubles of workspace a task needs, and the Gram order it implies
 size_t rank1_workspace_doubles(int nmodes, const int* dims, int* nmax_out, int* zs_len_out, int* mt_len_out,
