@@ -679,7 +679,7 @@ static int layout_fit(tpls_handle h, int L, int R) {
     TRY(dev_alloc(h, (void**)&h->grampart, sizeof(double) * 148 * 64, tr));
     TRY(dev_alloc(h, (void**)&h->q_prev, sizeof(double) * 8, tr));
     TRY(dev_alloc(h, (void**)&h->qpart, sizeof(double) * 2048 * kMaxFusedResp, tr));
-    TRY(dev_alloc(h, (void**)&h->res_bar, sizeof(unsigned int) * 4, tr));  // (the slab is zeroed when it is laid out)
+    TRY(dev_alloc(h, (void**)&h->res_bar, sizeof(unsigned int) * 32 * (h->sm_count + 1), tr));  // (the slab is zeroed when it is laid out)
     h->res_stamps = nullptr;
     if (tune_env("TPLS_RESIDENT_STAMPS", 0)) TRY(dev_alloc(h, (void**)&h->res_stamps, sizeof(long long) * 16, tr));
     TRY(dev_alloc(h, (void**)&h->e0vec, sizeof(double) * kMaxFusedResp, tr));

@@ -873,26 +873,24 @@ __global__ void __launch_bounds__(kRank1Threads, 1) cov_loop_kernel(const __grid
 // ---------------------------------------------------------------------------------------------------------------
 constexpr size_t kResidentScratch = 20 * 1024;  // bytes of dynamic shared memory the non-rank-1 phases use
 
-// Grid-wide barrier of co-resident CTAs (one per SM): arrivals counter + generation word in global memory.  The
-// generation is tracked in a register (read once at kernel start; every CTA takes part in every barrier), so an
-// arrival is ONE atomic with release/acquire semantics and the wait one polled word -- no load of the generation and
-// no separate fence ahead of the atomic.  The last arriver resets the counter before it publishes the next generation.
+// Grid-wide barrier of co-resident CTAs (one per SM).  Every CTA owns a flag word on its own 128-byte line
+// (bar[32 * (c + 1)]); bar[0] holds the generation the previous launch ended on.  Arriving = one release store of the
+// next generation into the own flag; waiting = thread c polls the flag of CTA c (relaxed loads, one fence after the
+// loop), then the CTA barrier joins them.  No atomic round trip and no counter to reset: an arrival is visible to a
+// poller one store and one load after the CTA's own writes have drained.
 __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int n_ctas, unsigned int& gen) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int old;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
-        if (old == n_ctas - 1) {
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1u) : "memory");
-        } else {
-            unsigned int g2;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 1) : "memory");
-            } while (g2 == gen);
-        }
-    }
     ++gen;
+    if (threadIdx.x == 0)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 32 * (blockIdx.x + 1)), "r"(gen) : "memory");
+    if (threadIdx.x < n_ctas) {
+        const unsigned int* f = bar + 32 * (threadIdx.x + 1);
+        unsigned int v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        } while ((int)(v - gen) < 0);
+        __threadfence();
+    }
     __syncthreads();
 }
 
@@ -1286,9 +1284,9 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
     unsigned int bar_gen = 0;
     if (tid < 8) qp_s[tid] = tid < M ? a.q_prev[tid] : 0.0;
     if (tid >= 32 && tid < 32 + M * M) gram_s[tid - 32] = a.gram[tid - 32];
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bar_gen) : "l"(a.bar) : "memory");  // every thread tracks it
     if (tid == 0) {
         stop_s = 0;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(bar_gen) : "l"(a.bar + 1) : "memory");
         mbar_init(&cache_bar, 1);
         fence_mbar_init();
     }
@@ -1487,6 +1485,7 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
             a.q_prev[tid] = q_s[tid];
         }
         if (tid == 0) {
+            a.bar[0] = bar_gen;  // the generation this launch ends on (every CTA has passed its last barrier)
             a.ctrl->done_trip = done_trip;
             a.ctrl->trips_taken = trip;
             a.ctrl->last_d2 = d2_last;
@@ -1539,7 +1538,7 @@ int resident_fine_stamps(long long* out32) {
 
 cudaError_t launch_resident_loop(const ResidentArgs& a_in, int n_ctas, size_t r1_smem_bytes, cudaStream_t s) {
     ResidentArgs a = a_in;
-    if (a.n_tensors < 1 || a.n_tensors > kMaxTensors || a.m > 8 || a.pitch_y > 8 || n_ctas < a.n_tensors) return cudaErrorInvalidValue;
+    if (a.n_tensors < 1 || a.n_tensors > kMaxTensors || a.m > 8 || a.pitch_y > 8 || n_ctas < a.n_tensors || n_ctas > kRank1Threads) return cudaErrorInvalidValue;
     const bool in_smem = a.r1_in_smem != 0 && r1_smem_bytes > 0;
     auto kern = in_smem ? resident_loop_kernel<true> : resident_loop_kernel<false>;
     // dynamic shared memory: [rank-1 workspace or the scratch of the other phases | row cache]
