@@ -1192,7 +1192,8 @@ static int trip_body(tpls_handle h, const StreamPlan& P, int a, unsigned long lo
 }
 
 // Can the inner trips of a component run in the resident loop kernel (rank1.cuh)?  One GPU, the Y side fused, rows
-// narrow enough for its thread layout, and a working set that stays in L2 (TPLS_RESIDENT_MB, default 80; the
+// narrow enough for its thread layout, and a working set of at most TPLS_RESIDENT_MB (default 256: measured on one
+// B200, tools/resident_sweep.py -- 20 MB 39 vs 51 us per trip, 82 MB 51 vs 71, 164 MB 97 vs 110, 328 MB 168 vs 173; the
 // streaming kernels win beyond that).  TPLS_RESIDENT=0 turns it off, =1 forces it whatever the size.  Profiled fits
 // keep the streaming kernels (their per-class timing is what the profile is for) unless forced.
 static int resident_ctas(tpls_handle h, const StreamPlan& P) {
@@ -1205,7 +1206,7 @@ static int resident_ctas(tpls_handle h, const StreamPlan& P) {
         if (t.pitch / (16 / t.elem) > kRank1Threads * kResidentKc) return 0;
         bytes += (double)h->n * t.pitch * t.elem;
     }
-    if (force != 1 && bytes > 1048576.0 * tune_env("TPLS_RESIDENT_MB", 80)) return 0;
+    if (force != 1 && bytes > 1048576.0 * tune_env("TPLS_RESIDENT_MB", 256)) return 0;
     if (P.r1_use_smem && P.r1_smem > 200 * 1024) return 0;
     const long long want = (h->n + 15) / 16;  // at least 16 samples per CTA
     return (int)std::max<long long>(P.L, std::min<long long>(h->sm_count, want));
@@ -1425,7 +1426,7 @@ static unsigned long long graph_key_of(tpls_handle h, int L, int R, double tol, 
     KEY(h->y_src); KEY(h->y_work); KEY(h->row_w); KEY(h->slab); KEY(h->slab_need);
     const bool pdl = pdl_enabled();
     KEY(pdl);
-    const int res_switch = tune_env("TPLS_RESIDENT", -1), res_mb = tune_env("TPLS_RESIDENT_MB", 80);  // resident_ctas()
+    const int res_switch = tune_env("TPLS_RESIDENT", -1), res_mb = tune_env("TPLS_RESIDENT_MB", 256);  // resident_ctas()
     KEY(res_switch); KEY(res_mb);
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
