@@ -1225,6 +1225,8 @@ static int run_resident(tpls_handle h, const StreamPlan& P, int a, int n_ctas) {
     ra.qvec = h->qvec;
     ra.q_prev = h->q_prev;
     ra.gram = h->arena + h->off_gram_y;
+    ra.grampart = h->grampart;
+    ra.u_out = h->U + (size_t)a * h->n;
     ra.ctrl = h->ctrl;
     ra.tol = P.tol;
     ra.max_iter = P.max_iter;
@@ -1383,14 +1385,16 @@ static int fit_streaming(tpls_handle h, const StreamPlan& P) {
         snprintf(nm, sizeof nm, "component %d", a);
         NvtxRange nvtx_comp(nm);
         double* Ua = h->U + (size_t)a * n;
-        {
+        // the resident loop forms Y'Y and u = Y q itself and leaves the control block as the streaming loop would
+        const bool resident = resident_ctas(h, P) > 0;
+        if (!resident) {
             ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
             CK(launch_reset_ctrl(h->ctrl, st));
             h->stats.kernel_launches++;
         }
-        if (P.fused) TRY(gram_y(h));
+        if (P.fused && !resident) TRY(gram_y(h));
         TRY(run_loop(h, P, a));
-        if (P.fused) {
+        if (P.fused && !resident) {
             // u = Y q of the last trip (tpls.py:102): inside the loop it only ever exists row by row
             RowPassArgs r{};
             r.g = h->gy_row;

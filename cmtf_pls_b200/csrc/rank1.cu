@@ -1283,7 +1283,6 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
     for (int l = 0; l < L; ++l) w_total += a.x[l].pitch;
     unsigned int bar_gen = 0;
     if (tid < 8) qp_s[tid] = tid < M ? a.q_prev[tid] : 0.0;
-    if (tid >= 32 && tid < 32 + M * M) gram_s[tid - 32] = a.gram[tid - 32];
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bar_gen) : "l"(a.bar) : "memory");  // every thread tracks it
     if (tid == 0) {
         stop_s = 0;
@@ -1307,6 +1306,26 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
         }
     }
     const int nblk = (int)(r_hi - r_lo);  // rows of this CTA's block
+    {
+        // this CTA's share of Y'Y (the stop test needs dq^T Y'Y dq): entry e = (i, j) on NTH / m^2 row lanes, the lanes
+        // folded in order; every CTA folds the partials of all CTAs before the first stop test
+        const int MM = M * M, nl = NTH / MM;
+        const int e = tid % MM, ln = tid / MM;
+        double acc = 0.0;
+        if (ln < nl) {
+            const double* yb = a.y + (size_t)r_lo * a.pitch_y;
+            const int i = e / M, j = e - i * M;
+            for (int k = ln; k < nblk; k += nl) acc = fma(yb[(size_t)k * a.pitch_y + i], yb[(size_t)k * a.pitch_y + j], acc);
+            scr[ln * MM + e] = acc;
+        }
+        __syncthreads();
+        if (tid < MM) {
+            double t = 0.0;
+            for (int q = 0; q < nl; ++q) t += scr[q * MM + tid];
+            a.grampart[(size_t)b * 64 + tid] = t;
+        }
+        __syncthreads();
+    }
     const RowSrc<double> ysrc{a.y + (size_t)r_lo * a.pitch_y, reinterpret_cast<const double*>(cache + y_cache_off), n_cached, a.pitch_y};
     int trip = 0;
     double d2_last = 0.0;
@@ -1400,6 +1419,31 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
         // ---- q = Y't / ||.||, stop test dq^T (Y'Y) dq (tpls.py:100-107): every CTA folds the same partials in the
         //      same order and takes the same decision; CTA 0 publishes it ----
         {
+            if (trip == 0) {
+                // Y'Y = sum of the CTAs' partials (written before the first grid barrier), 64 entries x 8 part-groups
+                const int e = tid & 63, grp8 = tid >> 6;
+                double g0 = 0.0, g1 = 0.0;
+                if (e < M * M) {
+                    int pb = grp8;
+                    for (; pb + 8 < G; pb += 16) {
+                        const double v0 = __ldcg(a.grampart + (size_t)pb * 64 + e);
+                        const double v1 = __ldcg(a.grampart + (size_t)(pb + 8) * 64 + e);
+                        g0 += v0;
+                        g1 += v1;
+                    }
+                    if (pb < G) g0 += __ldcg(a.grampart + (size_t)pb * 64 + e);
+                }
+                u_s[grp8 * 64 + e] = g0 + g1;
+                __syncthreads();
+                if (tid < M * M) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) t += u_s[k * 64 + tid];
+                    gram_s[tid] = t;
+                    if (b == 0) a.gram[tid] = t;
+                }
+                __syncthreads();
+            }
             const int col = tid & 7, grp = tid >> 3;  // 8 responses x 64 part-groups (4 per warp)
             double t0 = 0.0, t1 = 0.0;
             int pb = grp;
@@ -1478,6 +1522,15 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
     }
     if (stamping) a.stamps[9] += trip;
 #undef RES_MARK
+    // u = Y q of the last trip for this CTA's rows (tpls.py:102)
+    for (int k = tid; k < nblk; k += NTH) {
+        const double* yr = ysrc.row(k);
+        double ui = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < M) ui = fma(yr[q], q_s[q], ui);
+        a.u_out[r_lo + k] = ui;
+    }
     if (b == 0) {
         if (tid < a.pitch_y) a.qvec[tid] = tid < M ? q_s[tid] : 0.0;
         if (tid < M) {

@@ -102,7 +102,9 @@ struct ResidentArgs {
     double* qcol;           // out: unit q of the last trip [m]
     double* qvec;           // out: the same, zero-padded [pitch_y]
     double* q_prev;         // in/out [m] (what the stop test of the streaming loop keeps between launches)
-    const double* gram;     // Y'Y [m][m]
+    double* gram;           // out: Y'Y [m][m] of the current Y (formed in the launch: per-CTA partials, folded by every CTA)
+    double* grampart;       // [CTAs][64] per-CTA partials of Y'Y
+    double* u_out;          // out: u = Y q of the last trip [n_rows] (tpls.py:102; inside the loop it only exists row by row)
     Ctrl* ctrl;
     double tol;
     int max_iter;
