@@ -215,42 +215,23 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
             const long long r0 = tile * g.tile_rows;
             int rows = tile_rows_of(g, tile, n_tiles);
             if (dbg & (2 | 16)) rows = 0;
-            // what the epilogues of the tile's rows read from global memory is requested BEFORE the wait, so that its
-            // latency (microseconds while the HBM is saturated) overlaps the consumers' work on the tile: lane i
-            // holds the values of row i of the tile (of every further 32 rows: refilled when the rounds get there) and
-            // hands them to the lane that finishes the row by a shuffle.  (Until round 2 only the first round was
-            // prefetched: tiles of four 8 KB rows took a second round whose loads of the observed count and of the
-            // row of Y cost a DRAM round trip each -- masked projection of 100k x 2048 fp32: 4.5 TB/s.)
+            // what the first round's epilogue reads from global memory is requested BEFORE the wait, so that
+            // its latency (microseconds while the HBM is saturated) overlaps the consumers' work on the tile
             double old_pf = 0.0, cnt_pf = 1.0;
-            if (lane < rows && !slabbed) {
+            if (gl == 0 && rg < rows && !slabbed) {
                 // (t is read before it is written even when the epilogue does not use the old value: measured on
                 //  several B200s the first projection of a trip, whose stores missed in L2, took 2.50 ms per 16.4 GB
                 //  and 2.23 ms with this load in front of the store; on other boxes it made no difference)
-                asm volatile("ld.global.f64 %0, [%1];" : "=d"(old_pf) : "l"(a.t_out + r0 + lane));
-                if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + lane];
-                if (want_q) load_y_row(a, r0 + lane, y_pf);
+                asm volatile("ld.global.f64 %0, [%1];" : "=d"(old_pf) : "l"(a.t_out + r0 + rg));
+                if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + rg];
+                if (want_q) load_y_row(a, r0 + rg, y_pf);
             }
             mbar_wait(&red_full[sl], ph);
             const double* sp = slots + (size_t)sl * slot_doubles;
             const double* cp = sp + (size_t)g.tile_rows * lpr;
             for (int rb = 0; rb < rows; rb += rows_per_round) {
                 const int r = rb + rg;
-                if (rb != 0 && (rb & 31) == 0 && !slabbed) {  // the next 32 rows of a tall tile
-                    old_pf = 0.0;
-                    cnt_pf = 1.0;
-                    if (rb + lane < rows) {
-                        if (need_old) old_pf = a.t_out[r0 + rb + lane];
-                        if (MASKED && !COUNT) cnt_pf = a.rowcnt[r0 + rb + lane];
-                        if (want_q) load_y_row(a, r0 + rb + lane, y_pf);
-                    }
-                }
-                // this round's rows' values, from the lanes that hold them (every lane takes part)
-                const int src = r & 31;
-                const double old_r = need_old ? __shfl_sync(0xffffffffu, old_pf, src) : 0.0;
-                const double cnt_r = (MASKED && !COUNT) ? __shfl_sync(0xffffffffu, cnt_pf, src) : 1.0;
                 double v = 0.0, cnt = 0.0;
-                double nv_q = 0.0;      // the row's final score in the lane that finished it
-                bool fin_q = false;
                 if (r < rows) {
                     const double* rowp = sp + (size_t)r * lpr;
                     const double* rowc = cp + (size_t)r * lpr;
@@ -289,19 +270,16 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                                 cnt -= pads;
                                 if (a.rowcnt != nullptr) a.rowcnt[grow] = cnt;
                             } else {
-                                cnt = cnt_r;
+                                cnt = rb == 0 ? cnt_pf : a.rowcnt[grow];
                             }
                             v = v / cnt * p_total;  // missingvals.py:37: (dot / n_obs) * P, NaN if n_obs == 0
                         }
-                        nv_q = row_epilogue(a, grow, v, old_r, d2);
-                        fin_q = true;
-                    }
-                }
-                if (want_q) {
-#pragma unroll
-                    for (int m = 0; m < kMaxFusedResp; ++m) {
-                        const double ym = __shfl_sync(0xffffffffu, y_pf[m], src);
-                        if (fin_q) qacc[m] = fma(ym, nv_q, qacc[m]);
+                        const double old = !need_old ? 0.0 : (rb == 0 ? old_pf : a.t_out[grow]);
+                        const double nv = row_epilogue(a, grow, v, old, d2);
+                        if (want_q) {
+                            if (rb != 0) load_y_row(a, grow, y_pf);
+                            q_accumulate(qacc, y_pf, nv);
+                        }
                     }
                 }
             }
