@@ -517,6 +517,14 @@ def run_ours(args):
                           "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None}
                       for k, v in prof.items()},
     }
+    # ---- the two small BASELINE configurations (one GPU): their inner trips run in the resident trip loop (DESIGN.md
+    #      §3b), one launch per component; device time of a fit (CUDA events inside the library), best of five ----
+    small = None
+    if world == 1 and not args.quick:
+        try:
+            small = small_configs(local)
+        except Exception as exc:  # noqa: BLE001
+            small = {"error": str(exc)[:200]}
     cpu = None
     if world == 1 and not args.no_cpu:
         Xc, Yc = make_sample_host(CPU_SAMPLE_ROWS)
@@ -542,7 +550,7 @@ def run_ours(args):
                    "launches_per_trip": stats_timed.get("launches_per_trip"), "exchange": stats_timed.get("exchange"),
                    "launches_per_fit": stats_timed.get("kernel_launches"), "exchange_wait": xchg_diag if world > 1 else None,
                    "host_ms_last_fit": host_ms_last,
-                   "covariance_mode": cov, "transform": xform},
+                   "covariance_mode": cov, "transform": xform, "small_configs": small},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "parity_check": parity,
     }
@@ -551,6 +559,45 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_configs(device):
+    """BASELINE configs[0] (20 x 8 x 6, Y 20 x 1, 3 components) and configs[1] (10k x 32 x 16 coupled with 10k x 24, Y 10k x 4,
+    5 components, fp64) on one GPU: synthetic CP-structured data drawn on the device, data resident in HBM."""
+    import torch
+    from cmtf_pls_b200 import ctPLS
+
+    def draw(n, dims_list, m, latent, error, seed):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed)
+        T = torch.randn(n, latent, generator=g, device="cuda", dtype=torch.float64)
+        yf = torch.randn(m, latent, generator=g, device="cuda", dtype=torch.float64)
+        xs = []
+        for dims in dims_list:
+            kr = torch.ones(1, latent, device="cuda", dtype=torch.float64)
+            for d in dims:
+                f = torch.randn(d, latent, generator=g, device="cuda", dtype=torch.float64)
+                kr = (kr[:, None, :] * f[None, :, :]).reshape(-1, latent)
+            x = T @ kr.T + error * torch.randn(n, kr.shape[0], generator=g, device="cuda", dtype=torch.float64)
+            xs.append(x.reshape(n, *dims).contiguous())
+        y = T @ yf.T + error * torch.randn(n, m, generator=g, device="cuda", dtype=torch.float64)
+        return xs, y
+
+    out = {}
+    for name, n, dims_list, m, latent, error, r in (("configs[0]", 20, [(8, 6)], 1, 3, 0.1, 3),
+                                                    ("configs[1]", 10_000, [(32, 16), (24,)], 4, 8, 0.5, 5)):
+        xs, y = draw(n, dims_list, m, latent, error, 7)
+        est = ctPLS(r, device=device)
+        est.fit(xs, y)
+        ms = []
+        for _ in range(5):
+            est.fit(xs, y)
+            ms.append(est.stats_["fit_ms"])
+        trips = int(est.n_iter_.sum())
+        out[name] = {"fit_ms": min(ms), "trips": trips, "us_per_trip": min(ms) / trips * 1e3,
+                     "kernel_launches": int(est.stats_["kernel_launches"]), "resident_loops": int(est.stats_["resident_loops"]),
+                     "components": r}
+    return out
 
 
 def main():
