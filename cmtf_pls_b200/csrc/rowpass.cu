@@ -305,10 +305,13 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
     const int rl = tid / lpr;
     double wreg[CPT][VEC];
     bool cvalid[CPT];
+    int goff[CPT];  // element offset of the thread's k-th column group in a staged row; a group past the end of the row
+                    // reads the row's first group with weights 0 (no branch per group in the row loop)
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int cg = cl + k * lpr;
         cvalid[k] = FULL ? true : (cg * VEC < slab_cols);
+        goff[k] = cvalid[k] ? cg * VEC : 0;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) wreg[k][j] = cvalid[k] ? a.col_w[c0 + cg * VEC + j] : 0.0;
     }
@@ -351,9 +354,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
                 if (live[i]) {
 #pragma unroll
                     for (int k = 0; k < CPT; ++k) {
-                        if (!FULL && !cvalid[k]) continue;
                         const int cg = cl + k * lpr;
-                        in[i][k].v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + cg * VEC);
+                        in[i][k].v = *reinterpret_cast<const typename VecOf<XT>::type*>(tp + (size_t)r * srow + (FULL ? cg * VEC : goff[k]));
                     }
                 }
             }
@@ -375,16 +377,13 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowpass_kernel(const __grid_co
 #pragma unroll
                     for (int k = 0; k < CPT; ++k) {
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) acc[k][j] = 0.0;
-                        if (!FULL && !cvalid[k]) continue;
-#pragma unroll
                         for (int j = 0; j < VEC; ++j) {
                             const XT xs = in[i][k].e[j];
                             if (MASKED) {
                                 const bool ob = (xs == xs);
                                 const XT xc = ob ? xs : (XT)0;  // select in the storage type, convert once
                                 acc[k][j] = (double)xc * wreg[k][j];
-                                if (COUNT) icnt += ob ? 1 : 0;
+                                if (COUNT) icnt += (ob && (FULL || cvalid[k])) ? 1 : 0;
                             } else {
                                 acc[k][j] = (double)xs * wreg[k][j];
                             }
