@@ -521,7 +521,10 @@ __device__ __forceinline__ int als_sweeps(const Rank1Task& T, double* const fb, 
     return sweeps;
 }
 
-__device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int normalize_on_break, double* ws) {
+// wkron_alt: a second destination for kron(w) (the resident loop's shared-memory copy); publish = false keeps the
+// task's outputs out of global memory (every CTA of the resident loop runs the task, one of them publishes).
+__device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int normalize_on_break, double* ws,
+                                           double* wkron_alt = nullptr, bool publish = true) {
     __shared__ double red[(kMaxZModes + 1) * 4 * NWARP];
     __shared__ int ired[(kMaxZModes + 1) * 2 * NWARP];
     __shared__ double mode_out[2 * kMaxZModes];  // per mode: ||f||^2 of the start, sigma
@@ -555,10 +558,13 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
         const double normz = sqrt(bsum(s, cta));
         for (int i = threadIdx.x; i < T.pitch; i += NTH) {
             const double w = i < p ? zs[i] / normz : 0.0;
-            if (i < p) T.w[0][i] = w;
-            T.wkron[i] = w;
+            if (publish) {
+                if (i < p) T.w[0][i] = w;
+                T.wkron[i] = w;
+            }
+            if (wkron_alt != nullptr) wkron_alt[i] = w;
         }
-        if (threadIdx.x == 0 && T.sweeps) *T.sweeps = 0;
+        if (publish && threadIdx.x == 0 && T.sweeps) *T.sweeps = 0;
         return;
     }
 
@@ -729,7 +735,7 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
 
     TPLS_STAMP(4);
     // ---- publish ----
-    {
+    if (publish) {
         int fo = 0;
         for (int m = 0; m < nm; ++m) {
             for (int i = threadIdx.x; i < T.dims[m]; i += NTH) T.w[m][i] = fac[fo + i];
@@ -754,9 +760,10 @@ __device__ __forceinline__ void rank1_task(const Rank1Task& T, double tol, int n
                 }
             }
         }
-        T.wkron[i] = pr;
+        if (publish) T.wkron[i] = pr;
+        if (wkron_alt != nullptr) wkron_alt[i] = pr;
     }
-    if (threadIdx.x == 0 && T.sweeps) *T.sweeps = sweeps;
+    if (publish && threadIdx.x == 0 && T.sweeps) *T.sweeps = sweeps;
     TPLS_STAMP(5);
 }
 
@@ -1279,8 +1286,7 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
     const int n_cached = (int)max(0ll, min((long long)a.cache_rows, r_hi - r_lo));
     size_t y_cache_off = 0;  // tensor l starts cache_rows * (bytes per row of the tensors before it) into the cache; Y is last
     for (int l = 0; l < L; ++l) y_cache_off += (size_t)a.cache_rows * a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
-    int w_total = 0;
-    for (int l = 0; l < L; ++l) w_total += a.x[l].pitch;
+    double* const w_reg = a.w_off != 0 ? reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(dyn) + a.w_off) : nullptr;
     unsigned int bar_gen = 0;
     if (tid < 8) qp_s[tid] = tid < M ? a.q_prev[tid] : 0.0;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bar_gen) : "l"(a.bar) : "memory");  // every thread tracks it
@@ -1371,31 +1377,42 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
         RES_MARK(0);
         grid_sync(a.bar, G, bar_gen);
         RES_MARK(5);
-        // ---- rank-1 step: the first L CTAs, one tensor each (tpls.py:84-90, cmtf.py:98-104) ----
-        if (b < L) {
-            if (SMEM)
-                rank1_task(a.r1[b], a.tol, a.normalize_on_break, dyn);
-            else
-                rank1_task(a.r1[b], a.tol, a.normalize_on_break, a.r1[b].scratch);
+        // ---- rank-1 step (tpls.py:84-90, cmtf.py:98-104): on the first L CTAs, one tensor each, followed by a grid
+        //      barrier -- or, when the launcher found it cheap enough (at most one coupled tensor with a Z of two or
+        //      more modes), on EVERY CTA: each forms the same weights from the same Z, kron(w) lands in its own shared
+        //      memory, and there is no barrier to wait at and no staging round trip (CTA 0 publishes) ----
+        {
+            const bool everywhere = SMEM && a.r1_everywhere != 0;
+            const int l_lo = everywhere ? 0 : min(b, L), l_hi = everywhere ? L : min(b + 1, L);
+            int woff = 0;
+            for (int l = 0; l < l_lo; ++l) woff += a.x[l].pitch;
+            for (int l = l_lo; l < l_hi; ++l) {
+                rank1_task(a.r1[l], a.tol, a.normalize_on_break, SMEM ? dyn : a.r1[l].scratch, everywhere ? w_reg + woff : nullptr,
+                           !everywhere || b == 0);
+                woff += a.x[l].pitch;
+                if (everywhere) __syncthreads();  // the next task reuses the workspace
+            }
+            RES_MARK(1);
+            if (!everywhere) grid_sync(a.bar, G, bar_gen);
+            RES_MARK(6);
         }
-        RES_MARK(1);
-        grid_sync(a.bar, G, bar_gen);
-        RES_MARK(6);
         // ---- projection of this CTA's rows (a warp per row), coupled average, partials of q = Y't ----
         if (trip == 0 && n_cached > 0) mbar_wait(&cache_bar, 0);  // the cached rows have landed
         {
             double qacc = 0.0;  // lane i < pitch_y: response i
             const double* w_s = nullptr;
-            if (w_total <= (int)(kResidentScratch / sizeof(double))) {
-                // kron(w) of all tensors into shared memory: one L2 round trip for the CTA instead of one per warp and slice
-                int woff = 0;
-                for (int l = 0; l < L; ++l) {
-                    const double* wk = a.x[l].wkron;
-                    for (int i = tid; i < a.x[l].pitch; i += NTH) scr[woff + i] = wk[i];
-                    woff += a.x[l].pitch;
+            if (w_reg != nullptr) {
+                if (!(SMEM && a.r1_everywhere != 0)) {
+                    // kron(w) of all tensors into shared memory: one L2 round trip for the CTA instead of one per warp and slice
+                    int woff = 0;
+                    for (int l = 0; l < L; ++l) {
+                        const double* wk = a.x[l].wkron;
+                        for (int i = tid; i < a.x[l].pitch; i += NTH) w_reg[woff + i] = wk[i];
+                        woff += a.x[l].pitch;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
-                w_s = scr;
+                w_s = w_reg;
             }
             FINE_DECL;
             // rows still in L2 first and with whole rows in flight (their loads are the long ones), then the cached rows
@@ -1617,13 +1634,27 @@ cudaError_t launch_resident_loop(const ResidentArgs& a_in, int n_ctas, size_t r1
         const char* v = getenv("TPLS_RESIDENT_CACHE");  // =0: every pass reads its rows from L2 (A/B switch)
         return v == nullptr || *v != '0';
     }();
-    size_t row_bytes = (size_t)a.pitch_y * 8;
-    for (int l = 0; l < a.n_tensors; ++l) row_bytes += (size_t)a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
+    size_t row_bytes = (size_t)a.pitch_y * 8, w_bytes = 0;
+    int n_big = 0;  // coupled tensors whose Z has two or more modes (their rank-1 step is the expensive kind)
+    for (int l = 0; l < a.n_tensors; ++l) {
+        row_bytes += (size_t)a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
+        w_bytes += (size_t)a.x[l].pitch * sizeof(double);
+        n_big += a.r1[l].nmodes >= 2 ? 1 : 0;
+    }
+    // kron(w) of all tensors in shared memory, behind the rank-1 workspace, when it is at most kResidentScratch bytes
+    w_bytes = w_bytes <= kResidentScratch ? ((w_bytes + 127) & ~(size_t)127) : 0;
+    a.w_off = w_bytes ? (unsigned)front : 0u;
+    static const bool everywhere_on = [] {
+        const char* v = getenv("TPLS_RESIDENT_R1_ALL");  // =0: the rank-1 step on the first L CTAs only (A/B switch)
+        return v == nullptr || *v != '0';
+    }();
+    a.r1_everywhere = (everywhere_on && in_smem && w_bytes != 0 && n_big <= 1) ? 1 : 0;
+    const size_t head = front + w_bytes;
     const long long per = (a.n_rows + n_ctas - 1) / n_ctas;
-    const size_t room = dyn_max[in_smem ? 1 : 0] > front ? dyn_max[in_smem ? 1 : 0] - front : 0;
+    const size_t room = dyn_max[in_smem ? 1 : 0] > head ? dyn_max[in_smem ? 1 : 0] - head : 0;
     a.cache_rows = cache_on ? (int)std::min<long long>(per, (long long)(room / row_bytes)) : 0;
-    a.cache_off = (unsigned)front;
-    const size_t smem = front + (size_t)a.cache_rows * row_bytes;
+    a.cache_off = (unsigned)head;
+    const size_t smem = head + (size_t)a.cache_rows * row_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // A cooperative launch: the CTAs spin on each other at the grid barriers, so all of them must be resident at once

@@ -111,6 +111,8 @@ struct ResidentArgs {
     int normalize_on_break;
     int r1_in_smem;         // rank-1 workspace in dynamic shared memory (else the tasks' global scratch)
     unsigned int* bar;      // grid barrier: [0] generation, [32 * (c + 1)] flag of CTA c; 32 * (CTAs + 1) words, zero-initialised once
+    unsigned w_off;         // set by the launcher: byte offset of the shared-memory copy of kron(w) of all tensors (0: none)
+    int r1_everywhere;      // set by the launcher: every CTA runs the rank-1 step (no barrier after it), CTA 0 publishes
     int cache_rows;         // set by the launcher: rows of every CTA's block (X of all tensors and Y) that are copied into
     unsigned cache_off;     //   shared memory once per launch, and the byte offset of that cache in dynamic shared memory
     long long* stamps;      // optional diagnostics (TPLS_RESIDENT_STAMPS=1): ns CTA 0 spent per phase, summed over the trips

@@ -40,11 +40,18 @@ def _fit(g, **kw):
     return est
 
 
+@pytest.mark.parametrize("loop", ["resident", "streaming"])
 @pytest.mark.parametrize("case", golden_cases())
-def test_fit_matches_reference_golden(case):
+def test_fit_matches_reference_golden(case, loop, monkeypatch):
+    """Every golden case through both inner loops: the resident trip loop (the default at these sizes) and
+    the streaming kernels under the graph WHILE node (what large and sharded fits run)."""
+    if loop == "streaming":
+        monkeypatch.setenv("TPLS_RESIDENT", "0")
     g = load_golden(case)
     kw = {"max_iter": 4} if "maxiter" in case else {}
     est = _fit(g, **kw)
+    M = 1 if g["Y"].ndim == 1 else g["Y"].shape[1]
+    assert (est.stats_["resident_loops"] > 0) == (loop == "resident" and M <= 8)
     tol = FP32_TOL if "f32" in case else FP64_TOL
     assert est.n_iter_.tolist() == g["trips"].tolist()
     for k, e in aligned_errors(_state(est, bool(g["coupled"])), g).items():
@@ -458,8 +465,10 @@ def test_resident_trip_loop_with_a_partly_cached_block(dtype, nan_frac, monkeypa
     assert np.max(np.abs(a.coef_ - b.coef_)) < tol and np.max(np.abs(a.R2Y - b.R2Y)) < 1e-10
 
 
-@pytest.mark.parametrize("env", [{"TPLS_NO_GRAPH": "1"}, {"TPLS_PDL": "0"}, {"TPLS_NO_GRAPH": "1", "TPLS_PDL": "0"}])
-def test_host_enqueued_and_plain_launch_paths_give_the_same_fit(env, tmp_path):
+@pytest.mark.parametrize("env", [{"TPLS_NO_GRAPH": "1"}, {"TPLS_PDL": "0"}, {"TPLS_NO_GRAPH": "1", "TPLS_PDL": "0"},
+                                 {"TPLS_NO_GRAPH": "1", "TPLS_RESIDENT": "0"}, {"TPLS_PDL": "0", "TPLS_RESIDENT": "0"},
+                                 {"TPLS_NO_GRAPH": "1", "TPLS_PDL": "0", "TPLS_RESIDENT": "0"}])
+def test_host_enqueued_and_plain_launch_paths_give_the_same_fit(env, tmp_path, monkeypatch):
     """The graph-launched fit (default), the host-enqueued trips (profiling / NCCL fallback) and launches without the
     PDL attribute run the same kernels: bit-identical results.  The switches are read once per process, so the
     variants run in a subprocess."""
@@ -468,8 +477,11 @@ def test_host_enqueued_and_plain_launch_paths_give_the_same_fit(env, tmp_path):
     import sys
     from cmtf_pls_b200 import ctPLS
     g = load_golden("ct_90x32x16_90x24_m4_r5")
+    if "TPLS_RESIDENT" in env:      # (read at every fit) the streaming trip body in both processes
+        monkeypatch.setenv("TPLS_RESIDENT", env["TPLS_RESIDENT"])
     est = ctPLS(5)
     est.fit([x.copy() for x in g["Xs"]], g["Y"].copy())
+    assert (est.stats_["resident_loops"] == 0) == ("TPLS_RESIDENT" in env)
     out = str(tmp_path / "variant.npz")
     code = (
         "import sys, numpy as np\n"
