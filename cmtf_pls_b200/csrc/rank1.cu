@@ -1348,18 +1348,23 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
                     const int c = chunk * 32 + lane;   // 32 columns x 16 part-groups
                     double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
                     if (c < X.pitch) {
-                        int pb = warp;
-                        for (; pb + 3 * NWARP < n_parts; pb += 4 * NWARP) {
-                            const double v0 = __ldcg(X.zpart + (size_t)pb * X.pitch + c);
-                            const double v1 = __ldcg(X.zpart + (size_t)(pb + NWARP) * X.pitch + c);
-                            const double v2 = __ldcg(X.zpart + (size_t)(pb + 2 * NWARP) * X.pitch + c);
-                            const double v3 = __ldcg(X.zpart + (size_t)(pb + 3 * NWARP) * X.pitch + c);
-                            t0 += v0;
-                            t1 += v1;
-                            t2 += v2;
-                            t3 += v3;
+                        // a warp's share of the partials (one per CTA: ~10 rows) in ONE round of loads: rows past the end
+                        // are not read and add 0 (three dependent L2 round trips with four loads at a time)
+                        for (int pb = warp; pb < n_parts; pb += 12 * NWARP) {
+                            double v[12];
+#pragma unroll
+                            for (int k = 0; k < 12; ++k) {
+                                const int pk = pb + k * NWARP;
+                                v[k] = pk < n_parts ? __ldcg(X.zpart + (size_t)pk * X.pitch + c) : 0.0;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 12; k += 4) {
+                                t0 += v[k];
+                                t1 += v[k + 1];
+                                t2 += v[k + 2];
+                                t3 += v[k + 3];
+                            }
                         }
-                        for (; pb < n_parts; pb += NWARP) t0 += __ldcg(X.zpart + (size_t)pb * X.pitch + c);
                     }
                     __syncthreads();
                     scr[warp * 33 + lane] = (t0 + t1) + (t2 + t3);
@@ -1463,14 +1468,16 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
             }
             const int col = tid & 7, grp = tid >> 3;  // 8 responses x 64 part-groups (4 per warp)
             double t0 = 0.0, t1 = 0.0;
-            int pb = grp;
-            for (; pb + NTH / 8 < G; pb += 2 * (NTH / 8)) {
-                const double v0 = __ldcg(a.qpart + (size_t)pb * 8 + col);
-                const double v1 = __ldcg(a.qpart + (size_t)(pb + NTH / 8) * 8 + col);
-                t0 += v0;
-                t1 += v1;
+            for (int pb = grp; pb < G; pb += 4 * (NTH / 8)) {  // (one round of loads for up to 256 CTAs)
+                double v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pk = pb + k * (NTH / 8);
+                    v[k] = pk < G ? __ldcg(a.qpart + (size_t)pk * 8 + col) : 0.0;
+                }
+                t0 += v[0] + v[2];
+                t1 += v[1] + v[3];
             }
-            if (pb < G) t0 += __ldcg(a.qpart + (size_t)pb * 8 + col);
             double t = t0 + t1;
             t += shfl_xor_d(t, 8);
             t += shfl_xor_d(t, 16);
