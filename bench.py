@@ -310,6 +310,17 @@ def run_ours(args):
                 dist.destroy_process_group()
             sys.exit(3)
 
+    # ---- the two small BASELINE configurations (one GPU): their inner trips run in the resident trip loop (DESIGN.md
+    #      §3b), one launch per component; device time of a fit (CUDA events inside the library), best of five.  They
+    #      are latency-bound, i.e. proportional to the SM clock: measured here, before the streaming workload has
+    #      pulled the GPU into its power cap (after it they take ~10-20 % longer at ~1.43 GHz) ----
+    small = None
+    if world == 1 and not args.quick:
+        try:
+            small = small_configs(local)
+        except Exception as exc:  # noqa: BLE001
+            small = {"error": str(exc)[:200]}
+
     est = ctPLS(R, device=local, process_group=group)
     for _ in range(args.warmup):
         est.fit(Xs, Y)
@@ -517,14 +528,6 @@ def run_ours(args):
                           "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None}
                       for k, v in prof.items()},
     }
-    # ---- the two small BASELINE configurations (one GPU): their inner trips run in the resident trip loop (DESIGN.md
-    #      §3b), one launch per component; device time of a fit (CUDA events inside the library), best of five ----
-    small = None
-    if world == 1 and not args.quick:
-        try:
-            small = small_configs(local)
-        except Exception as exc:  # noqa: BLE001
-            small = {"error": str(exc)[:200]}
     cpu = None
     if world == 1 and not args.no_cpu:
         Xc, Yc = make_sample_host(CPU_SAMPLE_ROWS)
