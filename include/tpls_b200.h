@@ -142,8 +142,9 @@ typedef struct tpls_stats {
     int64_t xchg_count;
     double xchg_ms;
     double xchg_wait_ms;
-    int64_t resident_loops;     /* components whose inner trips ran in ONE persistent launch (one CTA per SM, grid barriers
-                                   between the phases of a trip): working sets that stay in L2, one GPU, <= 8 responses */
+    int64_t resident_loops;     /* components whose inner trips ran in ONE persistent launch (one CTA per SM, rows cached in
+                                   shared memory, grid barriers between the phases of a trip): working sets of up to 256 MB
+                                   (TPLS_RESIDENT_MB), one GPU, <= 8 responses */
 } tpls_stats;
 int tpls_get_stats(tpls_handle h, tpls_stats* out);
 

@@ -67,3 +67,18 @@ def test_argument_checks_match_reference():
     assert len(p) == 3
     with pytest.raises(IndexError):
         p[3]
+
+
+def test_stats_struct_of_the_binding_matches_the_header():
+    """`tpls_stats` (include/tpls_b200.h) field by field against the ctypes mirror: same names, order and types -- the
+    struct is filled by the library and read through ctypes, so a field added on one side only shifts everything after it."""
+    import ctypes as C
+    import re
+    from cmtf_pls_b200 import _engine
+    src = open(os.path.join(ROOT, "include", "tpls_b200.h")).read()
+    body = re.search(r"typedef struct tpls_stats \{(.*?)\} tpls_stats;", src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"(double|int64_t|int)\s+(\w+)\s*;", body)
+    ctype = {"double": C.c_double, "int64_t": C.c_int64, "int": C.c_int}
+    assert [(n, ctype[t]) for t, n in fields] == list(_engine.Stats._fields_)
+    assert "working sets" in src and "256" in src      # (the header states the resident loop's default size limit)
