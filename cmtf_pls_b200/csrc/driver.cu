@@ -676,7 +676,7 @@ static int layout_fit(tpls_handle h, int L, int R) {
     TRY(dev_alloc(h, (void**)&h->sspart_y, sizeof(double) * h->gy.grid_x * h->gy.n_slabs, tr));
     TRY(dev_alloc(h, (void**)&h->d2part, sizeof(double) * 2048, tr));
     TRY(dev_alloc(h, (void**)&h->dotpart, sizeof(double) * 148 * 64, tr));
-    TRY(dev_alloc(h, (void**)&h->grampart, sizeof(double) * 148 * 64, tr));
+    TRY(dev_alloc(h, (void**)&h->grampart, sizeof(double) * std::max(148, h->sm_count) * 64, tr));
     TRY(dev_alloc(h, (void**)&h->q_prev, sizeof(double) * 8, tr));
     TRY(dev_alloc(h, (void**)&h->qpart, sizeof(double) * 2048 * kMaxFusedResp, tr));
     TRY(dev_alloc(h, (void**)&h->res_bar, sizeof(unsigned int) * 32 * (h->sm_count + 1), tr));  // (the slab is zeroed when it is laid out)
