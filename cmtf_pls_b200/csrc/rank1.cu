@@ -1178,7 +1178,7 @@ __device__ __forceinline__ void resident_contract(const ResidentTensor& X, const
 // Writes the scores, adds the rows' share of q = Y't to qacc (lane i < pitch_y: response i).
 template <int NR, int H>
 __device__ __forceinline__ void resident_project_rows(const ResidentArgs& a, int lo, int hi, long long r_lo, const unsigned char* cache,
-                                                      int n_cached, const double* w_s, const RowSrc<double>& ysrc, int warp, int lane,
+                                                      int nblk, const double* w_s, const RowSrc<double>& ysrc, int warp, int lane,
                                                       double& qacc) {
     const int L = a.n_tensors;
     const double inv_l = 1.0 / (double)L;
@@ -1200,7 +1200,7 @@ __device__ __forceinline__ void resident_project_rows(const ResidentArgs& a, int
             double v[NR];
             if (X.dtype == 0) {
                 const RowSrc<float> src{reinterpret_cast<const float*>(X.x) + (size_t)r_lo * X.pitch,
-                                        reinterpret_cast<const float*>(cache + coff), n_cached, X.pitch};
+                                        reinterpret_cast<const float*>(cache + coff), min(X.cache_rows, nblk), X.pitch};
                 const float* xr[NR];
 #pragma unroll
                 for (int i = 0; i < NR; ++i) xr[i] = src.row(ks[i]);
@@ -1208,10 +1208,10 @@ __device__ __forceinline__ void resident_project_rows(const ResidentArgs& a, int
                     resident_row_dots<float, true, NR, H>(xr, X.pitch, wk, lane, v);
                 else
                     resident_row_dots<float, false, NR, H>(xr, X.pitch, wk, lane, v);
-                coff += (size_t)a.cache_rows * X.pitch * 4;
+                coff += (size_t)X.cache_rows * X.pitch * 4;
             } else {
                 const RowSrc<double> src{reinterpret_cast<const double*>(X.x) + (size_t)r_lo * X.pitch,
-                                         reinterpret_cast<const double*>(cache + coff), n_cached, X.pitch};
+                                         reinterpret_cast<const double*>(cache + coff), min(X.cache_rows, nblk), X.pitch};
                 const double* xr[NR];
 #pragma unroll
                 for (int i = 0; i < NR; ++i) xr[i] = src.row(ks[i]);
@@ -1219,7 +1219,7 @@ __device__ __forceinline__ void resident_project_rows(const ResidentArgs& a, int
                     resident_row_dots<double, true, NR, H>(xr, X.pitch, wk, lane, v);
                 else
                     resident_row_dots<double, false, NR, H>(xr, X.pitch, wk, lane, v);
-                coff += (size_t)a.cache_rows * X.pitch * 8;
+                coff += (size_t)X.cache_rows * X.pitch * 8;
             }
             woff += X.pitch;
             if (X.masked) {
@@ -1281,11 +1281,18 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
     const long long per = (a.n_rows + G - 1) / G;
     const long long r_lo = min(a.n_rows, (long long)b * per), r_hi = min(a.n_rows, r_lo + per);
     double* scr = dyn;  // phases other than the rank-1 step: <= kResidentScratch bytes
-    // rows [r_lo, r_lo + n_cached) of every tensor and of Y live in shared memory from the first projection on
+    // The first rows of the block live in shared memory from the first projection on: x[l].cache_rows of tensor l,
+    // y_cache_rows of Y (the launcher gives narrow tensors and Y all their rows first; the widest tensor gets what is
+    // left), tensor after tensor, Y last.  n_cached = the rows that EVERY tensor has in shared memory.
     unsigned char* const cache = reinterpret_cast<unsigned char*>(dyn) + a.cache_off;
-    const int n_cached = (int)max(0ll, min((long long)a.cache_rows, r_hi - r_lo));
-    size_t y_cache_off = 0;  // tensor l starts cache_rows * (bytes per row of the tensors before it) into the cache; Y is last
-    for (int l = 0; l < L; ++l) y_cache_off += (size_t)a.cache_rows * a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
+    const int nblk = (int)(r_hi - r_lo);  // rows of this CTA's block
+    const int n_cached = max(0, min(a.cache_rows, nblk));
+    size_t y_cache_off = 0;
+    bool any_cached = nblk > 0 && a.y_cache_rows > 0;
+    for (int l = 0; l < L; ++l) {
+        y_cache_off += (size_t)a.x[l].cache_rows * a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
+        any_cached = any_cached || (nblk > 0 && a.x[l].cache_rows > 0);
+    }
     double* const w_reg = a.w_off != 0 ? reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(dyn) + a.w_off) : nullptr;
     unsigned int bar_gen = 0;
     if (tid < 8) qp_s[tid] = tid < M ? a.q_prev[tid] : 0.0;
@@ -1296,22 +1303,23 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0 && n_cached > 0) {
+    if (tid == 0 && any_cached) {
         // one thread hands the copies to the bulk-copy engine; they land while the first fold and rank-1 step run
-        unsigned int total = (unsigned int)n_cached * (unsigned int)(a.pitch_y * 8);
-        for (int l = 0; l < L; ++l) total += (unsigned int)n_cached * (unsigned int)(a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8));
+        unsigned int total = (unsigned int)min(a.y_cache_rows, nblk) * (unsigned int)(a.pitch_y * 8);
+        for (int l = 0; l < L; ++l)
+            total += (unsigned int)min(a.x[l].cache_rows, nblk) * (unsigned int)(a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8));
         mbar_arrive_expect_tx(&cache_bar, total);
         size_t off = 0;
         for (int l = 0; l <= L; ++l) {
             const size_t row_b = l < L ? (size_t)a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8) : (size_t)a.pitch_y * 8;
+            const int rows_l = l < L ? a.x[l].cache_rows : a.y_cache_rows;
             const unsigned char* g = reinterpret_cast<const unsigned char*>(l < L ? a.x[l].x : (const void*)a.y) + (size_t)r_lo * row_b;
-            const size_t bytes = (size_t)n_cached * row_b;
+            const size_t bytes = (size_t)min(rows_l, nblk) * row_b;
             for (size_t o = 0; o < bytes; o += 32768)
                 bulk_g2s(cache + off + o, g + o, (uint32_t)min((size_t)32768, bytes - o), &cache_bar);
-            off += (size_t)a.cache_rows * row_b;
+            off += (size_t)rows_l * row_b;
         }
     }
-    const int nblk = (int)(r_hi - r_lo);  // rows of this CTA's block
     {
         // this CTA's share of Y'Y (the stop test needs dq^T Y'Y dq): entry e = (i, j) on NTH / m^2 row lanes, the lanes
         // folded in order; every CTA folds the partials of all CTAs before the first stop test
@@ -1332,7 +1340,8 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
         }
         __syncthreads();
     }
-    const RowSrc<double> ysrc{a.y + (size_t)r_lo * a.pitch_y, reinterpret_cast<const double*>(cache + y_cache_off), n_cached, a.pitch_y};
+    const RowSrc<double> ysrc{a.y + (size_t)r_lo * a.pitch_y, reinterpret_cast<const double*>(cache + y_cache_off), min(a.y_cache_rows, nblk),
+                              a.pitch_y};
     int trip = 0;
     double d2_last = 0.0;
     int done_trip = -1;
@@ -1402,7 +1411,7 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
             RES_MARK(6);
         }
         // ---- projection of this CTA's rows (a warp per row), coupled average, partials of q = Y't ----
-        if (trip == 0 && n_cached > 0) mbar_wait(&cache_bar, 0);  // the cached rows have landed
+        if (trip == 0 && any_cached) mbar_wait(&cache_bar, 0);  // the cached rows have landed
         {
             double qacc = 0.0;  // lane i < pitch_y: response i
             const double* w_s = nullptr;
@@ -1421,9 +1430,9 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
             }
             FINE_DECL;
             // rows still in L2 first and with whole rows in flight (their loads are the long ones), then the cached rows
-            resident_project_rows<2, 8>(a, n_cached, nblk, r_lo, cache, n_cached, w_s, ysrc, warp, lane, qacc);
+            resident_project_rows<2, 8>(a, n_cached, nblk, r_lo, cache, nblk, w_s, ysrc, warp, lane, qacc);
             FINE(0);
-            resident_project_rows<4, 2>(a, 0, n_cached, r_lo, cache, n_cached, w_s, ysrc, warp, lane, qacc);
+            resident_project_rows<4, 2>(a, 0, n_cached, r_lo, cache, nblk, w_s, ysrc, warp, lane, qacc);
             FINE(1);
             if (lane < 8) qw_s[warp][lane] = lane < a.pitch_y ? qacc : 0.0;
             __syncthreads();
@@ -1529,14 +1538,14 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
                 double* zrow = X.zpart + (size_t)b * X.pitch;
                 if (X.dtype == 0) {
                     const RowSrc<float> src{reinterpret_cast<const float*>(X.x) + (size_t)r_lo * X.pitch,
-                                            reinterpret_cast<const float*>(cache + coff), n_cached, X.pitch};
+                                            reinterpret_cast<const float*>(cache + coff), min(X.cache_rows, nblk), X.pitch};
                     resident_contract<float>(X, src, ysrc, M, q_s, nblk, u_s, u_lo, zrow, scr);
-                    coff += (size_t)a.cache_rows * X.pitch * 4;
+                    coff += (size_t)X.cache_rows * X.pitch * 4;
                 } else {
                     const RowSrc<double> src{reinterpret_cast<const double*>(X.x) + (size_t)r_lo * X.pitch,
-                                             reinterpret_cast<const double*>(cache + coff), n_cached, X.pitch};
+                                             reinterpret_cast<const double*>(cache + coff), min(X.cache_rows, nblk), X.pitch};
                     resident_contract<double>(X, src, ysrc, M, q_s, nblk, u_s, u_lo, zrow, scr);
-                    coff += (size_t)a.cache_rows * X.pitch * 8;
+                    coff += (size_t)X.cache_rows * X.pitch * 8;
                 }
             }
         }
@@ -1641,10 +1650,9 @@ cudaError_t launch_resident_loop(const ResidentArgs& a_in, int n_ctas, size_t r1
         const char* v = getenv("TPLS_RESIDENT_CACHE");  // =0: every pass reads its rows from L2 (A/B switch)
         return v == nullptr || *v != '0';
     }();
-    size_t row_bytes = (size_t)a.pitch_y * 8, w_bytes = 0;
+    size_t w_bytes = 0;
     int n_big = 0;  // coupled tensors whose Z has two or more modes (their rank-1 step is the expensive kind)
     for (int l = 0; l < a.n_tensors; ++l) {
-        row_bytes += (size_t)a.x[l].pitch * (a.x[l].dtype == 0 ? 4 : 8);
         w_bytes += (size_t)a.x[l].pitch * sizeof(double);
         n_big += a.r1[l].nmodes >= 2 ? 1 : 0;
     }
@@ -1659,9 +1667,29 @@ cudaError_t launch_resident_loop(const ResidentArgs& a_in, int n_ctas, size_t r1
     const size_t head = front + w_bytes;
     const long long per = (a.n_rows + n_ctas - 1) / n_ctas;
     const size_t room = dyn_max[in_smem ? 1 : 0] > head ? dyn_max[in_smem ? 1 : 0] - head : 0;
-    a.cache_rows = cache_on ? (int)std::min<long long>(per, (long long)(room / row_bytes)) : 0;
+    // Who gets the room: Y and the narrow tensors all rows of the block first (a few KB buy a whole L2 round trip per
+    // pass: their rows past the cached ones would be fetched behind the wide tensor's), the widest tensor what is left.
+    size_t left = cache_on ? room : 0;
+    a.y_cache_rows = (int)std::min<long long>(per, (long long)(left / ((size_t)a.pitch_y * 8)));
+    left -= (size_t)a.y_cache_rows * a.pitch_y * 8;
+    int order[kMaxTensors];
+    for (int l = 0; l < a.n_tensors; ++l) order[l] = l;
+    std::sort(order, order + a.n_tensors, [&](int p, int q) {
+        const size_t bp = (size_t)a.x[p].pitch * (a.x[p].dtype == 0 ? 4 : 8), bq = (size_t)a.x[q].pitch * (a.x[q].dtype == 0 ? 4 : 8);
+        return bp != bq ? bp < bq : p < q;
+    });
+    a.cache_rows = (int)per;  // rows that every tensor has in shared memory
+    size_t cached_bytes = (size_t)a.y_cache_rows * a.pitch_y * 8;
+    for (int i = 0; i < a.n_tensors; ++i) {
+        ResidentTensor& X = a.x[order[i]];
+        const size_t rb = (size_t)X.pitch * (X.dtype == 0 ? 4 : 8);
+        X.cache_rows = (int)std::min<long long>(per, (long long)(left / rb));
+        left -= (size_t)X.cache_rows * rb;
+        cached_bytes += (size_t)X.cache_rows * rb;
+        a.cache_rows = std::min(a.cache_rows, X.cache_rows);
+    }
     a.cache_off = (unsigned)head;
-    const size_t smem = head + (size_t)a.cache_rows * row_bytes;
+    const size_t smem = head + cached_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // A cooperative launch: the CTAs spin on each other at the grid barriers, so all of them must be resident at once

@@ -88,6 +88,7 @@ struct ResidentTensor {
     int parts0;             // rows of zpart that hold trip 0's partials (written by the fused centring/deflation pass)
     double* z;              // folded Z [pitch] (what the rank-1 task reads)
     const double* wkron;    // kron of this component's weight vectors [pitch] (what the rank-1 task writes)
+    int cache_rows;         // set by the launcher: rows of every CTA's block of this tensor that are copied into shared memory
 };
 
 struct ResidentArgs {
@@ -113,8 +114,9 @@ struct ResidentArgs {
     unsigned int* bar;      // grid barrier: [0] generation, [32 * (c + 1)] flag of CTA c; 32 * (CTAs + 1) words, zero-initialised once
     unsigned w_off;         // set by the launcher: byte offset of the shared-memory copy of kron(w) of all tensors (0: none)
     int r1_everywhere;      // set by the launcher: every CTA runs the rank-1 step (no barrier after it), CTA 0 publishes
-    int cache_rows;         // set by the launcher: rows of every CTA's block (X of all tensors and Y) that are copied into
-    unsigned cache_off;     //   shared memory once per launch, and the byte offset of that cache in dynamic shared memory
+    int cache_rows;         // set by the launcher: rows of every CTA's block that EVERY tensor has in shared memory,
+    int y_cache_rows;       //   the rows of Y there, and the byte offset of that cache in dynamic shared memory (the copies
+    unsigned cache_off;     //   are made once per launch)
     long long* stamps;      // optional diagnostics (TPLS_RESIDENT_STAMPS=1): ns CTA 0 spent per phase, summed over the trips
                             //   [0] fold [1] rank-1 [2] projection [3] q / stop [4] contraction [5..8] the four barriers [9] trips
 };
