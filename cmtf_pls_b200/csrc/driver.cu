@@ -673,7 +673,7 @@ static int layout_fit(tpls_handle h, int L, int R) {
     TRY(dev_alloc(h, (void**)&h->ymean_d, sizeof(double) * h->pitch_y, tr));
     TRY(dev_alloc(h, (void**)&h->zpart_y, sizeof(double) * h->gy.grid_x * h->pitch_y, tr));
     TRY(dev_alloc(h, (void**)&h->cntpart_y, sizeof(double) * h->gy.grid_x * h->pitch_y, tr));
-    TRY(dev_alloc(h, (void**)&h->sspart_y, sizeof(double) * h->gy.grid_x * h->gy.n_slabs, tr));
+    TRY(dev_alloc(h, (void**)&h->sspart_y, sizeof(double) * std::max(h->gy.grid_x * h->gy.n_slabs, h->sm_count), tr));
     TRY(dev_alloc(h, (void**)&h->d2part, sizeof(double) * 2048, tr));
     TRY(dev_alloc(h, (void**)&h->dotpart, sizeof(double) * 148 * 64, tr));
     TRY(dev_alloc(h, (void**)&h->grampart, sizeof(double) * std::max(148, h->sm_count) * 64, tr));
@@ -1212,6 +1212,8 @@ static int resident_ctas(tpls_handle h, const StreamPlan& P) {
     return (int)std::max<long long>(P.L, std::min<long long>(h->sm_count, want));
 }
 
+static bool resident_tail_on() { return tune_env("TPLS_RESIDENT_TAIL", 1) != 0; }
+
 static int run_resident(tpls_handle h, const StreamPlan& P, int a, int n_ctas) {
     ResidentArgs ra{};
     ra.n_tensors = P.L;
@@ -1227,6 +1229,19 @@ static int run_resident(tpls_handle h, const StreamPlan& P, int a, int n_ctas) {
     ra.gram = h->arena + h->off_gram_y;
     ra.grampart = h->grampart;
     ra.u_out = h->U + (size_t)a * h->n;
+    // the regression / Y-deflation tail of the component in the same launch (TPLS_RESIDENT_TAIL=0: the host launches it)
+    ra.tail = resident_tail_on() ? 1 : 0;
+    ra.comp = a;
+    ra.n_comp = P.R;
+    ra.T = h->T;
+    ra.row_w = h->row_w;
+    ra.y_rw = h->y_work;
+    ra.dotpart = h->dotpart;
+    ra.gram_t = h->gram;
+    ra.coef = h->coef;
+    ra.trips_out = h->trips_dev;
+    ra.conv_out = h->conv_dev;
+    ra.sspart_y = h->sspart_y;
     ra.ctrl = h->ctrl;
     ra.tol = P.tol;
     ra.max_iter = P.max_iter;
@@ -1377,7 +1392,7 @@ static int fit_streaming(tpls_handle h, const StreamPlan& P) {
             }
             ss.add(t.sspart, t.g.grid_x * t.g.n_slabs, 1, 1, t.off_ss + a - h->off_ss);
         }
-        if (a > 0) ss.add(h->sspart_y, h->gy.grid_x * h->gy.n_slabs, 1, 1, (size_t)(P.ss_y + a - A) - h->off_ss);
+        if (a > 0) ss.add(h->sspart_y, h->sspart_y_n, 1, 1, (size_t)(P.ss_y + a - A) - h->off_ss);
         TRY(fold_sum(h, ss, h->off_ss, h->ss_len, nullptr, true));
         if (a == R) break;
 
@@ -1405,7 +1420,12 @@ static int fit_streaming(tpls_handle h, const StreamPlan& P) {
             r.div = 1.0;
             TRY(row_pass(h, TPLS_F64, 0, r, TPLS_K_YSIDE));
         }
-        TRY(component_tail(h, R, a, P.ss_y, true));
+        if (resident && resident_tail_on()) {
+            h->sspart_y_n = resident_ctas(h, P);  // the resident loop ran the tail: one partial of ||Y||^2 per CTA
+        } else {
+            TRY(component_tail(h, R, a, P.ss_y, true));
+            h->sspart_y_n = h->gy.grid_x * h->gy.n_slabs;
+        }
         if (!P.fused && a + 1 < R) {
             ProfScope ps_small(h, TPLS_K_OTHER, 0.0);
             CK(launch_gather_col(h->y_work, n, h->pitch_y, 0, h->U + (size_t)(a + 1) * n, st));
@@ -1431,7 +1451,8 @@ static unsigned long long graph_key_of(tpls_handle h, int L, int R, double tol, 
     const bool pdl = pdl_enabled();
     KEY(pdl);
     const int res_switch = tune_env("TPLS_RESIDENT", -1), res_mb = tune_env("TPLS_RESIDENT_MB", 256);  // resident_ctas()
-    KEY(res_switch); KEY(res_mb);
+    const int res_tail = tune_env("TPLS_RESIDENT_TAIL", 1);
+    KEY(res_switch); KEY(res_mb); KEY(res_tail);
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
         KEY(t.src); KEY(t.work); KEY(t.dtype); KEY(t.ndim); KEY(t.masked);

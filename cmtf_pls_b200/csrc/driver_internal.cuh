@@ -97,6 +97,7 @@ struct tpls_ctx {
     double *T = nullptr, *U = nullptr, *Q = nullptr, *coef = nullptr, *gram = nullptr;
     double *arena = nullptr, *qvec = nullptr, *svec = nullptr, *ymean_d = nullptr;
     double *zpart_y = nullptr, *cntpart_y = nullptr, *sspart_y = nullptr, *d2part = nullptr, *dotpart = nullptr;
+    int sspart_y_n = 0;  // partials of ||Y||^2 the last Y deflation left in sspart_y (its pass's grid, or the resident loop's CTAs)
     double* scratch_ss = nullptr;
     int* trips_dev = nullptr;
     int* ymiss_flag = nullptr;

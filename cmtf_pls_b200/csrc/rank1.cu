@@ -1564,6 +1564,142 @@ __global__ void __launch_bounds__(kRank1Threads, 1) resident_loop_kernel(const _
             if (q < M) ui = fma(yr[q], q_s[q], ui);
         a.u_out[r_lo + k] = ui;
     }
+    // ---- the tail of the component (tpls.py:110-113), as solve_coef / lincomb / the Y deflation pass do it ----
+    if (a.tail) {
+        const int ka = a.comp + 1, npairs = 2 * ka, R = a.n_comp;
+        __syncthreads();  // u of this CTA's rows is in global memory
+        // partial dot products over the block: pair j < ka is T_j . T_a, pair ka + j is T_j . u (weighted rows)
+        for (int j = warp; j < npairs; j += NWARP) {
+            const double* pa = a.T + (size_t)(j < ka ? j : j - ka) * a.n_rows + r_lo;
+            const double* pb = (j < ka ? a.t_out : a.u_out) + r_lo;
+            double sacc = 0.0;
+            for (int k = lane; k < nblk; k += 32) {
+                double av = pa[k];
+                if (a.row_w != nullptr) av *= a.row_w[r_lo + k];
+                sacc = fma(av, pb[k], sacc);
+            }
+            sacc = warp_sum(sacc);
+            if (lane == 0) a.dotpart[(size_t)b * 64 + j] = sacc;
+        }
+        grid_sync(a.bar, G, bar_gen);
+        // every CTA: fold the partials (64 pairs x 8 part-groups), the Gram block of the scores so far into shared memory
+        double* Gs = scr;            // [ka][ka]
+        double* Lm = scr + 1024;     // [ka][ka] Cholesky factor
+        double* dots_s = u_s + 512;  // [npairs]; then y, x, 1/||t||, dropped flags
+        double* ys = u_s + 576;
+        double* xs = u_s + 640;
+        double* dinv = u_s + 704;
+        double* drop = u_s + 768;
+        {
+            const int e = tid & 63, grp8 = tid >> 6;
+            double g0 = 0.0, g1 = 0.0;
+            if (e < npairs) {
+                int pb = grp8;
+                for (; pb + 8 < G; pb += 16) {
+                    const double v0 = __ldcg(a.dotpart + (size_t)pb * 64 + e);
+                    const double v1 = __ldcg(a.dotpart + (size_t)(pb + 8) * 64 + e);
+                    g0 += v0;
+                    g1 += v1;
+                }
+                if (pb < G) g0 += __ldcg(a.dotpart + (size_t)pb * 64 + e);
+            }
+            u_s[grp8 * 64 + e] = g0 + g1;
+            for (int i = tid; i < ka * ka; i += NTH) {
+                const int r = i / ka, c = i - r * ka;
+                Gs[i] = (r == a.comp || c == a.comp) ? 0.0 : a.gram_t[r * R + c];
+            }
+            __syncthreads();
+            if (tid < npairs) {
+                double t = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t += u_s[k * 64 + tid];
+                dots_s[tid] = t;
+            }
+            __syncthreads();
+            if (tid < ka) {
+                Gs[tid * ka + a.comp] = dots_s[tid];
+                Gs[a.comp * ka + tid] = dots_s[tid];
+                if (b == 0) {
+                    a.gram_t[tid * R + a.comp] = dots_s[tid];
+                    a.gram_t[a.comp * R + tid] = dots_s[tid];
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            // normal equations on unit-norm score columns; a column that is zero or dependent on the earlier ones gets
+            // the coefficient 0, like the reference's lstsq (small.cu: solve_coef_kernel, same arithmetic)
+            for (int i = 0; i < ka; ++i) {
+                const double g = Gs[i * ka + i];
+                drop[i] = !(g > 0.0) ? 1.0 : 0.0;
+                dinv[i] = drop[i] != 0.0 ? 0.0 : 1.0 / sqrt(g);
+            }
+            for (int i = 0; i < ka; ++i) {
+                for (int j = 0; j <= i; ++j) {
+                    double sv = (drop[i] != 0.0 || drop[j] != 0.0) ? (i == j ? 1.0 : 0.0) : Gs[i * ka + j] * dinv[i] * dinv[j];
+                    for (int q = 0; q < j; ++q) sv -= Lm[i * ka + q] * Lm[j * ka + q];
+                    if (i == j) {
+                        if (!(sv > 1e-14)) {  // no independent part left in column i
+                            drop[i] = 1.0;
+                            for (int q = 0; q < i; ++q) Lm[i * ka + q] = 0.0;
+                            sv = 1.0;
+                        }
+                        Lm[i * ka + i] = sqrt(sv);
+                    } else {
+                        Lm[i * ka + j] = sv / Lm[j * ka + j];
+                    }
+                }
+            }
+            for (int i = 0; i < ka; ++i) {
+                double sv = drop[i] != 0.0 ? 0.0 : dots_s[ka + i] * dinv[i];
+                for (int q = 0; q < i; ++q) sv -= Lm[i * ka + q] * ys[q];
+                ys[i] = sv / Lm[i * ka + i];
+            }
+            for (int i = ka - 1; i >= 0; --i) {
+                double sv = ys[i];
+                for (int q = i + 1; q < ka; ++q) sv -= Lm[q * ka + i] * xs[q];
+                xs[i] = drop[i] != 0.0 ? 0.0 : sv / Lm[i * ka + i];
+            }
+            for (int i = 0; i < ka; ++i) xs[i] *= dinv[i];  // the coefficients of this component
+            if (b == 0) {
+                for (int i = 0; i < ka; ++i) a.coef[i * R + a.comp] = xs[i];
+                a.trips_out[a.comp] = trip;
+                a.conv_out[a.comp] = done_trip >= 0 ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        // Y deflation of this CTA's rows (tpls.py:113) and their share of the residual norm of Y
+        double ssy = 0.0;
+        for (int k = tid; k < nblk; k += NTH) {
+            const long long r = r_lo + k;
+            double sv = 0.0;
+            for (int bb = 0; bb < ka; ++bb) sv = fma(a.T[(size_t)bb * a.n_rows + r], xs[bb], sv);
+            double sw = 1.0;
+            if (a.row_w != nullptr) {
+                sw = a.row_w[r];
+                sv *= sw;
+            }
+            double* yr = a.y_rw + (size_t)r * a.pitch_y;
+            double rs = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < M) {
+                    const double yv = fma(-sv, q_s[c], yr[c]);
+                    yr[c] = yv;
+                    rs = fma(yv, yv, rs);
+                }
+            ssy = fma(sw, rs, ssy);
+        }
+        ssy = warp_sum(ssy);
+        if (lane == 0) qw_s[warp][0] = ssy;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) t += qw_s[w][0];
+            a.sspart_y[b] = t;
+        }
+    }
     if (b == 0) {
         if (tid < a.pitch_y) a.qvec[tid] = tid < M ? q_s[tid] : 0.0;
         if (tid < M) {

@@ -112,6 +112,19 @@ struct ResidentArgs {
     int normalize_on_break;
     int r1_in_smem;         // rank-1 workspace in dynamic shared memory (else the tasks' global scratch)
     unsigned int* bar;      // grid barrier: [0] generation, [32 * (c + 1)] flag of CTA c; 32 * (CTAs + 1) words, zero-initialised once
+    // ---- the tail of the component in the same launch (tpls.py:110-113): regression of u on the scores so far, Y
+    //      deflation, residual norm of Y; off when tail == 0 (the host then launches the five kernels that do it) ----
+    int tail;
+    int comp, n_comp;       // index of this component, components of the fit (<= 32)
+    const double* T;        // scores so far [n_comp][n_rows] (row comp = t_out)
+    const double* row_w;    // optional 0/1 sample weights [n_rows] (cross-validation folds), else nullptr
+    double* y_rw;           // = y: deflated in place, y -= (T coef_a) q^T
+    double* dotpart;        // [CTAs][64] per-CTA partials of T_b . T_a and T_b . u
+    double* gram_t;         // T'T [n_comp][n_comp]: row and column comp are filled here
+    double* coef;           // [n_comp][n_comp]: column comp out
+    int* trips_out;         // [n_comp]: entry comp out
+    int* conv_out;          // [n_comp]: entry comp out (1 = met the stop test)
+    double* sspart_y;       // [CTAs] out: per-CTA residual norm of the deflated Y (weighted)
     unsigned w_off;         // set by the launcher: byte offset of the shared-memory copy of kron(w) of all tensors (0: none)
     int r1_everywhere;      // set by the launcher: every CTA runs the rank-1 step (no barrier after it), CTA 0 publishes
     int cache_rows;         // set by the launcher: rows of every CTA's block that EVERY tensor has in shared memory,
