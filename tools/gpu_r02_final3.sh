@@ -1,6 +1,6 @@
 #!/bin/bash
 # session-3: the judged bench line on the final code (small configurations measured first)
-O=gpurun_out/r02final3; mkdir -p $O
+O=gpurun_out/r02final5; mkdir -p $O
 timeout 900 python bench.py > $O/bench1.json 2> $O/bench1.err; echo "bench rc=$?"
 python - <<P
 import json
