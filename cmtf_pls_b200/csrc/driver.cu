@@ -1194,7 +1194,8 @@ static int trip_body(tpls_handle h, const StreamPlan& P, int a, unsigned long lo
 // Can the inner trips of a component run in the resident loop kernel (rank1.cuh)?  One GPU, the Y side fused, rows
 // narrow enough for its thread layout, and a working set of at most TPLS_RESIDENT_MB (default 256: measured on one
 // B200, tools/resident_sweep.py -- 20 MB 39 vs 51 us per trip, 82 MB 51 vs 71, 164 MB 97 vs 110, 328 MB 168 vs 173; the
-// streaming kernels win beyond that).  TPLS_RESIDENT=0 turns it off, =1 forces it whatever the size.  Profiled fits
+// streaming kernels win beyond that) of which at most ~256 rows per CTA stay outside shared memory.  TPLS_RESIDENT=0 turns
+// it off, =1 forces it whatever the size.  Profiled fits
 // keep the streaming kernels (their per-class timing is what the profile is for) unless forced.
 static int resident_ctas(tpls_handle h, const StreamPlan& P) {
     const int force = tune_env("TPLS_RESIDENT", -1);
@@ -1209,7 +1210,19 @@ static int resident_ctas(tpls_handle h, const StreamPlan& P) {
     if (force != 1 && bytes > 1048576.0 * tune_env("TPLS_RESIDENT_MB", 256)) return 0;
     if (P.r1_use_smem && P.r1_smem > 200 * 1024) return 0;
     const long long want = (h->n + 15) / 16;  // at least 16 samples per CTA
-    return (int)std::max<long long>(P.L, std::min<long long>(h->sm_count, want));
+    const int n_ctas = (int)std::max<long long>(P.L, std::min<long long>(h->sm_count, want));
+    if (force != 1) {
+        // Rows of a CTA's block that do not fit in shared memory are fetched from L2 / HBM by a warp per row, a few rows
+        // at a time: fine for a few hundred of them, slow for thousands of narrow rows (the streaming kernels move those
+        // at the HBM rate).  An estimate of the launcher's split is enough here.
+        const long long per = (h->n + n_ctas - 1) / n_ctas;
+        double row_bytes = (double)h->pitch_y * 8.0;
+        for (int l = 0; l < P.L; ++l) row_bytes += (double)h->x[l].pitch * h->x[l].elem;
+        const double room = 190.0 * 1024.0 - (P.r1_use_smem ? std::max(0.0, (double)P.r1_smem - 20.0 * 1024.0) : 0.0);
+        const long long cached = std::min<long long>(per, (long long)(std::max(0.0, room) / row_bytes));
+        if (per - cached > tune_env("TPLS_RESIDENT_UNCACHED_ROWS", 256)) return 0;
+    }
+    return n_ctas;
 }
 
 static bool resident_tail_on() { return tune_env("TPLS_RESIDENT_TAIL", 1) != 0; }
@@ -1451,8 +1464,8 @@ static unsigned long long graph_key_of(tpls_handle h, int L, int R, double tol, 
     const bool pdl = pdl_enabled();
     KEY(pdl);
     const int res_switch = tune_env("TPLS_RESIDENT", -1), res_mb = tune_env("TPLS_RESIDENT_MB", 256);  // resident_ctas()
-    const int res_tail = tune_env("TPLS_RESIDENT_TAIL", 1);
-    KEY(res_switch); KEY(res_mb); KEY(res_tail);
+    const int res_tail = tune_env("TPLS_RESIDENT_TAIL", 1), res_unc = tune_env("TPLS_RESIDENT_UNCACHED_ROWS", 256);
+    KEY(res_switch); KEY(res_mb); KEY(res_tail); KEY(res_unc);
     for (int l = 0; l < L; ++l) {
         Tensor& t = h->x[l];
         KEY(t.src); KEY(t.work); KEY(t.dtype); KEY(t.ndim); KEY(t.masked);

@@ -465,6 +465,29 @@ def test_resident_trip_loop_with_a_partly_cached_block(dtype, nan_frac, monkeypa
     assert np.max(np.abs(a.coef_ - b.coef_)) < tol and np.max(np.abs(a.R2Y - b.R2Y)) < 1e-10
 
 
+def test_tall_narrow_blocks_keep_the_streaming_kernels_and_agree_with_the_forced_resident_loop(monkeypatch):
+    """200k rows of 24 columns: a CTA's block is 1352 rows of which ~870 fit in shared memory -- too many rows left in
+    L2 for a warp per row, so the fit keeps the streaming kernels by default (driver.cu: resident_ctas).  Forced, the
+    resident loop walks its block in two chunks of u = Y q (rank1.cu: kResidentUChunk) and must give the same fit."""
+    from oracle import tpls_oracle as orc
+    from cmtf_pls_b200 import tPLS
+    X, Y, _ = orc.synthetic((200_000, 6, 4), 3, 4, error=0.5, seed=5)
+    fits = {}
+    for mode in (None, "1"):
+        if mode is None:
+            monkeypatch.delenv("TPLS_RESIDENT", raising=False)
+        else:
+            monkeypatch.setenv("TPLS_RESIDENT", mode)
+        est = tPLS(3)
+        est.fit(X.copy(), Y.copy())
+        fits[mode] = est
+        assert est.stats_["resident_loops"] == (0 if mode is None else 3)
+    a, b = fits["1"], fits[None]
+    assert a.n_iter_.tolist() == b.n_iter_.tolist()
+    assert np.max(np.abs(a.X_factors[0] - b.X_factors[0])) < 1e-10 * max(1.0, np.max(np.abs(b.X_factors[0])))
+    assert np.max(np.abs(a.coef_ - b.coef_)) < 1e-10 and np.max(np.abs(a.R2Y - b.R2Y)) < 1e-10
+
+
 @pytest.mark.parametrize("env", [{"TPLS_NO_GRAPH": "1"}, {"TPLS_PDL": "0"}, {"TPLS_NO_GRAPH": "1", "TPLS_PDL": "0"},
                                  {"TPLS_NO_GRAPH": "1", "TPLS_RESIDENT": "0"}, {"TPLS_PDL": "0", "TPLS_RESIDENT": "0"},
                                  {"TPLS_NO_GRAPH": "1", "TPLS_PDL": "0", "TPLS_RESIDENT": "0"}])
