@@ -11,12 +11,16 @@
 // trace-normalised matrix, A <- A*A / tr(A*A).  tr(A*A) -> 1 exactly when A is
 // rank one, so "1 - trace < 1e-7" means the iterate just formed has a
 // second-to-first eigenvalue ratio below ~1e-14: logarithmic in the spectral
-// gap, one tiny reduction per step, then two polish steps against the original
-// Gram matrix.  Everything is fp64.  Matrices are stored with their order rounded
-// up to 4 (zero pads, so the 4x4 register tiles need no bounds checks and load 16
-// bytes at a time) and a leading dimension of that + 2, so that consecutive rows
-// start 16 bytes apart modulo 128: the lanes that split a contraction index
-// between them read conflict-free.
+// gap, one tiny reduction per step, then a polish step against the original
+// Gram matrix.  Everything is fp64.  Gram matrices and squarings run on the fp64
+// tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA): matrices are stored with
+// their order rounded up to 8 (zero pads) and a leading dimension of that + 4, so
+// that every fragment load of a half-warp is conflict-free.
+//
+// The same file holds the two kernels that keep a whole inner loop on the device:
+// cov_loop_kernel (covariance mode, one CTA per coupled tensor in a cluster) and
+// resident_loop_kernel (all trips of a component in one cooperative launch, one
+// CTA per SM, rows cached in shared memory -- rank1.cuh).
 #include "rank1.cuh"
 
 #include <cooperative_groups.h>
